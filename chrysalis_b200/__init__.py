@@ -1,0 +1,10 @@
+"""chrysalis_b200 - the detect_svgs -> pca -> aa hot path of rockdeme/chrysalis on B200 (sm_100a).
+
+Re-exports mirror ``/root/reference/chrysalis/__init__.py:10-12`` for the path this package
+replaces; everything else of the reference (plots, utils) is out of scope.
+"""
+from .core import detect_svgs
+from .anndata_lite import AnnDataLite
+
+__all__ = ["detect_svgs", "AnnDataLite"]
+__version__ = "0.1.0"

@@ -1,0 +1,114 @@
+"""Drop-in ``detect_svgs`` / ``pca`` / ``aa`` on B200.
+
+Same signatures, same AnnData fields and same error behaviour as
+``/root/reference/chrysalis/core.py`` (``detect_svgs`` :12-92, ``pca`` :95-137, ``aa`` :140-208);
+the numeric bodies (scanpy / libpysal / esda / sklearn / archetypes calls) are replaced by
+hand-written sm_100a kernels reached through the C ABI (``include/chrysalis_b200.h``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import device as dv
+
+
+def _make_unique(names) -> pd.Index:
+    """``AnnData.var_names_make_unique()`` (core.py:54): 2nd+ duplicates get '-1', '-2', ..."""
+    names = pd.Index(names)
+    if names.is_unique:
+        return names
+    out = np.array(names, dtype=object)
+    seen = set(out)
+    counter = {}
+    dup = names.duplicated(keep="first")
+    for i in np.flatnonzero(dup):
+        base = out[i]
+        c = counter.get(base, 0)
+        while True:
+            c += 1
+            cand = f"{base}-{c}"
+            if cand not in seen:
+                break
+        counter[base] = c
+        seen.add(cand)
+        out[i] = cand
+    return pd.Index(out)
+
+
+def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False):
+    """Device part of ``detect_svgs``: filter -> normalise/log1p -> kNN W -> Moran's I.
+
+    Returns host arrays ``(keep_mask (G,), I (G',), C (G',) or None)``; also usable directly
+    (bench, multi-GPU driver).  Mirrors core.py:53-76.
+    """
+    n = X.shape[0]
+    csr = dv.upload_csr(X)
+    # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
+    gene_nnz = dv.csr_gene_nnz(csr)
+    keep = gene_nnz >= int(n * min_spots)
+    gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
+                           torch.full_like(gene_nnz, -1))
+    n_keep = int(keep.sum().item())
+    if n_keep == 0:
+        return keep.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
+    # core.py:55-57  normalize_total + log1p on the filtered copy unless the caller already did
+    scale = None
+    if not already_log1p:
+        scale = dv.median_scale(dv.csr_spot_totals(csr, gene_col))
+    # core.py:61-65  kNN weights on (x, -y), row-standardised
+    pts = np.array(spatial, dtype=np.float64, copy=True)
+    pts[:, 1] = pts[:, 1] * -1
+    xy = dv.to_device(pts, torch.float64)
+    bbox = dv.spatial_bbox(xy)
+    order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(n, device=order.device)
+    nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
+    # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
+    dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank, apply_log1p=not already_log1p)
+    # core.py:71-76  the gene loop
+    I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing)
+    return keep.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
+
+
+def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
+                geary: bool = False):
+    """
+    Calculate spatial autocorrelation (Moran's I) to define spatially variable genes.
+
+    Drop-in for ``chrysalis.detect_svgs`` (/root/reference/chrysalis/core.py:12-92).
+
+    :param adata: AnnData (or duck-typed equivalent) of shape ``n_obs`` x ``n_vars``; spatial coordinates in
+        ``.obsm['spatial']``.
+    :param min_spots: only genes expressed in at least this fraction of capture spots are scored.
+    :param top_svg: cutoff for top ranked spatially variable genes.
+    :param min_morans: Moran's I cutoff; only active when it retains fewer genes than ``top_svg``.
+    :param neighbors: number of nearest neighbours used for Moran's I.
+    :param geary: also compute Geary's C into ``.var["Geary's C"]``.
+    :return: None; updates ``.var["Moran's I"]`` and ``.var["spatially_variable"]``.
+    """
+    assert 0 < min_spots < 1
+
+    keep, I, C = svg_stage(adata.X, adata.obsm['spatial'], min_spots, neighbors, geary,
+                           already_log1p="log1p" in adata.uns_keys())
+
+    # names of the filtered copy after var_names_make_unique (core.py:53-54)
+    names = _make_unique(pd.Index(adata.var_names)[keep])
+
+    moran_df = pd.DataFrame(data=I, index=names, columns=["Moran's I"])
+    moran_df = moran_df.sort_values(ascending=False, by="Moran's I")
+    adata.var["Moran's I"] = moran_df["Moran's I"]
+
+    if geary:
+        geary_df = pd.DataFrame(data=C, index=names, columns=["Geary's C"])
+        geary_df = geary_df.sort_values(ascending=False, by="Geary's C")
+        adata.var["Geary's C"] = geary_df["Geary's C"]
+
+    # select thresholds (core.py:88-92)
+    if len(moran_df[:top_svg]) < len(moran_df[moran_df["Moran's I"] > min_morans]):
+        chosen = set(moran_df[:top_svg].index)
+    else:
+        chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
+    adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]

@@ -1,0 +1,110 @@
+// K2 - preprocessing front-end on CSR counts (spots x genes).
+//
+// Replaces  sc.pp.filter_genes(min_cells) / sc.pp.normalize_total / sc.pp.log1p / ad.to_df()
+// of /root/reference/chrysalis/core.py:53-59:
+//   gene_nnz[g]   = #{i : X[i,g] > 0}                      (filter_genes keeps gene_nnz >= min_cells)
+//   totals[i]     = sum over KEPT genes of X[i,g]          (normalize_total runs on the filtered copy)
+//   dense[r(i)][c(g)] = log1p(X[i,g] * scale[i])           (scale = median(totals>0)/totals, host side)
+// The dense float32 matrix is the reference's `gene_matrix = ad.to_df()`; rows can be written
+// through a permutation so the matrix comes out in Hilbert (spatially coherent) spot order.
+#include "common.cuh"
+
+namespace chr {
+
+__global__ void csr_gene_nnz_kernel(const int32_t* __restrict__ indices, const float* __restrict__ data, int64_t nnz,
+                                    int32_t* __restrict__ gene_nnz) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride)
+        if (data[e] > 0.f) atomicAdd(gene_nnz + indices[e], 1);
+}
+
+// nnz is read from indptr[n] on the device, so the launch needs no host sync
+__global__ void csr_gene_nnz_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                         const float* __restrict__ data, int64_t n, int32_t* __restrict__ gene_nnz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t b = indptr[i], e = indptr[i + 1];
+        for (int64_t t = b + lane; t < e; t += 32)
+            if (data[t] > 0.f) atomicAdd(gene_nnz + indices[t], 1);
+    }
+}
+
+__global__ void csr_spot_totals_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                       const float* __restrict__ data, int64_t n, const int32_t* __restrict__ gene_col,
+                                       double* __restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t b = indptr[i], e = indptr[i + 1];
+        double s = 0.0;
+        for (int64_t t = b + lane; t < e; t += 32)
+            if (gene_col[indices[t]] >= 0) s += (double)data[t];
+        s = warp_sum(s);
+        if (lane == 0) totals[i] = s;
+    }
+}
+
+__global__ void csr_densify_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   const float* __restrict__ data, int64_t n, const int32_t* __restrict__ gene_col,
+                                   const double* __restrict__ scale, const int64_t* __restrict__ row_of_spot,
+                                   float* __restrict__ dense, int64_t ld, int apply_log1p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t b = indptr[i], e = indptr[i + 1];
+        const double sc = scale ? scale[i] : 1.0;
+        float* __restrict__ row = dense + (row_of_spot ? row_of_spot[i] : i) * ld;
+        for (int64_t t = b + lane; t < e; t += 32) {
+            const int c = gene_col[indices[t]];
+            if (c < 0) continue;
+            float v = scale ? (float)((double)data[t] * sc) : data[t];
+            if (apply_log1p) v = log1pf(v);
+            row[c] = v;
+        }
+    }
+}
+
+}  // namespace chr
+
+extern "C" {
+
+int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n, int64_t n_genes,
+                     int32_t* gene_nnz, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(indptr && indices && data && gene_nnz && n > 0 && n_genes > 0, "chr_csr_gene_nnz: bad arguments");
+    CHR_CUDA(cudaMemsetAsync(gene_nnz, 0, (size_t)n_genes * sizeof(int32_t), st));
+    csr_gene_nnz_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n, gene_nnz);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+int chr_csr_spot_totals(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                        const int32_t* gene_col, double* totals, chr_stream_t stream) {
+    using namespace chr;
+    CHR_REQUIRE(indptr && indices && data && gene_col && totals && n > 0, "chr_csr_spot_totals: bad arguments");
+    csr_spot_totals_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(indptr, indices, data, n, gene_col, totals);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                          const int32_t* gene_col, const double* scale, const int64_t* row_of_spot, float* dense,
+                          int64_t ld, int apply_log1p, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(indptr && indices && data && gene_col && dense && n > 0 && ld > 0, "chr_csr_densify_log1p: bad arguments");
+    CHR_CUDA(cudaMemsetAsync(dense, 0, (size_t)n * ld * sizeof(float), st));
+    timer_begin(CHR_FAMILY_PREP, true, st);
+    csr_densify_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n, gene_col, scale, row_of_spot, dense, ld,
+                                                    apply_log1p);
+    timer_end(CHR_FAMILY_PREP, true, st);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

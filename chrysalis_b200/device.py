@@ -1,0 +1,161 @@
+"""Device-side building blocks of the hot path: thin Python over the C ABI.
+
+PyTorch is plumbing here - it owns device buffers, pinned staging and the current stream;
+every computation on the path is a call into ``libchrysalis_b200.so`` (hand-written sm_100a
+kernels).  There is no CPU fallback: without CUDA or without the library these raise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.ChrysalisNativeError("chrysalis_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
+    """Host ndarray -> device tensor through pinned memory."""
+    dev = _require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.pin_memory().to(dev, non_blocking=True)
+
+
+@dataclass
+class DeviceCSR:
+    """CSR counts (spots x genes) resident on the device."""
+    indptr: torch.Tensor   # int64 [n+1]
+    indices: torch.Tensor  # int32 [nnz]
+    data: torch.Tensor     # float32 [nnz]
+    shape: tuple
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.indptr, self.indices, self.data))
+
+
+def upload_csr(X) -> DeviceCSR:
+    """scipy CSR (or anything ``scipy.sparse.csr_matrix`` accepts, incl. dense) -> DeviceCSR."""
+    import scipy.sparse as sp
+
+    if not sp.issparse(X) or X.format != "csr":
+        X = sp.csr_matrix(X)
+    return DeviceCSR(to_device(X.indptr, torch.int64), to_device(X.indices, torch.int32),
+                     to_device(X.data, torch.float32), tuple(X.shape))
+
+
+# ---- K2 ----------------------------------------------------------------------------------
+
+def csr_gene_nnz(csr: DeviceCSR) -> torch.Tensor:
+    n, g = csr.shape
+    out = torch.empty(g, dtype=torch.int32, device=csr.data.device)
+    _lib.call("chr_csr_gene_nnz", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), n, g, _ptr(out), _stream())
+    return out
+
+
+def csr_spot_totals(csr: DeviceCSR, gene_col: torch.Tensor) -> torch.Tensor:
+    n, _ = csr.shape
+    out = torch.empty(n, dtype=torch.float64, device=csr.data.device)
+    _lib.call("chr_csr_spot_totals", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), n, _ptr(gene_col), _ptr(out),
+              _stream())
+    return out
+
+
+def dense_ld(n_cols: int) -> int:
+    """Row stride of the dense matrix: 128-byte aligned rows."""
+    return max(32, (n_cols + 31) // 32 * 32)
+
+
+def csr_densify(csr: DeviceCSR, gene_col: torch.Tensor, n_cols: int, scale: torch.Tensor | None,
+                row_of_spot: torch.Tensor | None, apply_log1p: bool) -> torch.Tensor:
+    n, _ = csr.shape
+    ld = dense_ld(n_cols)
+    dense = torch.empty((n, ld), dtype=torch.float32, device=csr.data.device)
+    _lib.call("chr_csr_densify_log1p", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), n, _ptr(gene_col),
+              _ptr(scale), _ptr(row_of_spot), _ptr(dense), ld, int(apply_log1p), _stream())
+    return dense
+
+
+def median_scale(totals: torch.Tensor) -> torch.Tensor:
+    """scanpy normalize_total scale factors: 1 / (T_i / median(T[T>0])), T_i == 0 -> T_i = 1."""
+    pos = totals[totals > 0]
+    if pos.numel() == 0:
+        return torch.ones_like(totals)
+    srt, _ = torch.sort(pos)
+    m = srt.numel()
+    after = srt[m // 2] if m % 2 else 0.5 * (srt[m // 2 - 1] + srt[m // 2])
+    counts = totals + (totals == 0).to(totals.dtype)
+    return 1.0 / (counts / after)
+
+
+# ---- K1 ----------------------------------------------------------------------------------
+
+def spatial_bbox(xy: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(4, dtype=torch.float64, device=xy.device)
+    _lib.call("chr_spatial_bbox", _ptr(xy), xy.shape[0], _ptr(out), _stream())
+    return out
+
+
+def hilbert_order(xy: torch.Tensor, bbox: torch.Tensor | None = None) -> torch.Tensor:
+    """Permutation that sorts spots along a Hilbert curve (stable; int64 [n])."""
+    bbox = spatial_bbox(xy) if bbox is None else bbox
+    keys = torch.empty(xy.shape[0], dtype=torch.int64, device=xy.device)
+    _lib.call("chr_hilbert_keys", _ptr(xy), xy.shape[0], _ptr(bbox), _ptr(keys), _stream())
+    return torch.sort(keys, stable=True).indices
+
+
+def knn_build(xy: torch.Tensor, k: int, bbox: torch.Tensor | None = None) -> torch.Tensor:
+    """k nearest other spots of every spot: int32 [n, k] (row-standardised W is implicit)."""
+    assert xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1] == 2
+    n = xy.shape[0]
+    bbox = spatial_bbox(xy) if bbox is None else bbox
+    ws_bytes = _lib.query("chr_knn_workspace_bytes", n, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xy.device)
+    nbr = torch.empty((n, k), dtype=torch.int32, device=xy.device)
+    _lib.call("chr_knn_build", _ptr(xy), n, k, _ptr(bbox), _ptr(nbr), _ptr(ws), ws_bytes, _stream())
+    return nbr
+
+
+# ---- K3 / K4 -----------------------------------------------------------------------------
+
+def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, geary: bool = False,
+                timing: bool = False, want_stats: bool = False, variant: int = 0):
+    """Moran's I (and Geary's C) of every column of the dense [n, ld] float32 matrix ``X``.
+
+    Returns ``(I, C, stats)`` float64 device tensors (``C``/``stats`` None unless requested).
+    """
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+    assert nbr.dtype == torch.int32 and nbr.is_contiguous()
+    n, k = nbr.shape
+    assert X.shape[0] == n
+    ld = X.stride(0)
+    g = X.shape[1] if n_genes is None else n_genes
+    flags = (_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (variant << _lib.VARIANT_SHIFT)
+    ws_bytes = _lib.query("chr_moran_workspace_bytes", n, g, k, flags)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    out_I = torch.empty(g, dtype=torch.float64, device=X.device)
+    out_C = torch.empty(g, dtype=torch.float64, device=X.device) if geary else None
+    stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
+    _lib.call("chr_moran_dense_f32", _ptr(X), n, g, ld, _ptr(nbr), k, flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
+              _ptr(ws), ws_bytes, _stream())
+    return out_I, out_C, stats
+
+
+def last_kernel_ms(family: int = _lib.FAMILY_MORAN) -> float:
+    return float(_lib.query("chr_last_kernel_ms", family))

@@ -1,0 +1,99 @@
+/*
+ * chrysalis_b200 - C ABI of the B200-native (sm_100a) hot path of rockdeme/chrysalis:
+ *   detect_svgs (Moran's I)  ->  pca  ->  aa
+ *
+ * The reference (pure Python, /root/reference/chrysalis/core.py) has no FFI; its boundary
+ * for this path is three Python callables and the third-party numeric calls inside them.
+ * Each entry point below replaces one of those numeric call sites; the Python host
+ * (chrysalis_b200/core.py) keeps the reference signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is a caller-owned DEVICE pointer unless a name says host
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), returns
+ *     0 on success, non-zero on failure; chr_last_error() gives the message (thread-local)
+ *   - no hidden global state, no allocation on the hot path: scratch is a caller-provided
+ *     workspace whose size comes from the matching *_workspace_bytes() query
+ *   - matrices are row-major; `ld` is the row stride in elements
+ */
+#ifndef CHRYSALIS_B200_H
+#define CHRYSALIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* chr_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------ */
+int chr_version(void);
+const char* chr_last_error(void);
+/* device time of the dominant kernel of the most recent call of each family that was made
+ * with CHR_FLAG_TIMING (two cudaEvents around that kernel); synchronises on those events. */
+float chr_last_kernel_ms(int family);
+#define CHR_FAMILY_MORAN 0
+#define CHR_FAMILY_GRAM 1
+#define CHR_FAMILY_AA 2
+#define CHR_FAMILY_KNN 3
+#define CHR_FAMILY_PREP 4
+
+#define CHR_FLAG_GEARY 0x1u   /* also accumulate Geary's C                                  */
+#define CHR_FLAG_TIMING 0x2u  /* record events around the dominant kernel                   */
+#define CHR_VARIANT_SHIFT 8   /* bits 8..15 of `flags`: kernel variant (0 = default; tuning)  */
+
+/* ---- K1: spatial weights -------------------------------------------------------------
+ * replaces  weights.KNN.from_array(points, k=neighbors); w.transform = 'R'
+ *           (/root/reference/chrysalis/core.py:64-65; libpysal -> scipy cKDTree.query(k+1))
+ * xy: [n][2] float64 coordinates (the caller has already negated y, core.py:62).
+ * nbr_out: [n][k] int32, the k nearest other spots of every spot in increasing distance
+ * (ties: lower index first).  Row-standardised W is implicit: every weight is 1/k. */
+/* bbox_out: device [4] float64 = {min_x, min_y, max_x, max_y} */
+int chr_spatial_bbox(const double* xy, int64_t n, double* bbox_out, chr_stream_t stream);
+size_t chr_knn_workspace_bytes(int64_t n, int k);
+int chr_knn_build(const double* xy, int64_t n, int k, const double* bbox, int32_t* nbr_out,
+                  void* workspace, size_t workspace_bytes, chr_stream_t stream);
+
+/* Hilbert-curve key (16 bits per axis over bbox) of every spot: sorting spots by it makes the
+ * rows of the dense matrix spatially coherent, so neighbour rows share L1/L2 lines.
+ * keys_out: [n] int64. */
+int chr_hilbert_keys(const double* xy, int64_t n, const double* bbox, int64_t* keys_out,
+                     chr_stream_t stream);
+
+/* ---- K2: preprocessing ---------------------------------------------------------------
+ * replaces  sc.pp.filter_genes(min_cells) / sc.pp.normalize_total / sc.pp.log1p / ad.to_df()
+ *           (/root/reference/chrysalis/core.py:53-59)
+ * CSR counts (spots x genes): indptr [n+1] int64, indices [nnz] int32, data [nnz] float32. */
+int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                     int64_t n_genes, int32_t* gene_nnz /* [n_genes], zeroed by callee */,
+                     chr_stream_t stream);
+/* per-spot totals over the kept genes (gene_col[g] >= 0), double accumulation, one warp per spot */
+int chr_csr_spot_totals(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                        const int32_t* gene_col, double* totals, chr_stream_t stream);
+/* dense[row_of_spot[i]][gene_col[g]] = f(data * scale[i]),  f = log1p if apply_log1p else identity,
+ * product formed in float64 and rounded once to float32 (scanpy normalize_total semantics);
+ * scale == NULL: no scaling.  dense is [n][ld] float32 and is zero-filled by the callee;
+ * row_of_spot may be NULL (identity); genes with gene_col[g] < 0 are dropped. */
+int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                          const int32_t* gene_col, const double* scale, const int64_t* row_of_spot,
+                          float* dense, int64_t ld, int apply_log1p, chr_stream_t stream);
+
+/* ---- K3/K4: Moran's I (and Geary's C) ------------------------------------------------
+ * replaces  the gene loop  esda.moran.Moran(gene_matrix[c], w, permutations=0).I
+ *           [+ esda.geary.Geary(...).C]      (/root/reference/chrysalis/core.py:71-76)
+ * X: [n_spots][ld] float32 dense expression (ld % 4 == 0, X 16-byte aligned, columns
+ *    n_genes..ld-1 readable), nbr: [n_spots][k] int32 (K1 output or any kNN list).
+ * out_I / out_C: [n_genes] float64 (out_C may be NULL without CHR_FLAG_GEARY).
+ * out_stats: optional [4][n_genes] float64 = {mean, z'z, z'Wz, geary numerator}.
+ * One pass over X; per-gene accumulators fp32 in 16-spot chunks -> fp64. */
+size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags);
+int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld,
+                        const int32_t* nbr, int k, unsigned flags, double* out_I, double* out_C,
+                        double* out_stats, void* workspace, size_t workspace_bytes,
+                        chr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHRYSALIS_B200_H */

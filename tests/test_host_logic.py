@@ -1,0 +1,70 @@
+"""Host-side logic of detect_svgs (field contract, name handling, selection rule) with the device
+stage replaced by the oracle's numbers - runs on the CPU box."""
+import numpy as np
+import pytest
+
+import chrysalis_b200 as ch
+from chrysalis_b200 import core
+from conftest import golden_csr
+
+
+def _oracle_stage(z):
+    def stage(X, spatial, min_spots, neighbors, geary, already_log1p, timing=False):
+        m = z["gene_mask"]
+        return m, z["morans"][m], (z["geary"][m] if geary else None)
+    return stage
+
+
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+def test_fields_and_selection_match_oracle(name, request, monkeypatch):
+    z = request.getfixturevalue(name)
+    monkeypatch.setattr(core, "svg_stage", _oracle_stage(z))
+    ad = ch.AnnDataLite(golden_csr(z), obsm={"spatial": z["xy"]})
+    X_before = ad.X.copy()
+    assert ch.detect_svgs(ad, neighbors=int(z["k"]), top_svg=int(z["top_svg"]), min_morans=float(z["min_morans"]),
+                          geary=True) is None
+    got = ad.var["Moran's I"].to_numpy()
+    assert np.array_equal(np.isnan(got), ~z["gene_mask"])          # filtered genes -> NaN (core.py:80)
+    assert np.array_equal(got[z["gene_mask"]], z["morans"][z["gene_mask"]])
+    assert np.array_equal(ad.var["Geary's C"].to_numpy()[z["gene_mask"]], z["geary"][z["gene_mask"]])
+    assert ad.var["spatially_variable"].dtype == bool
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), z["spatially_variable"])
+    assert (ad.X != X_before).nnz == 0                              # caller's X untouched
+    assert "log1p" not in ad.uns
+
+
+def test_min_spots_assertion():
+    z = None
+    ad = ch.AnnDataLite(np.zeros((4, 3), np.float32), obsm={"spatial": np.zeros((4, 2))})
+    for bad in (0, 1, -0.1, 1.5):
+        with pytest.raises(AssertionError):
+            ch.detect_svgs(ad, min_spots=bad)
+
+
+def test_make_unique_names():
+    out = core._make_unique(["a", "b", "a", "a", "b", "a-1"])
+    assert out.is_unique and out[0] == "a" and out[1] == "b" and out[5] == "a-1"
+    assert set(out[[2, 3]]) == {"a-2", "a-3"} and out[4] == "b-1"
+
+
+def test_duplicate_var_names_follow_pandas_alignment(golden_hex, monkeypatch):
+    z = golden_hex
+    monkeypatch.setattr(core, "svg_stage", _oracle_stage(z))
+    names = [f"g{j}" for j in range(int(z["shape"][1]))]
+    kept = np.flatnonzero(z["gene_mask"])
+    names[kept[1]] = names[kept[0]]                                  # duplicate among scored genes
+    ad = ch.AnnDataLite(golden_csr(z), obsm={"spatial": z["xy"]}, var_names=names)
+    ch.detect_svgs(ad, top_svg=int(z["top_svg"]))
+    v = ad.var["Moran's I"].to_numpy()
+    assert v[kept[0]] == v[kept[1]] == z["morans"][kept[0]]          # both rows align to the first name
+
+
+def test_top_svg_rule_branches(golden_hex, monkeypatch):
+    z = golden_hex
+    monkeypatch.setattr(core, "svg_stage", _oracle_stage(z))
+    from oracle import svg as osvg
+    for top, thr in [(5, 0.2), (1000, 0.2), (10, -1.0), (50, 0.05)]:
+        ad = ch.AnnDataLite(golden_csr(z), obsm={"spatial": z["xy"]})
+        ch.detect_svgs(ad, top_svg=top, min_morans=thr)
+        exp = osvg.select_svgs(z["morans"], z["gene_mask"], top, thr)
+        assert np.array_equal(ad.var["spatially_variable"].to_numpy(), exp), (top, thr)

@@ -1,0 +1,247 @@
+"""GPU parity of the SVG stage (K1-K4) against the CPU oracle - all calls go through the C ABI.
+
+Tolerance: Moran's I within 1e-5 relative (north_star).  The oracle computes z in float32 like
+the reference (core.py:59 -> esda), so for |I| below ~1e-3 its own rounding noise exceeds
+1e-5*|I|; there the bound is 1e-8 absolute and the float64 oracle is the arbiter.
+"""
+import numpy as np
+import pytest
+import torch
+
+import chrysalis_b200 as ch
+from chrysalis_b200 import device as dv
+from chrysalis_b200 import synth
+from conftest import golden_csr
+from oracle import moran as om
+from oracle import svg as osvg
+from oracle import weights as ow
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-8
+
+
+def assert_close(got, ref, rtol=RTOL, atol=ATOL, what="I"):
+    got, ref = np.asarray(got), np.asarray(ref)
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref) + atol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} off; worst abs {err.max():.3e} at ref {ref[err.argmax()]:.6g}"
+
+
+def dense_from(X_csr, mask=None):
+    Xn = osvg.normalize_total_log1p(X_csr if mask is None else X_csr[:, mask])
+    return np.asarray(Xn.todense(), dtype=np.float32)
+
+
+def gpu_moran(dense, nbr, geary=False, ld=None, **kw):
+    n, g = dense.shape
+    ld = dv.dense_ld(g) if ld is None else ld
+    Xd = torch.zeros((n, ld), dtype=torch.float32, device="cuda")
+    Xd[:, :g] = torch.from_numpy(dense).cuda()
+    nb = torch.from_numpy(np.ascontiguousarray(nbr, dtype=np.int32)).cuda()
+    I, C, st = dv.moran_dense(Xd, nb, g, geary=geary, **kw)
+    torch.cuda.synchronize()
+    return I.cpu().numpy(), (C.cpu().numpy() if geary else None), st
+
+
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+def test_moran_kernel_matches_golden(name, request):
+    z = request.getfixturevalue(name)
+    m = z["gene_mask"]
+    I, C, _ = gpu_moran(dense_from(golden_csr(z), m), z["nbr"], geary=True)
+    assert_close(I, z["morans"][m])
+    assert_close(C, z["geary"][m], what="C")
+
+
+@pytest.mark.parametrize("k", [1, 4, 6, 8, 18, 36, 40])
+def test_moran_kernel_any_k(k):
+    xy = synth.make_coords("random", 3000, seed=k)
+    X, _ = synth.make_counts_csr(xy, 200, seed=k)
+    dense = dense_from(X)
+    dense = dense[:, dense.std(0) > 0]
+    nbr = ow.knn_neighbors(xy, k)
+    I, C, _ = gpu_moran(dense, nbr, geary=True)
+    assert_close(I, om.morans_I_batched(dense, nbr))
+    assert_close(C, om.gearys_C_batched(dense, nbr), what="C")
+
+
+@pytest.mark.parametrize("n,g", [(33, 1), (513, 3), (1000, 127), (1025, 129), (4035, 260)])
+def test_ragged_shapes_and_strides(n, g):
+    rng = np.random.default_rng(n + g)
+    xy = rng.uniform(0, 100, (n, 2))
+    dense = np.log1p(rng.poisson(0.7, (n, g))).astype(np.float32) + rng.normal(0, 0.1, (n, g)).astype(np.float32)
+    nbr = ow.knn_neighbors(xy, 6)
+    ref = om.morans_I_batched(dense, nbr)
+    for ld in (dv.dense_ld(g), (g + 3) // 4 * 4, dv.dense_ld(g) + 64):
+        I, _, _ = gpu_moran(dense, nbr, ld=ld)
+        assert_close(I, ref)
+
+
+def test_constant_and_highly_expressed_genes():
+    """Cancellation guard: large mean / tiny variance genes, and a constant gene -> NaN."""
+    rng = np.random.default_rng(3)
+    n = 4035
+    xy = synth.make_coords("hex", n, seed=1)
+    nbr = ow.knn_neighbors(xy, 6)
+    base = rng.normal(0, 1, n)
+    dense = np.stack([7.0 + 0.01 * base, 100.0 + rng.normal(0, 0.5, n), np.full(n, 2.5), 5.0 + np.sin(xy[:, 0] / 300.0)],
+                     1).astype(np.float32)
+    I, _, _ = gpu_moran(dense, nbr)
+    ref64 = om.morans_I_batched(dense, nbr, dtype=np.float64)
+    assert np.isnan(I[2])
+    keep = [0, 1, 3]
+    # judged against the float64 statistic of the same float32 inputs
+    assert_close(I[keep], ref64[keep], rtol=1e-5, atol=2e-7)
+
+
+def test_known_answers_on_torus_lattice():
+    rows, cols = 64, 48
+    r, c = np.divmod(np.arange(rows * cols), cols)
+    def lat(offs):
+        return np.stack([((r + dr) % rows) * cols + (c + dc) % cols for dr, dc in offs], 1)
+    rook = [(-1, 0), (1, 0), (0, -1), (0, 1)]
+    queen = rook + [(-1, -1), (-1, 1), (1, -1), (1, 1)]
+    dense = np.stack([(r + c) % 2, r % 2, c % 2], 1).astype(np.float32)
+    I4, C4, _ = gpu_moran(dense, lat(rook), geary=True)
+    I8, _, _ = gpu_moran(dense, lat(queen))
+    assert np.allclose(I4, [-1.0, 0.0, 0.0], atol=1e-12)
+    assert np.allclose(I8, [0.0, -0.5, -0.5], atol=1e-12)
+    assert C4[0] == pytest.approx(2.0 * (rows * cols - 1) / (rows * cols), rel=1e-12)
+
+
+def test_invariances_full_spot_count():
+    """BASELINE cfg4 spot count (700k, k=8) with a thin gene slab: size-independent properties.
+    I is invariant to affine maps of expression and to relabelling spots; the oracle is run on
+    a column subsample."""
+    n, g, k = 700_000, 96, 8
+    side = int(np.ceil(np.sqrt(n)))
+    rr, cc = np.divmod(np.arange(n), side)
+    # exact square lattice -> queen stencil for interior bins, wrap-free clamp at the border
+    offs = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]
+    nbr = np.empty((n, k), dtype=np.int32)
+    for j, (dr, dc) in enumerate(offs):
+        r2 = np.clip(rr + dr, 0, (n - 1) // side)
+        c2 = np.clip(cc + dc, 0, side - 1)
+        idx = r2 * side + c2
+        idx = np.where(idx >= n, np.arange(n) - 1, idx)
+        idx = np.where(idx == np.arange(n), (np.arange(n) + 1) % n, idx)
+        nbr[:, j] = idx
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    xs = torch.linspace(0, 40, side, device="cuda")
+    field = (torch.sin(xs)[None, :] * torch.cos(xs * 0.7)[:, None]).reshape(-1)[:n]
+    amp = torch.linspace(0, 2, g, device="cuda")
+    X = torch.poisson(torch.exp(0.3 + amp[None, :] * field[:, None]).clamp_max(50.0), generator=gen)
+    X = torch.log1p(X)
+    Xd = torch.zeros((n, dv.dense_ld(g)), device="cuda")
+    Xd[:, :g] = X
+    nb = torch.from_numpy(nbr).cuda()
+    I, _, _ = dv.moran_dense(Xd, nb, g)
+    I2, _, _ = dv.moran_dense(Xd * 3.0 + 1.5, nb, g)             # affine invariance
+    assert_close(I2.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=1e-8)
+    perm = torch.randperm(n, device="cuda", generator=gen)        # relabel spots
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(n, device="cuda")
+    nb_p = inv[nb[perm].long()].to(torch.int32).contiguous()
+    I3, _, _ = dv.moran_dense(Xd[perm].contiguous(), nb_p, g)
+    assert_close(I3.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=1e-8)
+    I4, _, _ = dv.moran_dense(Xd, nb, g)                          # run-to-run bit reproducibility
+    assert torch.equal(I4, I)
+    cols = [0, 1, 17, 48, 95]
+    ref = om.morans_I_batched(X[:, cols].cpu().numpy(), nbr)
+    assert_close(I.cpu().numpy()[cols], ref)
+    assert I[-1] > 0.3 and abs(float(I[0])) < 0.01                # spatial signal grows with amp
+
+
+def test_gene_sharding_is_bit_identical():
+    """Multi-GPU contract: any contiguous gene shard reproduces the 1-GPU bits."""
+    xy = synth.make_coords("square", 20000, seed=3)
+    X, _ = synth.make_counts_csr(xy, 600, seed=3)
+    dense = dense_from(X)
+    nbr = ow.knn_neighbors(xy, 8)
+    I, _, _ = gpu_moran(dense, nbr)
+    for lo, hi in [(0, 150), (150, 413), (413, 600)]:
+        Is, _, _ = gpu_moran(np.ascontiguousarray(dense[:, lo:hi]), nbr)
+        assert np.array_equal(Is, I[lo:hi])
+
+
+@pytest.mark.parametrize("kind,n,k", [("hex", 4035, 6), ("random", 20000, 8), ("square", 30000, 8), ("random", 5000, 36)])
+def test_knn_builder_matches_ckdtree(kind, n, k):
+    xy = synth.make_coords(kind, n, seed=11)
+    xy[:, 1] *= -1
+    nbr = dv.knn_build(dv.to_device(xy, torch.float64), k).cpu().numpy()
+    ref = ow.knn_neighbors(xy, k)
+    assert np.array_equal(np.sort(nbr, 1), np.sort(ref, 1))       # jittered coords: unique kNN sets
+    d = np.linalg.norm(xy[nbr] - xy[:, None, :], axis=2)
+    assert (np.diff(d, axis=1) >= 0).all()                         # increasing distance order
+
+
+def test_knn_builder_exact_lattice_ties():
+    """Exact lattice: ties everywhere.  Neighbour *distances* must equal cKDTree's."""
+    xy = synth.make_coords("square", 10000, seed=0, jitter=0.0)
+    nbr = dv.knn_build(dv.to_device(xy, torch.float64), 8).cpu().numpy()
+    ref = ow.knn_neighbors(xy, 8)
+    dg = np.sort(np.linalg.norm(xy[nbr] - xy[:, None, :], axis=2), 1)
+    dr = np.sort(np.linalg.norm(xy[ref] - xy[:, None, :], axis=2), 1)
+    assert np.allclose(dg, dr)
+    assert not (nbr == np.arange(len(xy))[:, None]).any()
+
+
+def test_hilbert_order_is_a_permutation_and_local():
+    xy = synth.make_coords("random", 50000, seed=2)
+    order = dv.hilbert_order(dv.to_device(xy, torch.float64)).cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(len(xy)))
+    step = np.linalg.norm(np.diff(xy[order], axis=0), axis=1)
+    assert np.median(step) < 3 * np.sqrt(np.ptp(xy[:, 0]) * np.ptp(xy[:, 1]) / len(xy))
+
+
+def test_preprocessing_kernels_match_scanpy_semantics(golden_hex):
+    z = golden_hex
+    X = golden_csr(z)
+    csr = dv.upload_csr(X)
+    nnz = dv.csr_gene_nnz(csr).cpu().numpy()
+    assert np.array_equal(nnz, np.asarray((X > 0).sum(0)).ravel())
+    keep = torch.from_numpy(z["gene_mask"]).cuda()
+    gene_col = torch.where(keep, torch.cumsum(keep.int(), 0, dtype=torch.int32) - 1, torch.tensor(-1, dtype=torch.int32, device="cuda"))
+    tot = dv.csr_spot_totals(csr, gene_col)
+    assert np.array_equal(tot.cpu().numpy(), np.asarray(X[:, z["gene_mask"]].sum(1)).ravel().astype(np.float64))
+    dense = dv.csr_densify(csr, gene_col, int(z["gene_mask"].sum()), dv.median_scale(tot), None, True)
+    ref = dense_from(X, z["gene_mask"])
+    got = dense[:, :ref.shape[1]].cpu().numpy()
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.allclose(got, ref, rtol=3e-7, atol=0)
+    assert float(dense[:, ref.shape[1]:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+def test_detect_svgs_end_to_end(name, request):
+    z = request.getfixturevalue(name)
+    ad = ch.AnnDataLite(golden_csr(z), obsm={"spatial": z["xy"]})
+    ch.detect_svgs(ad, neighbors=int(z["k"]), top_svg=int(z["top_svg"]), min_morans=float(z["min_morans"]), geary=True)
+    m = z["gene_mask"]
+    got = ad.var["Moran's I"].to_numpy()
+    assert np.array_equal(np.isnan(got), ~m)
+    assert_close(got[m], z["morans"][m])
+    assert_close(ad.var["Geary's C"].to_numpy()[m], z["geary"][m], what="C")
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), z["spatially_variable"])
+
+
+def test_detect_svgs_respects_existing_log1p(golden_hex):
+    z = golden_hex
+    Xn = osvg.normalize_total_log1p(golden_csr(z))
+    ad = ch.AnnDataLite(Xn, obsm={"spatial": z["xy"]}, uns={"log1p": {"base": None}})
+    ch.detect_svgs(ad, neighbors=6)
+    ref = osvg.detect_svgs(Xn, z["xy"], neighbors=6, already_log1p=True)
+    m = ref["gene_mask"]
+    assert_close(ad.var["Moran's I"].to_numpy()[m], ref["morans"][m])
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+
+
+def test_cfg1_shape_selection_identical():
+    """BASELINE cfg1 spot count (4,035 hex spots, k=6) x 3,000 genes: identical SVG set."""
+    xy = synth.make_coords("hex", 4035, seed=42)
+    X, _ = synth.make_counts_csr(xy, 3000, seed=42)
+    ad = ch.AnnDataLite(X, obsm={"spatial": xy})
+    ch.detect_svgs(ad, neighbors=6, top_svg=200)
+    ref = osvg.detect_svgs(X, xy, neighbors=6, top_svg=200)
+    m = ref["gene_mask"]
+    assert_close(ad.var["Moran's I"].to_numpy()[m], ref["morans"][m])
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
