@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Headline benchmark: Moran's I genes/sec at Visium-HD scale (BASELINE.json cfg 4).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch: Moran's I for every gene of the
+700,000-bin x 18,000-gene dense float32 log1p matrix already resident in HBM (50.4 GB, far
+larger than L2, so no flush is needed between steps).  Under torchrun every rank holds its own
+18,000-gene shard of a N*18,000-gene matrix (genes shard with no data-path collective; only the
+per-gene statistics are all-gathered), i.e. weak scaling.  One JSON line is printed by rank 0.
+
+`e2e` is the same metric through the public host-buffer path: pinned host CSR counts ->
+H2D -> filter/normalise/log1p/densify -> kNN W -> Moran -> D2H of the per-gene statistics.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="cfg4_visium_hd", n=700_000, g=18_000, k=8)
+METRIC = "morans_I_genes_per_sec"
+UNIT = "genes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=WORKLOAD["n"], help="spots (debug: smaller workloads)")
+    ap.add_argument("--g", type=int, default=WORKLOAD["g"], help="genes per GPU")
+    ap.add_argument("--k", type=int, default=WORKLOAD["k"])
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (tuning)")
+    ap.add_argument("--sweep", default="", help="comma list of kernel variants to time (kernel ms only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (NVML in a thread, 20 ms period) - runs only during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.stop_flag, self.thread, self.max_mhz = [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES ordering when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------
+def lattice_coords(n, seed):
+    from chrysalis_b200 import synth
+    return synth.make_coords("square", n, seed=seed)          # Visium HD bins: square lattice, k=8 (A5:41)
+
+
+def build_device_workload(args, rank, torch, dv, synth):
+    """Coordinates -> Hilbert order -> W, device CSR counts and the resident dense log1p matrix."""
+    n, g, k = args.n, args.g, args.k
+    xy = lattice_coords(n, 42)
+    xy_d = dv.to_device(xy, torch.float64)
+    bbox = dv.spatial_bbox(xy_d)
+    order = dv.hilbert_order(xy_d, bbox)
+    xy_s = xy_d[order].contiguous()
+    nbr = dv.knn_build(xy_s, k, bbox)
+    # counts, generated on device in Hilbert row order, kept as CSR pieces
+    model = synth.make_expression_model(xy, g, n_zones=12, seed=42 + rank, log_rate_mean=-3.3, log_rate_sd=1.0,
+                                        device="cuda")
+    xy32 = xy_s.to(torch.float32)
+    chunk = 4096
+    row_nnz, idx_parts, val_parts = [], [], []
+    for b, i0 in enumerate(range(0, n, chunk)):
+        c = model.counts(xy32[i0:i0 + chunk], b)
+        nz = c > 0
+        row_nnz.append(nz.sum(1))
+        idx_parts.append(nz.nonzero()[:, 1].to(torch.int32))
+        val_parts.append(c[nz])
+        del c, nz
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    indptr[1:] = torch.cumsum(torch.cat(row_nnz), 0)
+    csr = dv.DeviceCSR(indptr, torch.cat(idx_parts), torch.cat(val_parts), (n, g))
+    del idx_parts, val_parts, row_nnz
+    return xy_s, nbr, csr
+
+
+def dense_from_csr(csr, min_spots, torch, dv):
+    """The product's own front-end (K2) on the device-resident counts."""
+    n, g = csr.shape
+    gene_nnz = dv.csr_gene_nnz(csr)
+    keep = gene_nnz >= int(n * min_spots)
+    gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
+                           torch.full_like(gene_nnz, -1))
+    n_keep = int(keep.sum().item())
+    scale = dv.median_scale(dv.csr_spot_totals(csr, gene_col))
+    return dv.csr_densify(csr, gene_col, n_keep, scale, None, apply_log1p=True), n_keep
+
+
+# ---------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from chrysalis_b200 import _lib, core, synth
+    from chrysalis_b200 import device as dv
+
+    _lib.load()
+    MIN_SPOTS = 1e-4
+    n, g, k = args.n, args.g, args.k
+    t0 = time.time()
+    xy_s, nbr, csr = build_device_workload(args, rank, torch, dv, synth)
+    X, g_scored = dense_from_csr(csr, MIN_SPOTS, torch, dv)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    density = csr.data.numel() / (n * g)
+
+    gathered = [torch.empty(g_scored, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step(timing=False):
+        I, _, _ = dv.moran_dense(X, nbr, g_scored, timing=timing, variant=args.variant)
+        if world > 1:
+            # every rank scores the same number of genes only if the filter keeps the same count;
+            # pad to a common length for the all-gather of per-gene statistics
+            dist.all_gather(gathered, I)
+        return I
+
+    # every rank must all-gather equal sizes: agree on min g_scored (synthetic shards differ by seed)
+    if world > 1:
+        t = torch.tensor([g_scored], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        g_scored = int(t.item())
+        gathered = [torch.empty(g_scored, dtype=torch.float64, device="cuda") for _ in range(world)]
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    sampler.start()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        I = step(timing=True)
+        kernel_ms.append(None)  # filled after the region (reading an event would synchronise)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # dominant-kernel duration: a separate short loop with per-launch events (same stream, same
+    # inputs > L2), so reading the events does not perturb the timed region above
+    kms = []
+    for _ in range(min(args.steps, 10)):
+        dv.moran_dense(X, nbr, g_scored, timing=True, variant=args.variant)
+        kms.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
+    kernel_ms = float(np.mean(kms))
+
+    sweep = {}
+    for v in [int(x) for x in args.sweep.split(",") if x != ""]:
+        ts = []
+        for _ in range(6):
+            Iv, _, _ = dv.moran_dense(X, nbr, g_scored, timing=True, variant=v)
+            ts.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
+        sweep[str(v)] = {"kernel_ms": round(float(np.mean(ts[1:])), 4), "bit_identical_to_default": bool(torch.equal(Iv, I))}
+
+    ms_per_step = total_ms / args.steps
+    value = world * g_scored / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (moran_ell_kernel): algorithmic bytes = one read of X
+    # + W indices + per-split partial sums + outputs  
+    ld = X.stride(0)
+    alg_bytes = 4.0 * n * g_scored + 4.0 * n * k + 8.0 * g_scored
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "moran_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "moran_ell_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
+                "kernel_share_of_step": round(kernel_ms / ms_per_step, 4)}
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (fp64 per-gene accumulators)", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes per GPU, square lattice, kNN k={k}, "
+                               f"dense float32 log1p(normalize_total(counts)) resident in HBM",
+                   "n_spots": n, "genes_per_gpu": g, "genes_scored_per_gpu": g_scored, "genes_total": world * g_scored,
+                   "neighbors": k, "ld": ld, "counts_density": round(density, 4), "parallelism": f"gene-shard x{world}",
+                   "l2_policy": "inputs_exceed_l2 (X = %.1f GB per GPU >> 126 MB L2)" % (4.0 * n * ld / 1e9),
+                   "variant": args.variant, "setup_s": round(setup_s, 1)},
+        "roofline": roofline, "clocks": clocks, "gpu_launches": 3 * args.steps,
+        "kernels_per_step": ["moran_pilot_kernel", "moran_ell_kernel", "moran_finalize_kernel"],
+    }
+    if sweep:
+        out["variant_sweep"] = sweep
+
+    # ---- e2e: host CSR (pinned) -> device -> full SVG stage -> host -------------------------------
+    if not args.no_e2e:
+        host = dv.PinnedCSR(csr.indptr.cpu().pin_memory(), csr.indices.cpu().pin_memory(), csr.data.cpu().pin_memory(),
+                            csr.shape)
+        xy_host = xy_s.cpu().numpy()
+        xy_host[:, 1] *= -1                                       # svg_stage negates y like core.py:62
+        del X
+        torch.cuda.empty_cache()
+        e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            keep, I_h, _ = core.svg_stage(host, xy_host, MIN_SPOTS, k, False, already_log1p=False)
+            return I_h
+
+        I_h = e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        for _ in range(e_steps):
+            I_h = e2e_step()
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t1) * 1e3 / e_steps
+        if world > 1:
+            t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        same = bool(len(I_h) >= g_scored and np.array_equal(I_h[:g_scored], I.cpu().numpy()))
+        out["e2e"] = {"value": round(world * len(I_h) / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 2),
+                      "h2d_bytes_per_step": int(host.nbytes + xy_host.nbytes), "d2h_bytes_per_step": int(8 * len(I_h) + g),
+                      "steps": e_steps, "path": "core.svg_stage(PinnedCSR counts, coords): H2D + filter/normalise/log1p/densify + "
+                                                "Hilbert sort + kNN + Moran + D2H",
+                      "bit_identical_to_resident_run": same}
+        X, _ = dense_from_csr(csr, MIN_SPOTS, torch, dv)
+
+    # ---- cpu baseline + parity on a bounded gene sample (rank 0, N=1 only) ---------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import moran as om
+        from oracle import weights as ow
+        cols = np.linspace(0, g_scored - 1, 64).astype(np.int64)
+        sample = X[:, torch.from_numpy(cols).cuda()].cpu().numpy()
+        nbr_h = nbr.cpu().numpy()
+        w = ow.row_standardised_csr(nbr_h)
+        I_dev = I.cpu().numpy()
+        t1 = time.perf_counter()
+        done, ref = 0, []
+        for j in range(sample.shape[1]):
+            ref.append(om.morans_I(np.ascontiguousarray(sample[:, j]), w))
+            done += 1
+            if time.perf_counter() - t1 > args.cpu_seconds:
+                break
+        cpu_s = time.perf_counter() - t1
+        ref = np.array(ref)
+        err = np.abs(I_dev[cols[:done]] - ref) / np.maximum(np.abs(ref), 1e-3)
+        out["cpu_baseline"] = {"value": round(done / cpu_s, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{done} evenly spaced genes of the same {n}-bin matrix, reference-style loop "
+                                         f"(one scipy CSR.vector per gene, oracle/moran.py:morans_I), {cpu_s:.1f} s"}
+        out["parity"] = {"genes_checked": done, "max_rel_err_vs_oracle": float(err.max()), "tolerance": 1e-5}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port; the real esda/libpysal are not installable)
+# ---------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _ref_worker(cols):
+    from oracle import moran as om
+    X, w = _G["X"], _G["w"]
+    return [om.morans_I(np.ascontiguousarray(X[:, j]), w) for j in cols]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    import torch
+
+    from chrysalis_b200 import synth
+    from oracle import weights as ow
+
+    n, g, k = args.n, args.g, args.k
+    cores = os.cpu_count() or 1
+    per_step = 4 * cores                                         # genes per step (bounded sample)
+    n_sample = per_step
+    xy = lattice_coords(n, 42)
+    model = synth.make_expression_model(xy, n_sample, n_zones=12, seed=42, log_rate_mean=-3.3, log_rate_sd=1.0)
+    xy_t = torch.as_tensor(xy, dtype=torch.float32)
+    X = np.empty((n, n_sample), dtype=np.float32)
+    for b, i0 in enumerate(range(0, n, 65536)):
+        c = model.counts(xy_t[i0:i0 + 65536], b)
+        X[i0:i0 + 65536] = synth.normalize_log1p_dense(c).numpy()
+    X = X[:, X.std(0) > 0]
+    n_sample = X.shape[1]
+    pts = xy.copy()
+    pts[:, 1] *= -1
+    w = ow.row_standardised_csr(ow.knn_neighbors(pts, k))
+    _G["X"], _G["w"] = X, w
+    chunks = [list(range(i, n_sample, cores)) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_worker, chunks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, chunks)
+        dt = time.perf_counter() - t0
+    ms = dt * 1e3 / args.steps
+    value = n_sample / (ms * 1e-3)
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 lag)", "data": "synthetic",
+           "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes, square lattice, kNN k={k}", "n_spots": n,
+                      "genes_per_gpu": g, "neighbors": k},
+           "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{n_sample} genes of the {n}-bin workload per step; reference-style per-gene loop "
+                                      f"(scipy cKDTree W + one CSR.vector per gene, oracle/moran.py) run gene-parallel on "
+                                      f"{cores} processes; the real esda/libpysal cannot be installed offline"},
+           "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -67,9 +67,15 @@ struct Acc4 {
     }
 };
 
-// K = compile-time neighbour count (0: runtime k, any value)
-template <int K, bool GEARY>
-__global__ void __launch_bounds__(kMoranThreads, 2)
+// one elected lane asks the TMA unit to pull a row segment into L2 ahead of use
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// K = compile-time neighbour count (0: runtime k, any value); MINB = CTAs/SM the register
+// budget is sized for; PF = L2 prefetch distance in warp iterations (0 = off)
+template <int K, bool GEARY, int MINB, int PF>
+__global__ void __launch_bounds__(kMoranThreads, MINB)
 moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t ncol, const int32_t* __restrict__ nbr,
                  int k_rt, const float* __restrict__ pilot, int64_t spots_per_split, double* __restrict__ part,
                  int64_t gpad) {
@@ -91,7 +97,15 @@ moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t nco
     Acc4 a1{}, a2{}, aw{}, as{}, aq{};
     int cnt = 0;
 
+    // bytes of this CTA's 128-gene slab that exist in the row (16-byte multiple)
+    const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
+    const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
+
     for (int64_t i = s_begin + warp; i < s_end; i += kMoranWarps) {
+        if (PF > 0 && lane == 0) {
+            const int64_t ip = i + (int64_t)PF * kMoranWarps;
+            if (ip < s_end) l2_prefetch_bulk(X + ip * ld + tile_col, tile_bytes);
+        }
         float4 x = zero, s = zero;
         if (active) x = ldg_f4(Xc + i * ld);
         if constexpr (K > 0 && K <= 32) {
@@ -202,15 +216,17 @@ static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld) {
     return p;
 }
 
-template <bool GEARY>
+template <bool GEARY, int MINB, int PF>
 static void launch_ell(int k, dim3 grid, cudaStream_t st, const float* X, int64_t n, int64_t ld, int64_t ncol,
                        const int32_t* nbr, const float* pilot, int64_t sps, double* part, int64_t gpad) {
+#define CHR_ELL(KK) moran_ell_kernel<KK, GEARY, MINB, PF><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad)
     switch (k) {
-        case 4: moran_ell_kernel<4, GEARY><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad); break;
-        case 6: moran_ell_kernel<6, GEARY><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad); break;
-        case 8: moran_ell_kernel<8, GEARY><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad); break;
-        default: moran_ell_kernel<0, GEARY><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad); break;
+        case 4: CHR_ELL(4); break;
+        case 6: CHR_ELL(6); break;
+        case 8: CHR_ELL(8); break;
+        default: CHR_ELL(0); break;
     }
+#undef CHR_ELL
 }
 
 }  // namespace chr
@@ -253,8 +269,16 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
 
     dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
     timer_begin(CHR_FAMILY_MORAN, timing, st);
-    if (geary) launch_ell<true>(k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad);
-    else launch_ell<false>(k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad);
+#define CHR_ARGS k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad
+    const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
+    if (geary) launch_ell<true, 2, 8>(CHR_ARGS);
+    else switch (variant) {
+        case 1: launch_ell<false, 2, 0>(CHR_ARGS); break;   // no prefetch
+        case 2: launch_ell<false, 2, 32>(CHR_ARGS); break;  // far prefetch
+        case 3: launch_ell<false, 3, 8>(CHR_ARGS); break;   // 3 CTAs/SM
+        default: launch_ell<false, 2, 8>(CHR_ARGS); break;
+    }
+#undef CHR_ARGS
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();
 

@@ -50,10 +50,29 @@ class DeviceCSR:
         return sum(t.numel() * t.element_size() for t in (self.indptr, self.indices, self.data))
 
 
+@dataclass
+class PinnedCSR:
+    """CSR counts staged in pinned host memory (what a loader hands to the device path)."""
+    indptr: torch.Tensor   # int64 [n+1], pinned
+    indices: torch.Tensor  # int32 [nnz], pinned
+    data: torch.Tensor     # float32 [nnz], pinned
+    shape: tuple
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.indptr, self.indices, self.data))
+
+
 def upload_csr(X) -> DeviceCSR:
-    """scipy CSR (or anything ``scipy.sparse.csr_matrix`` accepts, incl. dense) -> DeviceCSR."""
+    """scipy CSR (or anything ``scipy.sparse.csr_matrix`` accepts, incl. dense) or PinnedCSR -> DeviceCSR."""
     import scipy.sparse as sp
 
+    if isinstance(X, DeviceCSR):
+        return X
+    if isinstance(X, PinnedCSR):
+        dev = _require_cuda()
+        return DeviceCSR(X.indptr.to(dev, non_blocking=True), X.indices.to(dev, non_blocking=True),
+                         X.data.to(dev, non_blocking=True), tuple(X.shape))
     if not sp.issparse(X) or X.format != "csr":
         X = sp.csr_matrix(X)
     return DeviceCSR(to_device(X.indptr, torch.int64), to_device(X.indices, torch.int32),
