@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--n", type=int, default=WORKLOAD["n"], help="spots (debug: smaller workloads)")
     ap.add_argument("--g", type=int, default=WORKLOAD["g"], help="genes per GPU")
     ap.add_argument("--k", type=int, default=WORKLOAD["k"])
-    ap.add_argument("--variant", type=int, default=0, help="kernel variant (tuning)")
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("CHR_MORAN_VARIANT", "0")), help="kernel variant (tuning)")
     ap.add_argument("--sweep", default="", help="comma list of kernel variants to time (kernel ms only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

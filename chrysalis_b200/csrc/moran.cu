@@ -89,9 +89,6 @@ moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t nco
 
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) p = ldg_f4(pilot + col);
-    const float kf = (float)k;
-    const float4 kp = make_float4(kf * p.x, kf * p.y, kf * p.z, kf * p.w);
-
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 f1 = zero, f2 = zero, fw = zero, fs = zero, fq = zero;
     Acc4 a1{}, a2{}, aw{}, as{}, aq{};
@@ -115,9 +112,10 @@ moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t nco
             for (int j = 0; j < K; ++j) {
                 const int nj = __shfl_sync(0xffffffffu, my, j);
                 if (active) {
-                    const float4 v = ldg_f4(Xc + (int64_t)nj * ld);
-                    f4_add(s, v);
+                    float4 v = ldg_f4(Xc + (int64_t)nj * ld);
                     if (GEARY) f4_sqdiff(fq, x, v);
+                    v.x -= p.x; v.y -= p.y; v.z -= p.z; v.w -= p.w;
+                    f4_add(s, v);
                 }
             }
         } else {
@@ -129,15 +127,15 @@ moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t nco
                 for (int j = 0; j < kk; ++j) {
                     const int nj = __shfl_sync(0xffffffffu, my, j);
                     if (active) {
-                        const float4 v = ldg_f4(Xc + (int64_t)nj * ld);
-                        f4_add(s, v);
+                        float4 v = ldg_f4(Xc + (int64_t)nj * ld);
                         if (GEARY) f4_sqdiff(fq, x, v);
+                        v.x -= p.x; v.y -= p.y; v.z -= p.z; v.w -= p.w;
+                        f4_add(s, v);
                     }
                 }
             }
         }
         x.x -= p.x; x.y -= p.y; x.z -= p.z; x.w -= p.w;
-        s.x -= kp.x; s.y -= kp.y; s.z -= kp.z; s.w -= kp.w;
         f4_add(f1, x);
         f4_fma(f2, x, x);
         f4_fma(fw, x, s);
@@ -173,6 +171,189 @@ moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t nco
     if (GEARY) reduce_store(aq, 4);
 }
 
+// =============================================================================================
+// v2 streaming kernel.  Same mathematics, restructured after the first ncu capture
+// (profiles/r1a: 243 instructions and ~1700 cycles per spot-row, issue 57 %, 16 warps/SM):
+//   * W's neighbour lists are staged in shared memory, 128 spots at a time, by cp.async one
+//     chunk ahead, so the gather addresses never wait on a global load
+//   * every warp works on U = 2 spots at once: 18 independent 512-byte row loads in flight
+//   * all arithmetic is packed f32x2 (FADD2 / FFMA2): half the issue slots of scalar FP32
+//   * accumulation is two-level fp32 in registers (16 spots, then 16 x 16 spots); a CTA covers
+//     only 2048 spots, partial sums leave the CTA as fp64 - no fp64 and no F2F in the loop
+//   * row addresses are one IMAD.WIDE.U32 each (row index x row bytes + base)
+// =============================================================================================
+typedef unsigned long long f2_t;  // two packed fp32 values in a 64-bit register pair
+
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) { f2_t c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_pack(float x, float y) { f2_t c; asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(x), "f"(y)); return c; }
+__device__ __forceinline__ void f2_unpack(f2_t v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+
+struct Row4 {  // four consecutive genes of one spot
+    f2_t a, b;
+};
+__device__ __forceinline__ Row4 ld_row4(const char* p) {
+    Row4 r;
+    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void r4_add(Row4& s, const Row4& v) { s.a = f2_add(s.a, v.a); s.b = f2_add(s.b, v.b); }
+__device__ __forceinline__ void r4_sub(Row4& s, const Row4& v) { s.a = f2_sub(s.a, v.a); s.b = f2_sub(s.b, v.b); }
+__device__ __forceinline__ void r4_fma(Row4& s, const Row4& x, const Row4& y) { s.a = f2_fma(x.a, y.a, s.a); s.b = f2_fma(x.b, y.b, s.b); }
+__device__ __forceinline__ void r4_sqdiff(Row4& q, const Row4& x, const Row4& v) {
+    Row4 d = x;
+    r4_sub(d, v);
+    r4_fma(q, d, d);
+}
+
+constexpr int kV2Chunk = 128;                 // spots whose neighbour lists are staged at once
+constexpr int kV2PerWarp = kV2Chunk / kMoranWarps;  // 16 = level-1 accumulation length
+constexpr int kV2SpotsPerCta = 2048;          // 16 chunks -> level-2 accumulation length 16
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int K, bool GEARY, int MINB>
+__global__ void __launch_bounds__(kMoranThreads, MINB)
+moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ nbr,
+                    int k_rt, int nbr_vec16, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
+    const int k = K ? K : k_rt;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* s_idx = reinterpret_cast<int32_t*>(smem_raw);           // [2][kV2Chunk * k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
+    int64_t col = tile_col + lane * 4;
+    if (col >= ncol) col = tile_col;                                  // idle lanes shadow lane 0 (results unused)
+    const char* __restrict__ base = reinterpret_cast<const char*>(X + col);
+    const int64_t s_begin = (int64_t)blockIdx.y * kV2SpotsPerCta;
+    const int64_t s_end = s_begin + kV2SpotsPerCta < n ? s_begin + kV2SpotsPerCta : n;
+    const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
+
+    const float4 pf = __ldg(reinterpret_cast<const float4*>(pilot + col));
+    Row4 p;
+    p.a = f2_pack(pf.x, pf.y);
+    p.b = f2_pack(pf.z, pf.w);
+
+    const f2_t z2 = f2_pack(0.f, 0.f);
+    Row4 l1[kNStat], l2[kNStat];
+#pragma unroll
+    for (int s = 0; s < kNStat; ++s) { l1[s].a = l1[s].b = z2; l2[s].a = l2[s].b = z2; }
+
+    auto stage = [&](int buf, int64_t c0) {   // neighbour lists of spots [c0, c0 + chunk) -> smem
+        int32_t* dst = s_idx + buf * kV2Chunk * k;
+        const int64_t rem = (n - c0 < kV2Chunk ? n - c0 : kV2Chunk) * k;   // valid ints
+        const int32_t* src = nbr + c0 * k;
+        if (nbr_vec16) {
+            for (int t = threadIdx.x * 4; t < rem; t += kMoranThreads * 4) cp_async_16(dst + t, src + t);   // rem % 4 == 0 when k % 4 == 0, else scalar path
+        } else {
+            for (int t = threadIdx.x; t < rem; t += kMoranThreads) cp_async_4(dst + t, src + t);
+        }
+        cp_async_commit();
+    };
+
+    auto accumulate = [&](Row4 x, Row4 s) {   // s is already a sum of shifted values
+        r4_sub(x, p);
+        r4_add(l1[0], x);
+        r4_fma(l1[1], x, x);
+        r4_fma(l1[2], x, s);
+        r4_add(l1[3], s);
+    };
+
+    stage(0, s_begin);
+    int buf = 0;
+    for (int64_t c0 = s_begin; c0 < s_end; c0 += kV2Chunk, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();                                              // chunk `buf` visible; previous chunk fully consumed
+        if (c0 + kV2Chunk < s_end) stage(buf ^ 1, c0 + kV2Chunk);
+        const int32_t* my_idx = s_idx + buf * kV2Chunk * k + warp * kV2PerWarp * k;
+        const int64_t w0 = c0 + warp * kV2PerWarp;
+        // pull this warp's next chunk of own rows towards L2 while the current one is consumed
+        if (lane < kV2PerWarp) {
+            const int64_t ip = w0 + kV2Chunk + lane;
+            if (ip < s_end) l2_prefetch_bulk(reinterpret_cast<const char*>(X + tile_col) + (uint64_t)ip * row_bytes, tile_bytes);
+        }
+#pragma unroll 1
+        for (int it = 0; it < kV2PerWarp; it += 2) {
+            const int64_t i0 = w0 + it, i1 = i0 + 1;
+            if (i0 >= s_end) break;
+            const bool has1 = i1 < s_end;
+            const uint32_t r0 = (uint32_t)i0, r1 = (uint32_t)(has1 ? i1 : i0);
+            const int32_t* idx0 = my_idx + it * k;
+            const int32_t* idx1 = has1 ? idx0 + k : idx0;
+            Row4 x0 = ld_row4(base + (uint64_t)r0 * row_bytes);
+            Row4 x1 = ld_row4(base + (uint64_t)r1 * row_bytes);
+            Row4 s0, s1;
+            s0.a = s0.b = s1.a = s1.b = z2;
+            if constexpr (K > 0) {
+                Row4 v0[K], v1[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    v0[j] = ld_row4(base + (uint64_t)(uint32_t)idx0[j] * row_bytes);
+                    v1[j] = ld_row4(base + (uint64_t)(uint32_t)idx1[j] * row_bytes);
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (GEARY) { r4_sqdiff(l1[4], x0, v0[j]); if (has1) r4_sqdiff(l1[4], x1, v1[j]); }
+                    r4_sub(v0[j], p);                                  // shift before summing: partial sums stay O(std)
+                    r4_sub(v1[j], p);
+                    r4_add(s0, v0[j]);
+                    r4_add(s1, v1[j]);
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < k; ++j) {
+                    Row4 v0 = ld_row4(base + (uint64_t)(uint32_t)idx0[j] * row_bytes);
+                    Row4 v1 = ld_row4(base + (uint64_t)(uint32_t)idx1[j] * row_bytes);
+                    if (GEARY) { r4_sqdiff(l1[4], x0, v0); if (has1) r4_sqdiff(l1[4], x1, v1); }
+                    r4_sub(v0, p);
+                    r4_sub(v1, p);
+                    r4_add(s0, v0);
+                    r4_add(s1, v1);
+                }
+            }
+            accumulate(x0, s0);
+            if (has1) accumulate(x1, s1);
+        }
+        // level-1 -> level-2 (every 16 spots of this warp)
+#pragma unroll
+        for (int s = 0; s < kNStat; ++s) {
+            if (s == 4 && !GEARY) break;
+            r4_add(l2[s], l1[s]);
+            l1[s].a = l1[s].b = z2;
+        }
+    }
+
+    // level-2 -> fp64, cross-warp reduction in fixed order, one statistic at a time
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(smem_raw);               // [kMoranWarps][kGeneTile] (reuses the index buffers)
+#pragma unroll
+    for (int st = 0; st < kNStat; ++st) {
+        if (st == 4 && !GEARY) break;
+        float f0, f1, f2, f3;
+        f2_unpack(l2[st].a, f0, f1);
+        f2_unpack(l2[st].b, f2, f3);
+        red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
+        red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
+        red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
+        red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
+        __syncthreads();
+        if (threadIdx.x < kGeneTile) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kMoranWarps; ++w) t += red[w * kGeneTile + threadIdx.x];
+            part[((int64_t)blockIdx.y * kNStat + st) * gpad + tile_col + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- finalize: fixed-order sum of the split partials, then the statistic in fp64 ------------
 __global__ void moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad, int64_t g, int64_t n, int k,
                                       const float* __restrict__ pilot, bool geary, double* __restrict__ out_I,
@@ -204,9 +385,9 @@ struct MoranPlan {
     size_t pilot_off, part_off, total;
 };
 
-static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld) {
+static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld, bool v2) {
     MoranPlan p;
-    p.spots_per_split = moran_spots_per_split(n);
+    p.spots_per_split = v2 ? kV2SpotsPerCta : moran_spots_per_split(n);
     p.nsplit = (int)ceil_div<int64_t>(n, p.spots_per_split);
     p.ntile = (int)ceil_div<int64_t>(ld, kGeneTile);
     p.gpad = (int64_t)p.ntile * kGeneTile;
@@ -236,7 +417,9 @@ extern "C" {
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags) {
     (void)k; (void)flags;
     if (n_spots <= 0 || n_genes <= 0) return 256;
-    return chr::moran_plan(n_spots, n_genes, chr::round_up<int64_t>(n_genes, 4)).total + 512;
+    const int64_t ldc = chr::round_up<int64_t>(n_genes, 4);
+    const size_t a = chr::moran_plan(n_spots, n_genes, ldc, false).total, b = chr::moran_plan(n_spots, n_genes, ldc, true).total;
+    return (a > b ? a : b) + 512;
 }
 
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld, const int32_t* nbr, int k,
@@ -256,7 +439,9 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
 
     // the kernel reads ld columns; statistics are kept for the first round_up(n_genes,4) <= ld
     const int64_t ldc = round_up<int64_t>(n_genes, 4);
-    MoranPlan p = moran_plan(n_spots, n_genes, ldc);
+    const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
+    const bool v2 = variant >= 4;
+    MoranPlan p = moran_plan(n_spots, n_genes, ldc, v2);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* pilot = (float*)(ws + p.pilot_off);
@@ -270,8 +455,31 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
     timer_begin(CHR_FAMILY_MORAN, timing, st);
 #define CHR_ARGS k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad
-    const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
-    if (geary) launch_ell<true, 2, 8>(CHR_ARGS);
+    if (v2) {
+        CHR_REQUIRE(n_spots < (1LL << 32) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: v2 kernel needs n_spots, row bytes < 2^32");
+        const int vec16 = (k % 4 == 0) && (((uintptr_t)nbr & 15) == 0);
+        size_t smem = (size_t)2 * kV2Chunk * k * sizeof(int32_t);
+        if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
+        const uint32_t rb = (uint32_t)(ld * 4);
+#define CHR_V2(KK, GG, MB)                                                                                          \
+    do {                                                                                                            \
+        auto kern = moran_stream_kernel<KK, GG, MB>;                                                               \
+        if (smem > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, nbr, k, vec16, pilot, part, p.gpad);        \
+    } while (0)
+#define CHR_V2K(GG, MB)                                  \
+    switch (k) {                                         \
+        case 4: CHR_V2(4, GG, MB); break;                \
+        case 6: CHR_V2(6, GG, MB); break;                \
+        case 8: CHR_V2(8, GG, MB); break;                \
+        default: CHR_V2(0, GG, MB); break;               \
+    }
+        if (geary) { CHR_V2K(true, 1) }
+        else if (variant == 5) { CHR_V2K(false, 1) }
+        else { CHR_V2K(false, 2) }
+#undef CHR_V2K
+#undef CHR_V2
+    } else if (geary) launch_ell<true, 2, 8>(CHR_ARGS);
     else switch (variant) {
         case 1: launch_ell<false, 2, 0>(CHR_ARGS); break;   // no prefetch
         case 2: launch_ell<false, 2, 32>(CHR_ARGS); break;  // far prefetch

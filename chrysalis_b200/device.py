@@ -6,6 +6,7 @@ kernels).  There is no CPU fallback: without CUDA or without the library these r
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -154,7 +155,7 @@ def knn_build(xy: torch.Tensor, k: int, bbox: torch.Tensor | None = None) -> tor
 # ---- K3 / K4 -----------------------------------------------------------------------------
 
 def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, geary: bool = False,
-                timing: bool = False, want_stats: bool = False, variant: int = 0):
+                timing: bool = False, want_stats: bool = False, variant: int | None = None):
     """Moran's I (and Geary's C) of every column of the dense [n, ld] float32 matrix ``X``.
 
     Returns ``(I, C, stats)`` float64 device tensors (``C``/``stats`` None unless requested).
@@ -165,6 +166,8 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     assert X.shape[0] == n
     ld = X.stride(0)
     g = X.shape[1] if n_genes is None else n_genes
+    if variant is None:
+        variant = int(os.environ.get("CHR_MORAN_VARIANT", "0"))   # kernel-variant override for tuning runs
     flags = (_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (variant << _lib.VARIANT_SHIFT)
     ws_bytes = _lib.query("chr_moran_workspace_bytes", n, g, k, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)

@@ -1,8 +1,10 @@
 """GPU parity of the SVG stage (K1-K4) against the CPU oracle - all calls go through the C ABI.
 
-Tolerance: Moran's I within 1e-5 relative (north_star).  The oracle computes z in float32 like
-the reference (core.py:59 -> esda), so for |I| below ~1e-3 its own rounding noise exceeds
-1e-5*|I|; there the bound is 1e-8 absolute and the float64 oracle is the arbiter.
+Tolerance: Moran's I within 1e-5 relative (north_star) plus an absolute floor of 2e-7: the
+reference's input is float32 (core.py:59 ad.to_df()), and float32 rounding of z alone moves I
+by ~1e-7 - the oracle's float32 and float64 statements differ by that much on the golden data
+(tests/test_oracle.py::test_matches_in_repo_dense_formula), so nothing tighter is meaningful
+for |I| < 0.02.  Exact known answers on lattices are held to 1e-12.
 """
 import numpy as np
 import pytest
@@ -18,7 +20,7 @@ from oracle import weights as ow
 
 pytestmark = pytest.mark.gpu
 
-RTOL, ATOL = 1e-5, 1e-8
+RTOL, ATOL = 1e-5, 2e-7
 
 
 def assert_close(got, ref, rtol=RTOL, atol=ATOL, what="I"):
@@ -92,6 +94,9 @@ def test_constant_and_highly_expressed_genes():
     keep = [0, 1, 3]
     # judged against the float64 statistic of the same float32 inputs
     assert_close(I[keep], ref64[keep], rtol=1e-5, atol=2e-7)
+    # and the float32-faithful oracle is no closer to the float64 truth than the kernel is
+    ref32 = om.morans_I_loop(dense[:, keep], nbr)
+    assert np.abs(I[keep] - ref64[keep]).max() <= max(3 * np.abs(ref32 - ref64[keep]).max(), 2e-7)
 
 
 def test_known_answers_on_torus_lattice():
@@ -137,12 +142,12 @@ def test_invariances_full_spot_count():
     nb = torch.from_numpy(nbr).cuda()
     I, _, _ = dv.moran_dense(Xd, nb, g)
     I2, _, _ = dv.moran_dense(Xd * 3.0 + 1.5, nb, g)             # affine invariance
-    assert_close(I2.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=1e-8)
+    assert_close(I2.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=2e-8)
     perm = torch.randperm(n, device="cuda", generator=gen)        # relabel spots
     inv = torch.empty_like(perm); inv[perm] = torch.arange(n, device="cuda")
     nb_p = inv[nb[perm].long()].to(torch.int32).contiguous()
     I3, _, _ = dv.moran_dense(Xd[perm].contiguous(), nb_p, g)
-    assert_close(I3.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=1e-8)
+    assert_close(I3.cpu().numpy(), I.cpu().numpy(), rtol=2e-6, atol=2e-8)
     I4, _, _ = dv.moran_dense(Xd, nb, g)                          # run-to-run bit reproducibility
     assert torch.equal(I4, I)
     cols = [0, 1, 17, 48, 95]
