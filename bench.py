@@ -260,7 +260,12 @@ def run_native(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "moran_ell_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    kern_lists = {1: ["moran_pilot_kernel", "moran_ell_kernel", "moran_finalize_kernel"],
+                  4: ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"]}
+    kernels = kern_lists.get(args.variant, ["moran_pilot_kernel", "moran_pair_plan_kernel", "moran_pair_kernel",
+                                            "moran_finalize_kernel"])
+    main_kernel = [x for x in kernels if x not in ("moran_pilot_kernel", "moran_pair_plan_kernel", "moran_finalize_kernel")][0]
+    roofline = {"bound": "hbm", "kernel": main_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
                 "kernel_share_of_step": round(kernel_ms / ms_per_step, 4)}
@@ -275,8 +280,8 @@ def run_native(args):
                    "neighbors": k, "ld": ld, "counts_density": round(density, 4), "parallelism": f"gene-shard x{world}",
                    "l2_policy": "inputs_exceed_l2 (X = %.1f GB per GPU >> 126 MB L2)" % (4.0 * n * ld / 1e9),
                    "variant": args.variant, "setup_s": round(setup_s, 1)},
-        "roofline": roofline, "clocks": clocks, "gpu_launches": 3 * args.steps,
-        "kernels_per_step": ["moran_pilot_kernel", "moran_ell_kernel", "moran_finalize_kernel"],
+        "roofline": roofline, "clocks": clocks, "gpu_launches": len(kernels) * args.steps,
+        "kernels_per_step": kernels,
     }
     if sweep:
         out["variant_sweep"] = sweep

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libchrysalis_b200.so")
 
 FLAG_GEARY = 0x1
 FLAG_TIMING = 0x2
+FLAG_PRESHIFTED = 0x4
 VARIANT_SHIFT = 8
 FAMILY_MORAN, FAMILY_GRAM, FAMILY_AA, FAMILY_KNN, FAMILY_PREP = range(5)
 

@@ -354,6 +354,230 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
     }
 }
 
+// =============================================================================================
+// v3 pair kernel.  The r1b capture showed the v2 kernel pinned on the L1 data pipe (72 % of its
+// wavefront peak: 9 x 512-byte row reads per spot).  Consecutive spots of the Hilbert order
+// are spatial neighbours and share most of their neighbourhood (union of two closed
+// neighbourhoods: 12.1 rows instead of 18 on a square lattice, 10 on a hex lattice, 12.1 on
+// random points), so spots are processed in PAIRS (a, b) = (2q, 2q+1) and W is re-expressed
+// per pair as three disjoint lists
+//        only-a | common | only-b        (+ flags  b in N(a),  a in N(b))
+//   s_a = sum(only-a) + sum(common) [+ x_b],   s_b = sum(only-b) + sum(common) [+ x_a]
+// which needs 6 row reads and 5.5 adds per spot instead of 9 and 8.  The plan is built from
+// the kNN lists by moran_pair_plan_kernel; lists with duplicate entries or odd shapes take a
+// generic per-spot path (results are identical either way, only the summation order differs).
+// =============================================================================================
+constexpr int kPairRecPad = 4;   // ints before the index list: meta, 3 x pad (keeps lists 16-byte aligned)
+__host__ __device__ constexpr int pair_stride(int k) { return (2 * k + kPairRecPad + 3) & ~3; }   // ints per pair record
+
+__host__ __device__ constexpr int pair_ncm(int K) { return K / 2; }
+__host__ __device__ constexpr int pair_nam(int K) { return K / 2 + (K <= 4 ? 1 : 0); }
+
+// meta: n_a | n_c << 8 | n_b << 16 | fa << 24 | fb << 25 | fast << 26 | has_b << 27
+__global__ void moran_pair_plan_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int ncm, int nam,
+                                       int32_t* __restrict__ plan) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t npairs = (n + 1) / 2;
+    if (q >= npairs) return;
+    const int64_t a = 2 * q, b = 2 * q + 1;
+    const bool hasb = b < n;
+    const int stride = pair_stride(k);
+    int32_t* rec = plan + q * stride;
+    const int32_t* A = nbr + a * k;
+    const int32_t* B = nbr + (hasb ? b : a) * k;
+    bool simple = hasb;
+    for (int i = 0; i < k && simple; ++i)
+        for (int j = i + 1; j < k; ++j)
+            if (A[i] == A[j] || B[i] == B[j]) { simple = false; break; }
+    int na = 0, nc = 0, nb = 0, fa = 0, fb = 0;
+    int32_t* out = rec + kPairRecPad;
+    if (!hasb) {
+        for (int i = 0; i < k; ++i) out[na++] = A[i];
+    } else if (!simple) {
+        for (int i = 0; i < k; ++i) out[na++] = A[i];
+        for (int i = 0; i < k; ++i) out[na + nb++] = B[i];
+    } else {
+        // only-a
+        for (int i = 0; i < k; ++i) {
+            const int32_t x = A[i];
+            if (x == (int32_t)b) { fa = 1; continue; }
+            bool inB = false;
+            for (int j = 0; j < k; ++j) inB |= (B[j] == x);
+            if (!inB) out[na++] = x;
+        }
+        // common (order of A)
+        for (int i = 0; i < k; ++i) {
+            const int32_t x = A[i];
+            if (x == (int32_t)b) continue;
+            bool inB = false;
+            for (int j = 0; j < k; ++j) inB |= (B[j] == x);
+            if (inB) out[na + nc++] = x;
+        }
+        // only-b
+        for (int i = 0; i < k; ++i) {
+            const int32_t x = B[i];
+            if (x == (int32_t)a) { fb = 1; continue; }
+            bool inA = false;
+            for (int j = 0; j < k; ++j) inA |= (A[j] == x && x != (int32_t)b);
+            if (!inA) out[na + nc + nb++] = x;
+        }
+    }
+    for (int i = na + nc + nb; i < stride - kPairRecPad; ++i) out[i] = (int32_t)a;   // padding: a valid row
+    const int fast = (hasb && simple && nc <= ncm && na <= nam && nb <= nam) ? 1 : 0;
+    rec[0] = na | (nc << 8) | (nb << 16) | (fa << 24) | (fb << 25) | (fast << 26) | ((hasb ? 1 : 0) << 27);
+    rec[1] = rec[2] = rec[3] = 0;
+}
+
+constexpr int kV3PairsPerWarp = 8;                               // 16 spots: level-1 accumulation length
+constexpr int kV3ChunkPairs = kV3PairsPerWarp * kMoranWarps;     // 64 pairs = 128 spots per CTA chunk
+
+template <int K, bool SHIFT, int MINB>
+__global__ void __launch_bounds__(kMoranThreads, MINB)
+moran_pair_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ plan,
+                  int k_rt, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
+    const int k = K ? K : k_rt;
+    const int stride = pair_stride(k);                            // ints per pair record (multiple of 4)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* s_plan = reinterpret_cast<int32_t*>(smem_raw);       // [2][kV3ChunkPairs * stride]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
+    int64_t col = tile_col + lane * 4;
+    if (col >= ncol) col = tile_col;
+    const char* __restrict__ base = reinterpret_cast<const char*>(X + col);
+    const int64_t s_begin = (int64_t)blockIdx.y * kV2SpotsPerCta;
+    const int64_t s_end = s_begin + kV2SpotsPerCta < n ? s_begin + kV2SpotsPerCta : n;
+    const int64_t q_begin = s_begin / 2, q_end = (s_end + 1) / 2;  // kV2SpotsPerCta is even
+    const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
+
+    Row4 p;
+    p.a = p.b = f2_pack(0.f, 0.f);
+    if (SHIFT) {
+        const float4 pf = __ldg(reinterpret_cast<const float4*>(pilot + col));
+        p.a = f2_pack(pf.x, pf.y);
+        p.b = f2_pack(pf.z, pf.w);
+    }
+    const f2_t z2 = f2_pack(0.f, 0.f);
+    Row4 l1[4], l2[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { l1[s].a = l1[s].b = z2; l2[s].a = l2[s].b = z2; }
+
+    auto ld_shifted = [&](uint32_t row) {
+        Row4 v = ld_row4(base + (uint64_t)row * row_bytes);
+        if (SHIFT) r4_sub(v, p);
+        return v;
+    };
+    auto accumulate = [&](const Row4& x, const Row4& s) {
+        r4_add(l1[0], x);
+        r4_fma(l1[1], x, x);
+        r4_fma(l1[2], x, s);
+        r4_add(l1[3], s);
+    };
+    // each warp stages the records of its own 8 pairs of a chunk (no CTA barrier on the way)
+    const int warp_ints = kV3PairsPerWarp * stride;
+    auto stage = [&](int buf, int64_t q0) {
+        int32_t* dst = s_plan + (buf * kV3ChunkPairs + warp * kV3PairsPerWarp) * stride;
+        const int64_t qw = q0 + warp * kV3PairsPerWarp;
+        int64_t rem = (q_end - qw) * stride;
+        if (rem > warp_ints) rem = warp_ints;
+        const int32_t* src = plan + qw * stride;
+        for (int t = lane * 4; t < rem; t += 128) cp_async_16(dst + t, src + t);
+        cp_async_commit();
+    };
+
+    stage(0, q_begin);
+    int buf = 0, chunk_no = 0;
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += kV3ChunkPairs, buf ^= 1, ++chunk_no) {
+        cp_async_wait_all();
+        __syncwarp();
+        if ((chunk_no & 3) == 3) __syncthreads();                 // keep the warps of a CTA within 4 chunks of each other (L1 sharing)
+        if (q0 + kV3ChunkPairs < q_end) stage(buf ^ 1, q0 + kV3ChunkPairs);
+        const int32_t* my = s_plan + (buf * kV3ChunkPairs + warp * kV3PairsPerWarp) * stride;
+        const int64_t qw = q0 + warp * kV3PairsPerWarp;
+        if (lane < 2 * kV3PairsPerWarp) {                          // own rows of this warp's slice of the next chunk -> L2
+            const int64_t ip = 2 * (qw + kV3ChunkPairs) + lane;
+            if (ip < s_end) l2_prefetch_bulk(reinterpret_cast<const char*>(X + tile_col) + (uint64_t)ip * row_bytes, tile_bytes);
+        }
+#pragma unroll 1
+        for (int pi = 0; pi < kV3PairsPerWarp; ++pi) {
+            const int64_t q = qw + pi;
+            if (q >= q_end) break;
+            const int32_t* rec = my + pi * stride;
+            const int meta = rec[0];
+            const int na = meta & 0xff, nc = (meta >> 8) & 0xff, nb = (meta >> 16) & 0xff;
+            const bool fa = (meta >> 24) & 1, fb = (meta >> 25) & 1, fast = (meta >> 26) & 1, hasb = (meta >> 27) & 1;
+            const int32_t* idx = rec + kPairRecPad;
+            const uint32_t ra = (uint32_t)(2 * q), rb = hasb ? ra + 1 : ra;
+            const Row4 xa = ld_shifted(ra);
+            const Row4 xb = ld_shifted(rb);
+            Row4 sa, sb;
+            sa.a = sa.b = sb.a = sb.b = z2;
+            bool done = false;
+            if constexpr (K > 0) {
+                if (fast) {
+                    constexpr int NCM = pair_ncm(K), NAM = pair_nam(K);
+                    Row4 va[NAM], vc[NCM], vb[NAM];
+#pragma unroll
+                    for (int j = 0; j < NAM; ++j) if (j < na) va[j] = ld_shifted((uint32_t)idx[j]);
+#pragma unroll
+                    for (int j = 0; j < NCM; ++j) if (j < nc) vc[j] = ld_shifted((uint32_t)idx[na + j]);
+#pragma unroll
+                    for (int j = 0; j < NAM; ++j) if (j < nb) vb[j] = ld_shifted((uint32_t)idx[na + nc + j]);
+                    Row4 sc;
+                    sc.a = sc.b = z2;
+#pragma unroll
+                    for (int j = 0; j < NCM; ++j) if (j < nc) r4_add(sc, vc[j]);
+                    sa = sc;
+                    sb = sc;
+#pragma unroll
+                    for (int j = 0; j < NAM; ++j) if (j < na) r4_add(sa, va[j]);
+#pragma unroll
+                    for (int j = 0; j < NAM; ++j) if (j < nb) r4_add(sb, vb[j]);
+                    if (fa) r4_add(sa, xb);
+                    if (fb) r4_add(sb, xa);
+                    done = true;
+                }
+            }
+            if (!done) {   // generic per-spot path: a reads only-a|common, b reads common|only-b
+                const int la = na + nc, lb = nc + nb;
+#pragma unroll 4
+                for (int j = 0; j < la; ++j) r4_add(sa, ld_shifted((uint32_t)idx[j]));
+#pragma unroll 4
+                for (int j = 0; j < lb; ++j) r4_add(sb, ld_shifted((uint32_t)idx[na + j]));
+                if (fa) r4_add(sa, xb);
+                if (fb) r4_add(sb, xa);
+            }
+            accumulate(xa, sa);
+            if (hasb) accumulate(xb, sb);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            r4_add(l2[s], l1[s]);
+            l1[s].a = l1[s].b = z2;
+        }
+    }
+
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(smem_raw);
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        float f0, f1, f2, f3;
+        f2_unpack(l2[st].a, f0, f1);
+        f2_unpack(l2[st].b, f2, f3);
+        red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
+        red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
+        red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
+        red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
+        __syncthreads();
+        if (threadIdx.x < kGeneTile) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kMoranWarps; ++w) t += red[w * kGeneTile + threadIdx.x];
+            part[((int64_t)blockIdx.y * kNStat + st) * gpad + tile_col + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- finalize: fixed-order sum of the split partials, then the statistic in fp64 ------------
 __global__ void moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad, int64_t g, int64_t n, int k,
                                       const float* __restrict__ pilot, bool geary, double* __restrict__ out_I,
@@ -372,7 +596,7 @@ __global__ void moran_finalize_kernel(const double* __restrict__ part, int nspli
     out_I[col] = zwz / zz;
     if (geary && out_C) out_C[col] = (dn - 1.0) * (S[4] / dk) / (2.0 * dn * zz);
     if (out_stats) {
-        out_stats[0 * g + col] = m + (double)pilot[col];
+        out_stats[0 * g + col] = m + (double)pilot[col];   // pilot is all-zero for pre-shifted input
         out_stats[1 * g + col] = zz;
         out_stats[2 * g + col] = zwz;
         out_stats[3 * g + col] = geary ? S[4] / dk : 0.0;
@@ -382,10 +606,10 @@ __global__ void moran_finalize_kernel(const double* __restrict__ part, int nspli
 struct MoranPlan {
     int64_t spots_per_split, gpad;
     int nsplit, ntile;
-    size_t pilot_off, part_off, total;
+    size_t pilot_off, part_off, pair_off, total;
 };
 
-static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld, bool v2) {
+static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld, bool v2, int k) {
     MoranPlan p;
     p.spots_per_split = v2 ? kV2SpotsPerCta : moran_spots_per_split(n);
     p.nsplit = (int)ceil_div<int64_t>(n, p.spots_per_split);
@@ -393,7 +617,8 @@ static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld, bool v2) {
     p.gpad = (int64_t)p.ntile * kGeneTile;
     p.pilot_off = 0;
     p.part_off = round_up<size_t>((size_t)p.gpad * sizeof(float), 256);
-    p.total = p.part_off + (size_t)p.nsplit * kNStat * p.gpad * sizeof(double);
+    p.pair_off = round_up<size_t>(p.part_off + (size_t)p.nsplit * kNStat * p.gpad * sizeof(double), 256);
+    p.total = p.pair_off + (size_t)((n + 1) / 2) * pair_stride(k) * sizeof(int32_t);
     return p;
 }
 
@@ -415,10 +640,11 @@ static void launch_ell(int k, dim3 grid, cudaStream_t st, const float* X, int64_
 extern "C" {
 
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags) {
-    (void)k; (void)flags;
+    (void)flags;
     if (n_spots <= 0 || n_genes <= 0) return 256;
     const int64_t ldc = chr::round_up<int64_t>(n_genes, 4);
-    const size_t a = chr::moran_plan(n_spots, n_genes, ldc, false).total, b = chr::moran_plan(n_spots, n_genes, ldc, true).total;
+    const int kk = k > 0 ? k : 1;
+    const size_t a = chr::moran_plan(n_spots, n_genes, ldc, false, kk).total, b = chr::moran_plan(n_spots, n_genes, ldc, true, kk).total;
     return (a > b ? a : b) + 512;
 }
 
@@ -440,8 +666,13 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     // the kernel reads ld columns; statistics are kept for the first round_up(n_genes,4) <= ld
     const int64_t ldc = round_up<int64_t>(n_genes, 4);
     const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
-    const bool v2 = variant >= 4;
-    MoranPlan p = moran_plan(n_spots, n_genes, ldc, v2);
+    const bool preshifted = flags & CHR_FLAG_PRESHIFTED;
+    // variant 0: pair kernel (v3); Geary's C rides the v2 stream kernel.  1: v1, 4: v2, 6: v3 (tuning / regression)
+    const bool v1 = variant == 1 && !geary;
+    const bool v3 = !geary && (variant == 0 || variant == 6 || variant == 7);
+    const bool v2 = !v1;   // v2 and v3 share the 2048-spot split structure
+    CHR_REQUIRE(!preshifted || v3, "chr_moran_dense_f32: CHR_FLAG_PRESHIFTED is only supported by the default (pair) kernel without Geary");
+    MoranPlan p = moran_plan(n_spots, n_genes, ldc, v2, k);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* pilot = (float*)(ws + p.pilot_off);
@@ -449,18 +680,49 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
 
     // columns the kernels touch: [0, ncol), ncol % 4 == 0, ncol <= ld and <= gpad
     const int64_t ncol = ldc;
-    moran_pilot_kernel<<<(unsigned)ceil_div<int64_t>(ncol, 256), 256, 0, st>>>(X, n_spots, ld, ncol, pilot);
+    if (preshifted) CHR_CUDA(cudaMemsetAsync(pilot, 0, (size_t)p.gpad * sizeof(float), st));
+    else moran_pilot_kernel<<<(unsigned)ceil_div<int64_t>(ncol, 256), 256, 0, st>>>(X, n_spots, ld, ncol, pilot);
     CHR_LAUNCH_CHECK();
 
     dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
-    timer_begin(CHR_FAMILY_MORAN, timing, st);
 #define CHR_ARGS k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad
-    if (v2) {
+    if (v3) {
+        CHR_REQUIRE(n_spots < (1LL << 31) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: pair kernel needs n_spots < 2^31, row bytes < 2^32");
+        CHR_REQUIRE(k <= 120, "chr_moran_dense_f32: pair kernel supports k <= 120");
+        int32_t* pair_plan = (int32_t*)(ws + p.pair_off);
+        const int64_t npairs = (n_spots + 1) / 2;
+        const int ncm = (k == 4 || k == 6 || k == 8) ? pair_ncm(k) : -1, nam = (k == 4 || k == 6 || k == 8) ? pair_nam(k) : -1;
+        moran_pair_plan_kernel<<<(unsigned)ceil_div<int64_t>(npairs, 128), 128, 0, st>>>(nbr, n_spots, k, ncm, nam, pair_plan);
+        CHR_LAUNCH_CHECK();
+        size_t smem = (size_t)2 * kV3ChunkPairs * pair_stride(k) * sizeof(int32_t);
+        if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
+        const uint32_t rb = (uint32_t)(ld * 4);
+        timer_begin(CHR_FAMILY_MORAN, timing, st);
+#define CHR_V3(KK, SH, MB)                                                                                          \
+    do {                                                                                                            \
+        auto kern = moran_pair_kernel<KK, SH, MB>;                                                                 \
+        if (smem > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, pair_plan, k, pilot, part, p.gpad);         \
+    } while (0)
+#define CHR_V3K(SH, MB)                                  \
+    switch (k) {                                         \
+        case 4: CHR_V3(4, SH, MB); break;                \
+        case 6: CHR_V3(6, SH, MB); break;                \
+        case 8: CHR_V3(8, SH, MB); break;                \
+        default: CHR_V3(0, SH, MB); break;               \
+    }
+        if (preshifted) { CHR_V3K(false, 2) }
+        else if (variant == 7) { CHR_V3K(true, 1) }
+        else { CHR_V3K(true, 2) }
+#undef CHR_V3K
+#undef CHR_V3
+    } else if (v2) {
         CHR_REQUIRE(n_spots < (1LL << 32) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: v2 kernel needs n_spots, row bytes < 2^32");
         const int vec16 = (k % 4 == 0) && (((uintptr_t)nbr & 15) == 0);
         size_t smem = (size_t)2 * kV2Chunk * k * sizeof(int32_t);
         if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
         const uint32_t rb = (uint32_t)(ld * 4);
+        timer_begin(CHR_FAMILY_MORAN, timing, st);
 #define CHR_V2(KK, GG, MB)                                                                                          \
     do {                                                                                                            \
         auto kern = moran_stream_kernel<KK, GG, MB>;                                                               \
@@ -475,16 +737,12 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
         default: CHR_V2(0, GG, MB); break;               \
     }
         if (geary) { CHR_V2K(true, 1) }
-        else if (variant == 5) { CHR_V2K(false, 1) }
         else { CHR_V2K(false, 2) }
 #undef CHR_V2K
 #undef CHR_V2
-    } else if (geary) launch_ell<true, 2, 8>(CHR_ARGS);
-    else switch (variant) {
-        case 1: launch_ell<false, 2, 0>(CHR_ARGS); break;   // no prefetch
-        case 2: launch_ell<false, 2, 32>(CHR_ARGS); break;  // far prefetch
-        case 3: launch_ell<false, 3, 8>(CHR_ARGS); break;   // 3 CTAs/SM
-        default: launch_ell<false, 2, 8>(CHR_ARGS); break;
+    } else {
+        timer_begin(CHR_FAMILY_MORAN, timing, st);
+        launch_ell<false, 2, 8>(CHR_ARGS);
     }
 #undef CHR_ARGS
     timer_end(CHR_FAMILY_MORAN, timing, st);

@@ -155,10 +155,11 @@ def knn_build(xy: torch.Tensor, k: int, bbox: torch.Tensor | None = None) -> tor
 # ---- K3 / K4 -----------------------------------------------------------------------------
 
 def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, geary: bool = False,
-                timing: bool = False, want_stats: bool = False, variant: int | None = None):
+                timing: bool = False, want_stats: bool = False, variant: int | None = None, preshifted: bool = False):
     """Moran's I (and Geary's C) of every column of the dense [n, ld] float32 matrix ``X``.
 
     Returns ``(I, C, stats)`` float64 device tensors (``C``/``stats`` None unless requested).
+    ``preshifted``: the columns of ``X`` already have (near-)zero mean, skip the in-kernel shift.
     """
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
     assert nbr.dtype == torch.int32 and nbr.is_contiguous()
@@ -168,7 +169,8 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     g = X.shape[1] if n_genes is None else n_genes
     if variant is None:
         variant = int(os.environ.get("CHR_MORAN_VARIANT", "0"))   # kernel-variant override for tuning runs
-    flags = (_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (variant << _lib.VARIANT_SHIFT)
+    flags = ((_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) |
+             (_lib.FLAG_PRESHIFTED if preshifted else 0) | (variant << _lib.VARIANT_SHIFT))
     ws_bytes = _lib.query("chr_moran_workspace_bytes", n, g, k, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
     out_I = torch.empty(g, dtype=torch.float64, device=X.device)

@@ -41,6 +41,7 @@ float chr_last_kernel_ms(int family);
 
 #define CHR_FLAG_GEARY 0x1u   /* also accumulate Geary's C                                  */
 #define CHR_FLAG_TIMING 0x2u  /* record events around the dominant kernel                   */
+#define CHR_FLAG_PRESHIFTED 0x4u /* Moran: columns of X were already shifted to ~zero mean (no in-kernel shift) */
 #define CHR_VARIANT_SHIFT 8   /* bits 8..15 of `flags`: kernel variant (0 = default; tuning)  */
 
 /* ---- K1: spatial weights -------------------------------------------------------------

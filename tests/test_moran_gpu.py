@@ -55,7 +55,42 @@ def test_moran_kernel_matches_golden(name, request):
     assert_close(C, z["geary"][m], what="C")
 
 
-@pytest.mark.parametrize("k", [1, 4, 6, 8, 18, 36, 40])
+@pytest.mark.parametrize("variant", [1, 4, 6, 7])
+def test_all_kernel_generations_agree(variant, golden_random):
+    """v1 (ELL), v2 (stream) and v3 (pair) kernels are kept for regression: same statistic."""
+    z = golden_random
+    m = z["gene_mask"]
+    I, _, _ = gpu_moran(dense_from(golden_csr(z), m), z["nbr"], variant=variant)
+    assert_close(I, z["morans"][m])
+
+
+def test_preshifted_input_and_odd_spot_count():
+    xy = synth.make_coords("hex", 2501, seed=9)                       # odd n: last pair has one spot
+    X, _ = synth.make_counts_csr(xy, 150, seed=9)
+    dense = dense_from(X)
+    dense = dense[:, dense.std(0) > 0]
+    nbr = ow.knn_neighbors(xy, 6)
+    ref = om.morans_I_batched(dense, nbr)
+    I, _, _ = gpu_moran(dense, nbr)
+    assert_close(I, ref)
+    centred = dense - dense.mean(0, keepdims=True).astype(np.float32)
+    I2, _, _ = gpu_moran(centred, nbr, preshifted=True)
+    assert_close(I2, ref)
+
+
+def test_duplicate_and_self_neighbours_take_the_generic_path():
+    """Neighbour lists with repeated entries / self loops are legal input for the C ABI."""
+    rng = np.random.default_rng(4)
+    n, g, k = 1001, 40, 8
+    dense = rng.normal(1.0, 1.0, (n, g)).astype(np.float32)
+    nbr = rng.integers(0, n, (n, k))
+    nbr[::3, 1] = nbr[::3, 0]                                          # duplicates
+    nbr[::5, 2] = np.arange(n)[::5]                                    # self loops
+    I, _, _ = gpu_moran(dense, nbr)
+    assert_close(I, om.morans_I_batched(dense, nbr))
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 6, 8, 18, 36, 40])
 def test_moran_kernel_any_k(k):
     xy = synth.make_coords("random", 3000, seed=k)
     X, _ = synth.make_counts_csr(xy, 200, seed=k)
