@@ -261,9 +261,9 @@ def run_native(args):
         except Exception:  # noqa: BLE001
             traffic = None
     kern_lists = {1: ["moran_pilot_kernel", "moran_ell_kernel", "moran_finalize_kernel"],
-                  4: ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"]}
-    kernels = kern_lists.get(args.variant, ["moran_pilot_kernel", "moran_pair_plan_kernel", "moran_pair_kernel",
-                                            "moran_finalize_kernel"])
+                  6: ["moran_pilot_kernel", "moran_pair_plan_kernel", "moran_pair_kernel", "moran_finalize_kernel"]}
+    kern_lists[7] = kern_lists[6]
+    kernels = kern_lists.get(args.variant, ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"])
     main_kernel = [x for x in kernels if x not in ("moran_pilot_kernel", "moran_pair_plan_kernel", "moran_finalize_kernel")][0]
     roofline = {"bound": "hbm", "kernel": main_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,

@@ -38,6 +38,15 @@ _SIGNATURES = {
     "chr_csr_spot_totals": (c_int, [_P, _P, _P, c_int64, _P, _P, _P]),
     "chr_csr_densify_log1p": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int, _P]),
     "chr_moran_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_uint]),
+    "chr_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "chr_colsum_f64": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "chr_gram_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "chr_gram_centered_bf16x3": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_uint, _P, c_size_t, _P]),
+    "chr_eigh_default_steps": (c_int, [c_int64, c_int]),
+    "chr_eigh_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "chr_eigh_topk_f64": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "chr_pca_scores_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "chr_pca_scores_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int, _P, c_int64, _P, c_size_t, _P]),
     "chr_moran_dense_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_uint, _P, _P, _P, _P, c_size_t, _P]),
 }
 

@@ -112,3 +112,61 @@ def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans:
     else:
         chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
     adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]
+
+
+def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
+    """Device part of ``pca``: densify the SVG columns -> column means -> tcgen05 Gram ->
+    eigensolver -> scores.  Returns host arrays (scores (n, r) float32, components (r, S) float32,
+    explained_variance_ratio (r,) float32).  Mirrors sklearn's PCA(arpack) as called at core.py:127-128:
+    centre, top-r right singular vectors, ``svd_flip`` (v-based), scores = U * S.
+    """
+    n = X.shape[0]
+    s = int(sel.sum())
+    # sklearn's arpack solver needs 0 < n_components < min(n_samples, n_features)  (_pca.py)
+    if not 0 < n_pcs < min(n, s):
+        raise ValueError(f"n_components={n_pcs} must be strictly less than min(n_samples, n_features)={min(n, s)} "
+                         "with svd_solver='arpack'")
+    csr = dv.upload_csr(X)
+    sel_d = dv.to_device(sel.astype(np.bool_))
+    gene_col = torch.where(sel_d, torch.cumsum(sel_d.to(torch.int32), 0, dtype=torch.int32) - 1,
+                           torch.full((sel_d.numel(),), -1, dtype=torch.int32, device=sel_d.device))
+    P = dv.csr_densify(csr, gene_col, s, None, None, apply_log1p=False)     # core.py:126  .X.todense()
+    mean = dv.column_sums(P, s) / n
+    C = dv.gram_centered(P, s, mean, timing=timing) / (n - 1)               # covariance (ddof=1)
+    total_var = torch.diagonal(C).sum()
+    evals, V, _ = dv.eigh_topk(C, n_pcs)
+    # svd_flip(u, v, u_based_decision=False): largest-|.| entry of every component is positive
+    idx = V.abs().argmax(dim=1)
+    signs = torch.sign(V[torch.arange(V.shape[0], device=V.device), idx])
+    signs[signs == 0] = 1.0
+    V = V * signs[:, None]
+    scores = dv.pca_scores(P, s, mean, V)
+    ratio = (evals / total_var).to(torch.float32)
+    return scores.cpu().numpy(), V.to(torch.float32).cpu().numpy(), ratio.cpu().numpy()
+
+
+def pca(adata, n_pcs: int = 50):
+    """
+    Perform PCA (Principal Component Analysis) to calculate PCA coordinates, loadings, and variance decomposition.
+
+    Drop-in for ``chrysalis.pca`` (/root/reference/chrysalis/core.py:95-137).  Spatially variable genes need to
+    be defined in ``.var['spatially_variable']`` using ``detect_svgs``.
+
+    :param adata: AnnData (or duck-typed equivalent) of shape ``n_obs`` x ``n_vars``.
+    :param n_pcs: Number of principal components to be calculated.
+    :return: None; adds PCs to ``.obsm['chr_X_pca']`` and ``.uns['chr_pca']`` with 'variance_ratio',
+        'loadings' and 'features'.
+    """
+    sel = np.asarray(adata.var['spatially_variable'] == True)  # noqa: E712  (same test as core.py:126)
+    scores, components, ratio = pca_stage(adata.X, sel, n_pcs)
+    adata.obsm['chr_X_pca'] = scores
+
+    features = list(np.asarray(adata.var_names)[sel])
+    if 'chr_pca' not in adata.uns.keys():
+        adata.uns['chr_pca'] = {'variance_ratio': ratio,
+                                'loadings': components,
+                                'features': features}
+    else:
+        adata.uns['chr_pca']['variance_ratio'] = ratio
+        adata.uns['chr_pca']['loadings'] = components
+        adata.uns['chr_pca']['features'] = features

@@ -220,7 +220,7 @@ __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int K, bool GEARY, int MINB>
+template <int K, bool GEARY, int MINB, bool SHIFT>
 __global__ void __launch_bounds__(kMoranThreads, MINB)
 moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ nbr,
                     int k_rt, int nbr_vec16, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
@@ -236,10 +236,13 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
     const int64_t s_end = s_begin + kV2SpotsPerCta < n ? s_begin + kV2SpotsPerCta : n;
     const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
 
-    const float4 pf = __ldg(reinterpret_cast<const float4*>(pilot + col));
     Row4 p;
-    p.a = f2_pack(pf.x, pf.y);
-    p.b = f2_pack(pf.z, pf.w);
+    p.a = p.b = f2_pack(0.f, 0.f);
+    if (SHIFT) {
+        const float4 pf = __ldg(reinterpret_cast<const float4*>(pilot + col));
+        p.a = f2_pack(pf.x, pf.y);
+        p.b = f2_pack(pf.z, pf.w);
+    }
 
     const f2_t z2 = f2_pack(0.f, 0.f);
     Row4 l1[kNStat], l2[kNStat];
@@ -259,7 +262,7 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
     };
 
     auto accumulate = [&](Row4 x, Row4 s) {   // s is already a sum of shifted values
-        r4_sub(x, p);
+        if (SHIFT) r4_sub(x, p);
         r4_add(l1[0], x);
         r4_fma(l1[1], x, x);
         r4_fma(l1[2], x, s);
@@ -293,16 +296,27 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
             s0.a = s0.b = s1.a = s1.b = z2;
             if constexpr (K > 0) {
                 Row4 v0[K], v1[K];
+                int ia[K], ib[K];
+                if constexpr (K % 4 == 0) {   // neighbour lists as 128-bit broadcast loads
+#pragma unroll
+                    for (int j = 0; j < K; j += 4) {
+                        const int4 qa = *reinterpret_cast<const int4*>(idx0 + j), qb = *reinterpret_cast<const int4*>(idx1 + j);
+                        ia[j] = qa.x; ia[j + 1] = qa.y; ia[j + 2] = qa.z; ia[j + 3] = qa.w;
+                        ib[j] = qb.x; ib[j + 1] = qb.y; ib[j + 2] = qb.z; ib[j + 3] = qb.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) { ia[j] = idx0[j]; ib[j] = idx1[j]; }
+                }
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    v0[j] = ld_row4(base + (uint64_t)(uint32_t)idx0[j] * row_bytes);
-                    v1[j] = ld_row4(base + (uint64_t)(uint32_t)idx1[j] * row_bytes);
+                    v0[j] = ld_row4(base + (uint64_t)(uint32_t)ia[j] * row_bytes);
+                    v1[j] = ld_row4(base + (uint64_t)(uint32_t)ib[j] * row_bytes);
                 }
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (GEARY) { r4_sqdiff(l1[4], x0, v0[j]); if (has1) r4_sqdiff(l1[4], x1, v1[j]); }
-                    r4_sub(v0[j], p);                                  // shift before summing: partial sums stay O(std)
-                    r4_sub(v1[j], p);
+                    if (SHIFT) { r4_sub(v0[j], p); r4_sub(v1[j], p); }   // shift before summing: partial sums stay O(std)
                     r4_add(s0, v0[j]);
                     r4_add(s1, v1[j]);
                 }
@@ -312,8 +326,7 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
                     Row4 v0 = ld_row4(base + (uint64_t)(uint32_t)idx0[j] * row_bytes);
                     Row4 v1 = ld_row4(base + (uint64_t)(uint32_t)idx1[j] * row_bytes);
                     if (GEARY) { r4_sqdiff(l1[4], x0, v0); if (has1) r4_sqdiff(l1[4], x1, v1); }
-                    r4_sub(v0, p);
-                    r4_sub(v1, p);
+                    if (SHIFT) { r4_sub(v0, p); r4_sub(v1, p); }
                     r4_add(s0, v0);
                     r4_add(s1, v1);
                 }
@@ -667,11 +680,11 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     const int64_t ldc = round_up<int64_t>(n_genes, 4);
     const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
     const bool preshifted = flags & CHR_FLAG_PRESHIFTED;
-    // variant 0: pair kernel (v3); Geary's C rides the v2 stream kernel.  1: v1, 4: v2, 6: v3 (tuning / regression)
+    // variant 0/4: stream kernel (v2, default).  1: v1 ELL kernel, 6/7: v3 pair kernel (kept for regression / tuning)
     const bool v1 = variant == 1 && !geary;
-    const bool v3 = !geary && (variant == 0 || variant == 6 || variant == 7);
+    const bool v3 = !geary && (variant == 6 || variant == 7);
     const bool v2 = !v1;   // v2 and v3 share the 2048-spot split structure
-    CHR_REQUIRE(!preshifted || v3, "chr_moran_dense_f32: CHR_FLAG_PRESHIFTED is only supported by the default (pair) kernel without Geary");
+    CHR_REQUIRE(!preshifted || !v1, "chr_moran_dense_f32: CHR_FLAG_PRESHIFTED is not supported by the v1 kernel");
     MoranPlan p = moran_plan(n_spots, n_genes, ldc, v2, k);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -723,21 +736,23 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
         if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
         const uint32_t rb = (uint32_t)(ld * 4);
         timer_begin(CHR_FAMILY_MORAN, timing, st);
-#define CHR_V2(KK, GG, MB)                                                                                          \
+#define CHR_V2(KK, GG, MB, SH)                                                                                      \
     do {                                                                                                            \
-        auto kern = moran_stream_kernel<KK, GG, MB>;                                                               \
+        auto kern = moran_stream_kernel<KK, GG, MB, SH>;                                                               \
         if (smem > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, nbr, k, vec16, pilot, part, p.gpad);        \
     } while (0)
-#define CHR_V2K(GG, MB)                                  \
+#define CHR_V2K(GG, MB, SH)                              \
     switch (k) {                                         \
-        case 4: CHR_V2(4, GG, MB); break;                \
-        case 6: CHR_V2(6, GG, MB); break;                \
-        case 8: CHR_V2(8, GG, MB); break;                \
-        default: CHR_V2(0, GG, MB); break;               \
+        case 4: CHR_V2(4, GG, MB, SH); break;            \
+        case 6: CHR_V2(6, GG, MB, SH); break;            \
+        case 8: CHR_V2(8, GG, MB, SH); break;            \
+        default: CHR_V2(0, GG, MB, SH); break;           \
     }
-        if (geary) { CHR_V2K(true, 1) }
-        else { CHR_V2K(false, 2) }
+        if (geary && preshifted) { CHR_V2K(true, 1, false) }
+        else if (geary) { CHR_V2K(true, 1, true) }
+        else if (preshifted) { CHR_V2K(false, 2, false) }
+        else { CHR_V2K(false, 2, true) }
 #undef CHR_V2K
 #undef CHR_V2
     } else {

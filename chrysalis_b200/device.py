@@ -183,3 +183,65 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
 
 def last_kernel_ms(family: int = _lib.FAMILY_MORAN) -> float:
     return float(_lib.query("chr_last_kernel_ms", family))
+
+
+# ---- K6 - K8: PCA ------------------------------------------------------------------------
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def column_sums(P: torch.Tensor, s: int) -> torch.Tensor:
+    """float64 column sums of the first ``s`` columns of the dense [n, ld] float32 matrix."""
+    n, ld = P.shape[0], P.stride(0)
+    ws_bytes = _lib.query("chr_colsum_workspace_bytes", n, s)
+    ws = _workspace(ws_bytes, P.device)
+    out = torch.empty(s, dtype=torch.float64, device=P.device)
+    _lib.call("chr_colsum_f64", _ptr(P), n, s, ld, _ptr(out), _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def gram_centered(P: torch.Tensor, s: int, mean: torch.Tensor, timing: bool = False) -> torch.Tensor:
+    """(P - mean)^T (P - mean) as float64 [s, s] (tcgen05, split-bf16 operands)."""
+    n, ld = P.shape[0], P.stride(0)
+    assert mean.dtype == torch.float64 and mean.numel() == s
+    ws_bytes = _lib.query("chr_gram_workspace_bytes", n, s)
+    ws = _workspace(ws_bytes, P.device)
+    C = torch.empty((s, s), dtype=torch.float64, device=P.device)
+    _lib.call("chr_gram_centered_bf16x3", _ptr(P), n, s, ld, _ptr(mean), _ptr(C), _lib.FLAG_TIMING if timing else 0,
+              _ptr(ws), ws_bytes, _stream())
+    return C
+
+
+def eigh_topk(C: torch.Tensor, r: int, rtol: float = 1e-9):
+    """r largest eigenpairs of the symmetric float64 matrix C: (evals [r] desc, evecs [r, s]).
+
+    The Lanczos depth is doubled until every Ritz residual is below ``rtol * lambda_max``
+    (or the Krylov space is the whole space)."""
+    s = C.shape[0]
+    assert C.dtype == torch.float64 and C.is_contiguous() and C.shape[1] == s
+    m = _lib.query("chr_eigh_default_steps", s, r)
+    while True:
+        ws_bytes = _lib.query("chr_eigh_workspace_bytes", s, r, m)
+        ws = _workspace(ws_bytes, C.device)
+        evals = torch.empty(r, dtype=torch.float64, device=C.device)
+        evecs = torch.empty((r, s), dtype=torch.float64, device=C.device)
+        res = torch.empty(r, dtype=torch.float64, device=C.device)
+        _lib.call("chr_eigh_topk_f64", _ptr(C), s, r, m, _ptr(evals), _ptr(evecs), _ptr(res), _ptr(ws), ws_bytes, _stream())
+        worst = float((res / evals[0].abs().clamp_min(1e-300)).max().item())
+        if worst <= rtol or m >= min(s, 1024):
+            order = torch.argsort(evals, descending=True)
+            return evals[order], evecs[order], worst
+        m = min(s, 1024, 2 * m)
+
+
+def pca_scores(P: torch.Tensor, s: int, mean: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+    """(P - mean) V^T as float32 [n, r];  V: [r, s] float64."""
+    n, ld = P.shape[0], P.stride(0)
+    r = V.shape[0]
+    ws_bytes = _lib.query("chr_pca_scores_workspace_bytes", s, r)
+    ws = _workspace(ws_bytes, P.device)
+    Y = torch.empty((n, r), dtype=torch.float32, device=P.device)
+    _lib.call("chr_pca_scores_f32", _ptr(P), n, s, ld, _ptr(mean), _ptr(V.contiguous()), r, _ptr(Y), r, _ptr(ws), ws_bytes,
+              _stream())
+    return Y

@@ -94,6 +94,37 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
                         double* out_stats, void* workspace, size_t workspace_bytes,
                         chr_stream_t stream);
 
+/* ---- K6-K8: PCA of the SVG matrix ------------------------------------------------------
+ * replaces  PCA(n_components=n_pcs, svd_solver='arpack', random_state=42).fit_transform(pcs)
+ *           (/root/reference/chrysalis/core.py:126-128; sklearn -> scipy ARPACK svds)
+ * P: [n][ld] float32 dense SVG matrix (spots x selected genes).  Staged so that a spot-sharded
+ * multi-GPU run can all-reduce the column sums and the partial Grams between the calls. */
+size_t chr_colsum_workspace_bytes(int64_t n, int64_t s);
+/* sums[g] = sum_i P[i][g]  (float64, fixed summation order) */
+int chr_colsum_f64(const float* P, int64_t n, int64_t s, int64_t ld, double* sums, void* workspace,
+                   size_t workspace_bytes, chr_stream_t stream);
+size_t chr_gram_workspace_bytes(int64_t n, int64_t s);
+/* C_out[s][s] (float64, symmetric) = (P - mean)^T (P - mean): tcgen05 Gram, operands split into
+ * bf16 hi/lo pairs (3 MMAs per product pair, fp32 TMEM accumulators over <= 8192 spots,
+ * split-K partials reduced in float64).  mean: [s] float64. */
+int chr_gram_centered_bf16x3(const float* P, int64_t n, int64_t s, int64_t ld, const double* mean,
+                             double* C_out, unsigned flags, void* workspace, size_t workspace_bytes,
+                             chr_stream_t stream);
+/* r largest eigenpairs of the symmetric C [s][s]: m-step Lanczos with full reorthogonalisation,
+ * Sturm bisection + inverse iteration on the tridiagonal, Ritz vectors orthonormalised.
+ * evals: [r] descending Rayleigh quotients, evecs: [r][s], residuals: [r] = |C y - lambda y|.
+ * m: Lanczos steps, r <= m <= s (chr_eigh_default_steps gives the starting choice; the caller
+ * repeats with a larger m if a residual is too large). */
+int chr_eigh_default_steps(int64_t s, int r);
+size_t chr_eigh_workspace_bytes(int64_t s, int r, int m);
+int chr_eigh_topk_f64(const double* C, int64_t s, int r, int m, double* evals, double* evecs,
+                      double* residuals, void* workspace, size_t workspace_bytes, chr_stream_t stream);
+/* Y[i][c] = sum_g (P[i][g] - mean[g]) V[c][g]   (scores U*S of the SVD), Y: [n][ldy] float32 */
+size_t chr_pca_scores_workspace_bytes(int64_t s, int r);
+int chr_pca_scores_f32(const float* P, int64_t n, int64_t s, int64_t ld, const double* mean,
+                       const double* V, int r, float* Y, int64_t ldy, void* workspace,
+                       size_t workspace_bytes, chr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
