@@ -1,0 +1,574 @@
+// K9-K11 - archetypal analysis: alternating penalised non-negative least squares.
+//
+// Replaces  archetypes.AA(n_archetypes, n_init=3, max_iter, tol=0.001, random_state=42).fit(X)
+// (/root/reference/chrysalis/core.py:186-191; archetypes==0.4.2, pyproject.toml:24 - source not in
+// the reference tree, algorithm restated in oracle/aa.py and SURVEY.md App. A.6).  One iteration:
+//     alphas = optimize(X, Z)        N NNLS problems  min || [Z,M]^T a - [x_i,M] ||, a >= 0
+//     Z      = pinv(alphas) X        normal equations A^T A (A x A), A^T X (A x d)
+//     betas  = optimize(Z, X)        A NNLS problems with N unknowns each (<= d+1 non-zeros)
+//     Z      = betas X ;  rss = || X - alphas Z ||_F^2
+// with rows of alphas / betas renormalised to sum 1.  All arithmetic is fp64 (the reference
+// upcasts to float64 inside numpy / scipy.optimize.nnls).
+//
+// NNLS is Lawson-Hanson's active-set method on the normal equations (scipy.optimize.nnls is the
+// same method with QR updates): the alpha problems share G = Z Z^T + M^2 (kept in shared
+// memory, one thread per spot); the beta problems stream X once per active-set step for all
+// archetypes together (gradient = skinny GEMM + arg-max), then one CTA updates the passive sets.
+#include "common.cuh"
+
+namespace chr {
+
+constexpr int kAaMaxA = 64;     // archetypes
+constexpr int kAaMaxD = 64;     // embedding dimensions
+constexpr int kAaMaxP = kAaMaxD + 2;   // passive-set bound for the beta problems (rank of [X, M] <= d + 1)
+
+// ---- small dense helpers (per thread, column-major n x n in `a`, n <= 66) ----------------------
+// Cholesky solve of the SPD system  H s = r  restricted to the index list `idx` (size np) of a
+// full matrix `full` with leading dimension ld.  L is scratch (np*(np+1)/2).  Returns false if not SPD.
+__device__ bool chol_solve_subset(const double* __restrict__ full, int ld, const int* idx, int np, const double* rhs_full,
+                                  double* L, double* s) {
+    for (int i = 0; i < np; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double v = full[idx[i] * ld + idx[j]];
+            for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+            if (i == j) {
+                if (!(v > 0.0)) return false;
+                L[i * (i + 1) / 2 + i] = sqrt(v);
+            } else {
+                L[i * (i + 1) / 2 + j] = v / L[j * (j + 1) / 2 + j];
+            }
+        }
+    }
+    for (int i = 0; i < np; ++i) {
+        double v = rhs_full[idx[i]];
+        for (int k = 0; k < i; ++k) v -= L[i * (i + 1) / 2 + k] * s[k];
+        s[i] = v / L[i * (i + 1) / 2 + i];
+    }
+    for (int i = np - 1; i >= 0; --i) {
+        double v = s[i];
+        for (int k = i + 1; k < np; ++k) v -= L[k * (k + 1) / 2 + i] * s[k];
+        s[i] = v / L[i * (i + 1) / 2 + i];
+    }
+    return true;
+}
+
+// Lawson-Hanson NNLS on normal equations  min 1/2 a'Ga - c'a, a >= 0  (G: na x na, ld = na).
+// x: out (na).  Scratch arrays sized by the caller.  Ties in the arg-max go to the lowest index.
+template <int MAXA>
+__device__ void nnls_normal(const double* __restrict__ G, const double* c, int na, double* x) {
+    int pidx[MAXA];
+    double s[MAXA], w[MAXA], L[MAXA * (MAXA + 1) / 2];
+    bool inP[MAXA];
+    int np = 0;
+    double cmax = 0.0;
+    for (int j = 0; j < na; ++j) { x[j] = 0.0; inP[j] = false; w[j] = c[j]; cmax = fmax(cmax, fabs(c[j])); }
+    const double tol = 1e-12 * fmax(cmax, 1e-300);
+    for (int outer = 0; outer < 3 * na; ++outer) {
+        int jbest = -1;
+        double wbest = tol;
+        for (int j = 0; j < na; ++j)
+            if (!inP[j] && w[j] > wbest) { wbest = w[j]; jbest = j; }
+        if (jbest < 0) break;
+        inP[jbest] = true;
+        pidx[np++] = jbest;
+        for (int inner = 0; inner < 3 * na; ++inner) {
+            if (!chol_solve_subset(G, na, pidx, np, c, L, s)) {   // numerically dependent column: drop it again
+                inP[pidx[np - 1]] = false;
+                --np;
+                break;
+            }
+            double smin = 1e300;
+            for (int i = 0; i < np; ++i) smin = fmin(smin, s[i]);
+            if (smin > 0.0) {
+                for (int i = 0; i < np; ++i) x[pidx[i]] = s[i];
+                break;
+            }
+            double alpha = 1e300;
+            for (int i = 0; i < np; ++i)
+                if (s[i] <= 0.0) alpha = fmin(alpha, x[pidx[i]] / (x[pidx[i]] - s[i]));
+            for (int i = 0; i < np; ++i) x[pidx[i]] += alpha * (s[i] - x[pidx[i]]);
+            int q = 0;
+            for (int i = 0; i < np; ++i) {
+                if (x[pidx[i]] <= 1e-15 * fmax(1.0, cmax) && s[i] <= 0.0) { x[pidx[i]] = 0.0; inP[pidx[i]] = false; }
+                else pidx[q++] = pidx[i];
+            }
+            np = q;
+            if (np == 0) break;
+        }
+        for (int j = 0; j < na; ++j) {
+            double v = c[j];
+            for (int i = 0; i < np; ++i) v -= G[j * na + pidx[i]] * x[pidx[i]];
+            w[j] = v;
+        }
+    }
+}
+
+// ---- alpha step: one thread per spot ---------------------------------------------------------------
+// also accumulates the CTA's partial  A^T A (na x na)  and  A^T X (na x d)  for the pinv step
+template <int MAXA>
+__global__ void __launch_bounds__(128)
+aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Z, int na, double M,
+                double* __restrict__ alphas, double* __restrict__ part /*[grid][na*na + na*d]*/) {
+    extern __shared__ double sh[];
+    double* G = sh;                       // na x na
+    double* Zs = G + na * na;             // na x d
+    double* acc = Zs + na * d;            // na*na + na*d  CTA accumulators
+    const int nacc = na * na + na * d;
+    for (int e = threadIdx.x; e < na * d; e += blockDim.x) Zs[e] = Z[e];
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) acc[e] = 0.0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < na * na; e += blockDim.x) {
+        const int a = e / na, b = e % na;
+        double v = M * M;
+        for (int t = 0; t < d; ++t) v += Zs[a * d + t] * Zs[b * d + t];
+        G[e] = v;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double a_out[MAXA];
+    bool valid = i < n;
+    if (valid) {
+        double c[MAXA];
+        const double* __restrict__ x = X + i * d;
+        for (int a = 0; a < na; ++a) {
+            double v = M * M;
+            for (int t = 0; t < d; ++t) v += Zs[a * d + t] * x[t];
+            c[a] = v;
+        }
+        nnls_normal<MAXA>(G, c, na, a_out);
+        double sum = 0.0;
+        for (int a = 0; a < na; ++a) { a_out[a] = fmax(a_out[a], 0.0); sum += a_out[a]; }
+        const double inv = 1.0 / sum;
+        for (int a = 0; a < na; ++a) { a_out[a] *= inv; alphas[i * na + a] = a_out[a]; }
+    }
+    // CTA-level accumulation in fixed order: threads take turns per (warp-serialised) entry
+    // -> deterministic: each accumulator entry is summed over threads 0..blockDim-1 in order
+    __syncthreads();
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+        if ((int)threadIdx.x == t && valid) {
+            const double* __restrict__ x = X + i * d;
+            for (int a = 0; a < na; ++a) {
+                const double va = a_out[a];
+                if (va == 0.0) continue;
+                for (int b = 0; b < na; ++b) acc[a * na + b] += va * a_out[b];
+                for (int q = 0; q < d; ++q) acc[na * na + a * d + q] += va * x[q];
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) part[(size_t)blockIdx.x * nacc + e] = acc[e];
+}
+
+// ---- pinv step (single CTA): Zhat = pinv(alphas) X via eigen-decomposition of A^T A ---------------------
+__global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int na, int d, int64_t n, double* __restrict__ Zhat) {
+    extern __shared__ double sh[];
+    const int nacc = na * na + na * d;
+    double* S = sh;                 // na x na  (A^T A, becomes diagonal)
+    double* B = S + na * na;        // na x d   (A^T X)
+    double* Vv = B + na * d;        // na x na  eigenvectors (columns)
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+        double a = 0.0;
+        for (int p = 0; p < nparts; ++p) a += part[(size_t)p * nacc + e];
+        if (e < na * na) S[e] = a; else B[e - na * na] = a;
+    }
+    for (int e = threadIdx.x; e < na * na; e += blockDim.x) Vv[e] = (e / na == e % na) ? 1.0 : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // cyclic Jacobi (na <= 64: a few thousand rotations, serial is fine for a na x na matrix)
+        for (int sweep = 0; sweep < 60; ++sweep) {
+            double off = 0.0, diag = 0.0;
+            for (int p = 0; p < na; ++p) { diag += S[p * na + p] * S[p * na + p]; for (int q = p + 1; q < na; ++q) off += S[p * na + q] * S[p * na + q]; }
+            if (off <= 1e-30 * diag) break;
+            for (int p = 0; p < na - 1; ++p)
+                for (int q = p + 1; q < na; ++q) {
+                    const double apq = S[p * na + q];
+                    if (fabs(apq) < 1e-300) continue;
+                    const double theta = (S[q * na + q] - S[p * na + p]) / (2.0 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                    for (int k = 0; k < na; ++k) {
+                        const double skp = S[k * na + p], skq = S[k * na + q];
+                        S[k * na + p] = c * skp - s * skq;
+                        S[k * na + q] = s * skp + c * skq;
+                    }
+                    for (int k = 0; k < na; ++k) {
+                        const double spk = S[p * na + k], sqk = S[q * na + k];
+                        S[p * na + k] = c * spk - s * sqk;
+                        S[q * na + k] = s * spk + c * sqk;
+                    }
+                    for (int k = 0; k < na; ++k) {
+                        const double vkp = Vv[k * na + p], vkq = Vv[k * na + q];
+                        Vv[k * na + p] = c * vkp - s * vkq;
+                        Vv[k * na + q] = s * vkp + c * vkq;
+                    }
+                }
+        }
+    }
+    __syncthreads();
+    // pinv(A) X = V diag(1/lambda) V^T (A^T X);  numpy.linalg.pinv drops singular values below
+    // rtol * sigma_max with rtol = max(n, na) * eps, i.e. eigenvalues below (rtol^2) * lambda_max
+    double lmax = 0.0;
+    for (int p = 0; p < na; ++p) lmax = fmax(lmax, S[p * na + p]);
+    const double rt = (double)(n > na ? n : na) * 2.220446049250313e-16;
+    const double cut = fmax(rt * rt, 1e-14) * lmax;   // eigenvalues of A^T A are only resolved to ~1e-16 * lmax
+    for (int e = threadIdx.x; e < na * d; e += blockDim.x) {
+        const int a = e / d, q = e % d;
+        double v = 0.0;
+        for (int p = 0; p < na; ++p) {
+            const double lam = S[p * na + p];
+            if (lam <= cut) continue;
+            double t = 0.0;
+            for (int b = 0; b < na; ++b) t += Vv[b * na + p] * B[b * d + q];
+            v += Vv[a * na + p] * t / lam;
+        }
+        Zhat[e] = v;
+    }
+}
+
+// ---- beta step -------------------------------------------------------------------------------------
+// state per archetype a: passive list pidx[a][<=kAaMaxP], coefficient b[a][.], count np[a], done[a];
+// residual R[a][0..d] = [zhat_a, M] - sum_p b_p [x_p, M]
+struct BetaState {
+    int np[kAaMaxA];
+    int done[kAaMaxA];
+    int all_done;
+    int iters;
+};
+
+// gradient pass:  w[i][a] = [x_i, M] . R[a];  per CTA arg-max over its spots for every archetype
+__global__ void __launch_bounds__(256)
+aa_beta_grad_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ R, int na,
+                    const BetaState* __restrict__ st, const int* __restrict__ pidx, double* __restrict__ cand_w,
+                    int64_t* __restrict__ cand_i) {
+    if (st->all_done) return;
+    extern __shared__ double sh[];
+    double* Rs = sh;                                   // na x (d+1)
+    double* red_w = Rs + na * (d + 1);                 // [warps]
+    int64_t* red_i = reinterpret_cast<int64_t*>(red_w + 32);
+    for (int e = threadIdx.x; e < na * (d + 1); e += blockDim.x) Rs[e] = R[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * 1024;
+    const int64_t i1 = i0 + 1024 < n ? i0 + 1024 : n;
+    for (int a = 0; a < na; ++a) {
+        if (st->done[a]) {
+            if (threadIdx.x == 0) { cand_w[(size_t)blockIdx.x * na + a] = -1e300; cand_i[(size_t)blockIdx.x * na + a] = -1; }
+            continue;
+        }
+        const double* __restrict__ r = Rs + a * (d + 1);
+        double bw = -1e300;
+        int64_t bi = -1;
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+            const double* __restrict__ x = X + i * d;
+            double v = M * r[d];
+            for (int t = 0; t < d; ++t) v += x[t] * r[t];
+            if (v > bw) { bw = v; bi = i; }
+        }
+        // passive entries are excluded by the update kernel (their gradient is ~0); arg-max, lowest index wins ties
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ow > bw || (ow == bw && oi >= 0 && (bi < 0 || oi < bi))) { bw = ow; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { red_w[warp] = bw; red_i[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < nw; ++w)
+                if (red_w[w] > bw || (red_w[w] == bw && red_i[w] >= 0 && (bi < 0 || red_i[w] < bi))) { bw = red_w[w]; bi = red_i[w]; }
+            cand_w[(size_t)blockIdx.x * na + a] = bw;
+            cand_i[(size_t)blockIdx.x * na + a] = bi;
+        }
+    }
+    (void)pidx;
+}
+
+// one warp per archetype: final arg-max, add to the passive set, Lawson-Hanson inner loop, new residual
+__global__ void __launch_bounds__(32 * 8)
+aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ Zhat, int na,
+                      int nblocks, const double* __restrict__ cand_w, const int64_t* __restrict__ cand_i,
+                      BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef, double* __restrict__ R,
+                      double* __restrict__ scratch) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int a = warp;
+    if (a >= na || st->all_done) return;
+    if (!st->done[a]) {
+        // final arg-max over the CTAs of the gradient pass (lane-strided, lowest index wins ties)
+        double bw = -1e300;
+        int64_t bi = -1;
+        for (int b = lane; b < nblocks; b += 32) {
+            const double w = cand_w[(size_t)b * na + a];
+            const int64_t i = cand_i[(size_t)b * na + a];
+            if (w > bw || (w == bw && i >= 0 && (bi < 0 || i < bi))) { bw = w; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+            const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ow > bw || (ow == bw && oi >= 0 && (bi < 0 || oi < bi))) { bw = ow; bi = oi; }
+        }
+        if (lane == 0) {
+            const int dp = d + 1;
+            int* P = pidx + a * kAaMaxP;
+            double* b = bcoef + a * kAaMaxP;
+            int np = st->np[a];
+            // scale for the stopping test: |[zhat, M]| * max |[x, M]| ~ M^2
+            double znorm = M * M;
+            for (int t = 0; t < d; ++t) znorm += Zhat[a * d + t] * Zhat[a * d + t];
+            const double tol = 1e-11 * znorm;
+            bool in_set = false;
+            for (int p = 0; p < np; ++p) in_set |= (P[p] == (int)bi);
+            if (bi < 0 || bw <= tol || in_set || np >= kAaMaxP - 1) {
+                st->done[a] = 1;
+            } else {
+                P[np] = (int)bi;
+                b[np] = 0.0;
+                ++np;
+                // scratch per archetype: H (np x np), rhs, s, L
+                double* H = scratch + (size_t)a * (kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2);
+                double* rhs = H + kAaMaxP * kAaMaxP;
+                double* s = rhs + kAaMaxP;
+                double* L = s + kAaMaxP;
+                int ident[kAaMaxP];
+                for (int inner = 0; inner < 3 * kAaMaxP; ++inner) {
+                    for (int p = 0; p < np; ++p) {
+                        const double* xp = X + (int64_t)P[p] * d;
+                        for (int q = 0; q <= p; ++q) {
+                            const double* xq = X + (int64_t)P[q] * d;
+                            double v = M * M;
+                            for (int t = 0; t < d; ++t) v += xp[t] * xq[t];
+                            H[p * np + q] = v;
+                            H[q * np + p] = v;
+                        }
+                        double v = M * M;
+                        for (int t = 0; t < d; ++t) v += xp[t] * Zhat[a * d + t];
+                        rhs[p] = v;
+                        ident[p] = p;
+                    }
+                    if (!chol_solve_subset(H, np, ident, np, rhs, L, s)) { --np; st->done[a] = 1; break; }
+                    double smin = 1e300;
+                    for (int p = 0; p < np; ++p) smin = fmin(smin, s[p]);
+                    if (smin > 0.0) { for (int p = 0; p < np; ++p) b[p] = s[p]; break; }
+                    double alpha = 1e300;
+                    for (int p = 0; p < np; ++p)
+                        if (s[p] <= 0.0) alpha = fmin(alpha, b[p] / (b[p] - s[p]));
+                    for (int p = 0; p < np; ++p) b[p] += alpha * (s[p] - b[p]);
+                    int q = 0;
+                    for (int p = 0; p < np; ++p) {
+                        if (b[p] <= 1e-15 && s[p] <= 0.0) continue;
+                        P[q] = P[p]; b[q] = b[p]; ++q;
+                    }
+                    np = q;
+                    if (np == 0) break;
+                }
+                st->np[a] = np;
+                // residual  R[a] = [zhat_a, M] - sum_p b_p [x_p, M]
+                for (int t = 0; t < dp; ++t) {
+                    double v = t < d ? Zhat[a * d + t] : M;
+                    for (int p = 0; p < np; ++p) v -= b[p] * (t < d ? X[(int64_t)P[p] * d + t] : M);
+                    R[a * dp + t] = v;
+                }
+            }
+        }
+    }
+    (void)n;
+}
+
+__global__ void aa_beta_check_kernel(BetaState* st, int na) {
+    if (threadIdx.x == 0) {
+        int all = 1;
+        for (int a = 0; a < na; ++a) all &= st->done[a];
+        st->all_done = all;
+        st->iters += 1;
+    }
+}
+
+__global__ void aa_beta_init_kernel(BetaState* st, const double* __restrict__ Zhat, int na, int d, double M, double* __restrict__ R) {
+    const int t = threadIdx.x;
+    if (t == 0) { st->all_done = 0; st->iters = 0; }
+    if (t < na) { st->np[t] = 0; st->done[t] = 0; }
+    for (int e = t; e < na * (d + 1); e += blockDim.x) {
+        const int a = e / (d + 1), q = e % (d + 1);
+        R[e] = q < d ? Zhat[a * d + q] : M;
+    }
+}
+
+// Z[a] = sum_p coef_p x_p with coef = max(b,0) / sum;  also writes the sparse betas (index, coef) lists
+__global__ void aa_beta_finish_kernel(const double* __restrict__ X, int d, int na, const BetaState* __restrict__ st,
+                                      const int* __restrict__ pidx, double* __restrict__ bcoef, double* __restrict__ Z) {
+    const int a = blockIdx.x;
+    if (a >= na) return;
+    const int np = st->np[a];
+    const int* P = pidx + a * kAaMaxP;
+    double* b = bcoef + a * kAaMaxP;
+    __shared__ double inv;
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int p = 0; p < np; ++p) { b[p] = fmax(b[p], 0.0); sum += b[p]; }
+        inv = 1.0 / sum;
+        for (int p = 0; p < np; ++p) b[p] *= inv;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < d; t += blockDim.x) {
+        double v = 0.0;
+        for (int p = 0; p < np; ++p) v += b[p] * X[(int64_t)P[p] * d + t];
+        Z[a * d + t] = v;
+    }
+}
+
+// rss partials:  sum_i || x_i - sum_a alpha_ia Z_a ||^2
+__global__ void __launch_bounds__(256)
+aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ alphas, const double* __restrict__ Z,
+              int na, double* __restrict__ part) {
+    extern __shared__ double sh[];
+    double* Zs = sh;
+    __shared__ double red[32];
+    for (int e = threadIdx.x; e < na * d; e += blockDim.x) Zs[e] = Z[e];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double r = 0.0;
+    if (i < n) {
+        const double* __restrict__ x = X + i * d;
+        const double* __restrict__ al = alphas + i * na;
+        for (int t = 0; t < d; ++t) {
+            double v = x[t];
+            for (int a = 0; a < na; ++a) v -= al[a] * Zs[a * d + t];
+            r += v * v;
+        }
+    }
+    r = warp_sum(r);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void aa_sum_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int p = 0; p < np; ++p) t += part[p];
+        *out = t;
+    }
+}
+
+__global__ void aa_gather_rows_kernel(const double* __restrict__ X, int d, const int64_t* __restrict__ rows, int na,
+                                      double* __restrict__ Z) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < na * d) Z[e] = X[rows[e / d] * d + e % d];
+}
+
+struct AaPlan {
+    int alpha_blocks, grad_blocks, rss_blocks, nacc;
+    size_t off_part, off_zhat, off_R, off_state, off_pidx, off_bcoef, off_candw, off_candi, off_scr, off_rsspart, total;
+};
+
+static AaPlan aa_plan(int64_t n, int d, int na) {
+    AaPlan p;
+    p.alpha_blocks = (int)ceil_div<int64_t>(n, 128);
+    p.grad_blocks = (int)ceil_div<int64_t>(n, 1024);
+    p.rss_blocks = (int)ceil_div<int64_t>(n, 256);
+    p.nacc = na * na + na * d;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t x = o; o += round_up<size_t>(b, 256); return x; };
+    p.off_part = take((size_t)p.alpha_blocks * p.nacc * 8);
+    p.off_zhat = take((size_t)na * d * 8);
+    p.off_R = take((size_t)na * (d + 1) * 8);
+    p.off_state = take(sizeof(BetaState));
+    p.off_pidx = take((size_t)na * kAaMaxP * 4);
+    p.off_bcoef = take((size_t)na * kAaMaxP * 8);
+    p.off_candw = take((size_t)p.grad_blocks * na * 8);
+    p.off_candi = take((size_t)p.grad_blocks * na * 8);
+    p.off_scr = take((size_t)na * (kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2) * 8);
+    p.off_rsspart = take((size_t)p.rss_blocks * 8);
+    p.total = o;
+    return p;
+}
+
+}  // namespace chr
+
+extern "C" {
+
+size_t chr_aa_workspace_bytes(int64_t n, int d, int n_archetypes) {
+    if (n <= 0 || d <= 0 || n_archetypes <= 0) return 1024;
+    return chr::aa_plan(n, d, n_archetypes).total + 1024;
+}
+
+int chr_aa_init_archetypes(const double* X, int64_t n, int d, const int64_t* rows, int n_archetypes, double* Z,
+                           chr_stream_t stream) {
+    using namespace chr;
+    CHR_REQUIRE(X && rows && Z && n > 0 && d > 0 && n_archetypes > 0, "chr_aa_init_archetypes: bad arguments");
+    aa_gather_rows_kernel<<<(unsigned)ceil_div(n_archetypes * d, 256), 256, 0, (cudaStream_t)stream>>>(X, d, rows, n_archetypes, Z);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+// one full iteration:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);  Z <- betas X;  rss
+int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, double* Z, double* alphas,
+                   double* rss_out, int* beta_passes_out, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int na = n_archetypes;
+    CHR_REQUIRE(X && Z && alphas && rss_out && workspace, "chr_aa_iterate: null pointer argument");
+    CHR_REQUIRE(n > 0 && d > 0 && d <= kAaMaxD && na >= 2 && na <= kAaMaxA, "chr_aa_iterate: need 0 < d <= %d, 2 <= n_archetypes <= %d",
+                kAaMaxD, kAaMaxA);
+    AaPlan p = aa_plan(n, d, na);
+    CHR_REQUIRE(workspace_bytes >= p.total + 256, "chr_aa_iterate: workspace too small (%zu < %zu)", workspace_bytes, p.total + 256);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double* part = (double*)(ws + p.off_part);
+    double* Zhat = (double*)(ws + p.off_zhat);
+    double* R = (double*)(ws + p.off_R);
+    BetaState* bst = (BetaState*)(ws + p.off_state);
+    int* pidx = (int*)(ws + p.off_pidx);
+    double* bcoef = (double*)(ws + p.off_bcoef);
+    double* candw = (double*)(ws + p.off_candw);
+    int64_t* candi = (int64_t*)(ws + p.off_candi);
+    double* scr = (double*)(ws + p.off_scr);
+    double* rsspart = (double*)(ws + p.off_rsspart);
+
+    timer_begin(CHR_FAMILY_AA, true, st);
+    // ---- alphas
+    const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc) * 8;
+    if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+    else if (na <= 32) aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+    else {
+        CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
+        aa_alpha_kernel<64><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+    }
+    CHR_LAUNCH_CHECK();
+    // ---- Zhat = pinv(alphas) X
+    const size_t sm_pinv = (size_t)(2 * na * na + na * d) * 8;
+    if (sm_pinv > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pinv));
+    aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part, p.alpha_blocks, na, d, n, Zhat);
+    CHR_LAUNCH_CHECK();
+    // ---- betas: active-set passes, every archetype advances one step per pass
+    aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, R);
+    const size_t sm_grad = (size_t)na * (d + 1) * 8 + 32 * 8 + 32 * 8;
+    const int max_pass = 3 * (d + 2) + 8;
+    int passes = 0;
+    int host_done = 0;
+    while (passes < max_pass && !host_done) {
+        const int batch = passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4;   // first look after a handful of passes
+        for (int b = 0; b < batch && passes < max_pass; ++b, ++passes) {
+            aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
+            aa_beta_update_kernel<<<(unsigned)ceil_div(na * 32, 256), 256, 0, st>>>(X, n, d, penalty_M, Zhat, na, p.grad_blocks, candw,
+                                                                                 candi, bst, pidx, bcoef, R, scr);
+            aa_beta_check_kernel<<<1, 32, 0, st>>>(bst, na);
+        }
+        CHR_LAUNCH_CHECK();
+        CHR_CUDA(cudaMemcpyAsync(&host_done, &bst->all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CHR_CUDA(cudaStreamSynchronize(st));
+    }
+    if (beta_passes_out) *beta_passes_out = passes;
+    aa_beta_finish_kernel<<<na, 64, 0, st>>>(X, d, na, bst, pidx, bcoef, Z);
+    // ---- rss
+    aa_rss_kernel<<<p.rss_blocks, 256, (size_t)na * d * 8, st>>>(X, n, d, alphas, Z, na, rsspart);
+    aa_sum_kernel<<<1, 32, 0, st>>>(rsspart, p.rss_blocks, rss_out);
+    timer_end(CHR_FAMILY_AA, true, st);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

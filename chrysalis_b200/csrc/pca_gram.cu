@@ -33,13 +33,8 @@ __global__ void colsum_partial_kernel(const float* __restrict__ P, int64_t n, in
     if (col >= s) return;
     const int64_t r0 = (int64_t)blockIdx.y * kCsRows, r1 = r0 + kCsRows < n ? r0 + kCsRows : n;
     double acc = 0.0;
-    float f = 0.f;
-    int c = 0;
-    for (int64_t r = r0; r < r1; ++r) {
-        f += __ldg(P + r * ld + col);
-        if (++c == 32) { acc += (double)f; f = 0.f; c = 0; }
-    }
-    part[(int64_t)blockIdx.y * s + col] = acc + (double)f;
+    for (int64_t r = r0; r < r1; ++r) acc += (double)__ldg(P + r * ld + col);
+    part[(int64_t)blockIdx.y * s + col] = acc;
 }
 
 __global__ void colsum_final_kernel(const double* __restrict__ part, int nsplit, int64_t s, double* __restrict__ sums) {
