@@ -170,3 +170,110 @@ def pca(adata, n_pcs: int = 50):
         adata.uns['chr_pca']['variance_ratio'] = ratio
         adata.uns['chr_pca']['loadings'] = components
         adata.uns['chr_pca']['features'] = features
+
+
+def _furthest_sum(X: np.ndarray, n_archetypes: int, rs: np.random.RandomState) -> np.ndarray:
+    """FurthestSum seeding (Morup & Hansen 2012) as archetypes 0.4.x draws it: a random start, greedy
+    picks of the point with the largest summed distance to the chosen set, then 10 re-pick rounds."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    sq = np.einsum("ij,ij->i", X, X)
+
+    def dist(i):
+        return np.sqrt(np.maximum(sq - 2.0 * (X @ X[i]) + sq[i], 0.0))
+
+    picks = [int(rs.randint(n))]
+    free = np.ones(n, dtype=bool)
+    free[picks[0]] = False
+    total = np.zeros(n)
+    cur = picks[0]
+    for step in range(1, n_archetypes + 11):
+        if step > n_archetypes - 1:
+            oldest = picks.pop(0)
+            total -= dist(oldest)
+            free[oldest] = True
+        total += dist(cur)
+        cand = np.flatnonzero(free)
+        cur = int(cand[np.argmax(total[cand])])
+        picks.append(cur)
+        free[cur] = False
+    return np.array(picks[:n_archetypes], dtype=np.int64)
+
+
+def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int = 3, tol: float = 0.001,
+             random_state: int = 42, init_rows=None):
+    """Device part of ``aa``: ``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit(X)``
+    (core.py:186-191).  ``init_rows``: optional list of n_init index arrays (matched initialisation).
+    Returns a dict with alphas (N, A), archetypes (A, d), rss, n_iter and the initial rows used."""
+    X = np.ascontiguousarray(np.asarray(X), dtype=np.float64)   # numpy upcasts the float32 scores inside archetypes
+    n, d = X.shape
+    rs = np.random.RandomState(random_state)
+    Xd = dv.to_device(X, torch.float64)
+    best = None
+    used = []
+    for r in range(n_init):
+        if init_rows is not None:
+            rows = np.asarray(init_rows[r], dtype=np.int64)
+        else:
+            rows = _furthest_sum(X, n_archetypes, rs)
+            rs.choice(n_archetypes, n, replace=True)            # alphas0 draw: unused by the updates, keeps the RNG stream
+        used.append(rows)
+        st = dv.AAState(Xd, n_archetypes)
+        st.init_from_rows(rows)
+        rss_prev, rss, it = np.inf, np.inf, 0
+        for it in range(max_iter):
+            rss = st.iterate()
+            if abs(rss_prev - rss) < tol:
+                break
+            rss_prev = rss
+        if best is None or rss < best["rss"]:
+            best = {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
+    out = {"alphas": best["alphas"].cpu().numpy(), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
+           "n_iter": best["n_iter"], "init_rows": used}
+    return out
+
+
+def aa(adata, n_archetypes: int = 8, pca_key: str = None, n_pcs: int = None, max_iter: int = 200):
+    """
+    Run archetypal analysis on the low-dimensional embedding.
+
+    Drop-in for ``chrysalis.aa`` (/root/reference/chrysalis/core.py:140-208).  Needs ``chrysalis.pca`` first.
+
+    :param adata: AnnData (or duck-typed equivalent) of shape ``n_obs`` x ``n_vars``.
+    :param n_archetypes: Number of archetypes (tissue compartments) to be identified.
+    :param pca_key: alternative PCA input from ``.obsm``; by default ``.obsm['chr_X_pca']``.
+    :param n_pcs: Number of PCs to be used (default ``n_archetypes - 1``).
+    :param max_iter: Maximum number of iterations.
+    :return: None; adds ``.obsm['chr_aa']`` and ``.uns['chr_aa']`` with 'archetypes', 'alphas', 'loadings', 'RSS'.
+    """
+    if not isinstance(n_archetypes, int):
+        raise TypeError
+    elif n_archetypes < 2:
+        raise ValueError(f"n_archetypes cannot be less than 2.")
+
+    if n_pcs is None:
+        pcs = n_archetypes - 1
+    else:
+        pcs = n_pcs
+
+    if pca_key is None:
+        emb = adata.obsm['chr_X_pca'][:, :pcs]
+    else:
+        emb = adata.obsm[pca_key][:, :pcs]
+    fit = aa_stage(np.asarray(emb), n_archetypes, max_iter=max_iter)
+
+    adata.obsm['chr_aa'] = fit["alphas"]
+
+    # archetype loadings (core.py:197)
+    aa_loadings = np.dot(fit["archetypes"], adata.uns['chr_pca']['loadings'][:pcs, :])
+
+    if 'chr_aa' not in adata.uns.keys():
+        adata.uns['chr_aa'] = {'archetypes': fit["archetypes"],
+                               'alphas': fit["alphas"],
+                               'loadings': aa_loadings,
+                               'RSS': fit["rss"]}
+    else:
+        adata.uns['chr_aa']['archetypes'] = fit["archetypes"]
+        adata.uns['chr_aa']['alphas'] = fit["alphas"]
+        adata.uns['chr_aa']['loadings'] = aa_loadings
+        adata.uns['chr_aa']['RSS'] = fit["rss"]

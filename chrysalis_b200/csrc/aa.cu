@@ -141,21 +141,26 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
         const double inv = 1.0 / sum;
         for (int a = 0; a < na; ++a) { a_out[a] *= inv; alphas[i * na + a] = a_out[a]; }
     }
-    // CTA-level accumulation in fixed order: threads take turns per (warp-serialised) entry
-    // -> deterministic: each accumulator entry is summed over threads 0..blockDim-1 in order
+    // CTA-level accumulation in fixed order: the CTA's alpha rows go to shared memory, then every
+    // thread owns accumulator entries and sums them over the spots 0..blockDim-1 in order
+    double* As = acc + nacc;              // blockDim x na
+    for (int a = 0; a < na; ++a) As[threadIdx.x * na + a] = valid ? a_out[a] : 0.0;
     __syncthreads();
-    for (int t = 0; t < (int)blockDim.x; ++t) {
-        if ((int)threadIdx.x == t && valid) {
-            const double* __restrict__ x = X + i * d;
-            for (int a = 0; a < na; ++a) {
-                const double va = a_out[a];
-                if (va == 0.0) continue;
-                for (int b = 0; b < na; ++b) acc[a * na + b] += va * a_out[b];
-                for (int q = 0; q < d; ++q) acc[na * na + a * d + q] += va * x[q];
-            }
+    const int64_t i_base = (int64_t)blockIdx.x * blockDim.x;
+    const int nvalid = (int)((n - i_base) < (int64_t)blockDim.x ? (n - i_base) : (int64_t)blockDim.x);
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+        double v = 0.0;
+        if (e < na * na) {
+            const int a = e / na, b = e % na;
+            for (int t = 0; t < nvalid; ++t) v += As[t * na + a] * As[t * na + b];
+        } else {
+            const int a = (e - na * na) / d, q = (e - na * na) % d;
+            const double* __restrict__ xq = X + i_base * d + q;
+            for (int t = 0; t < nvalid; ++t) v += As[t * na + a] * xq[(int64_t)t * d];
         }
-        __syncthreads();
+        acc[e] = v;
     }
+    __syncthreads();
     for (int e = threadIdx.x; e < nacc; e += blockDim.x) part[(size_t)blockIdx.x * nacc + e] = acc[e];
 }
 
@@ -530,10 +535,12 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
 
     timer_begin(CHR_FAMILY_AA, true, st);
     // ---- alphas
-    const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc) * 8;
+    const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc + 128 * na) * 8;
     if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
-    else if (na <= 32) aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
-    else {
+    else if (na <= 32) {
+        CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
+        aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+    } else {
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
         aa_alpha_kernel<64><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
     }

@@ -245,3 +245,40 @@ def pca_scores(P: torch.Tensor, s: int, mean: torch.Tensor, V: torch.Tensor) -> 
     _lib.call("chr_pca_scores_f32", _ptr(P), n, s, ld, _ptr(mean), _ptr(V.contiguous()), r, _ptr(Y), r, _ptr(ws), ws_bytes,
               _stream())
     return Y
+
+
+# ---- K9 - K11: archetypal analysis ---------------------------------------------------------
+
+AA_PENALTY_M = 200.0   # weight of the sum-to-one row in the penalised NNLS problems (archetypes 0.4.x)
+
+
+class AAState:
+    """Device buffers of one AA restart: data X [n, d] float64, archetypes Z, coefficients alphas."""
+
+    def __init__(self, X: torch.Tensor, n_archetypes: int):
+        assert X.dtype == torch.float64 and X.is_contiguous() and X.dim() == 2
+        self.X, self.na = X, int(n_archetypes)
+        n, d = X.shape
+        self.Z = torch.empty((self.na, d), dtype=torch.float64, device=X.device)
+        self.alphas = torch.empty((n, self.na), dtype=torch.float64, device=X.device)
+        self.rss = torch.empty(1, dtype=torch.float64, device=X.device)
+        self.ws_bytes = _lib.query("chr_aa_workspace_bytes", n, d, self.na)
+        self.ws = _workspace(self.ws_bytes, X.device)
+        self.beta_passes = 0
+
+    def init_from_rows(self, rows):
+        """Z = X[rows]: one-hot betas0 (archetypes 0.4.x initialises archetypes on data points)."""
+        n, d = self.X.shape
+        r = torch.as_tensor(np.asarray(rows, dtype=np.int64)).to(self.X.device)
+        _lib.call("chr_aa_init_archetypes", _ptr(self.X), n, d, _ptr(r), self.na, _ptr(self.Z), _stream())
+
+    def iterate(self) -> float:
+        """One alternating-NNLS iteration in place; returns the residual sum of squares."""
+        import ctypes
+
+        n, d = self.X.shape
+        passes = ctypes.c_int(0)
+        _lib.call("chr_aa_iterate", _ptr(self.X), n, d, self.na, AA_PENALTY_M, _ptr(self.Z), _ptr(self.alphas),
+                  _ptr(self.rss), ctypes.addressof(passes), _ptr(self.ws), self.ws_bytes, _stream())
+        self.beta_passes = passes.value
+        return float(self.rss.item())

@@ -125,6 +125,26 @@ int chr_pca_scores_f32(const float* P, int64_t n, int64_t s, int64_t ld, const d
                        const double* V, int r, float* Y, int64_t ldy, void* workspace,
                        size_t workspace_bytes, chr_stream_t stream);
 
+/* ---- K9-K11: archetypal analysis -------------------------------------------------------
+ * replaces  archetypes.AA(n_archetypes, n_init=3, max_iter, tol=0.001, random_state=42).fit(X)
+ *           (/root/reference/chrysalis/core.py:186-191; archetypes==0.4.2: alternating
+ *           penalised NNLS, Cutler & Breiman)
+ * X: [n][d] float64 (the first d PCA scores), Z: [n_archetypes][d] float64 archetypes,
+ * alphas: [n][n_archetypes] float64.  d <= 64, 2 <= n_archetypes <= 64.  The restart loop,
+ * the stopping rule |rss_prev - rss| < tol and the best-of-n_init choice stay on the host
+ * (chrysalis_b200/core.py:aa), like they do in the reference's fit(). */
+size_t chr_aa_workspace_bytes(int64_t n, int d, int n_archetypes);
+/* Z[a] = X[rows[a]]  (one-hot betas0: the initial archetypes are data points); rows: device int64 */
+int chr_aa_init_archetypes(const double* X, int64_t n, int d, const int64_t* rows, int n_archetypes,
+                           double* Z, chr_stream_t stream);
+/* one iteration, in place:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);
+ * Z <- betas X;  *rss_out (device) = ||X - alphas Z||_F^2.  beta_passes_out: HOST int (may be
+ * NULL), number of active-set passes of the beta step.  Synchronises the stream (the beta
+ * step's termination flag is read back). */
+int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, double* Z,
+                   double* alphas, double* rss_out, int* beta_passes_out, void* workspace,
+                   size_t workspace_bytes, chr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

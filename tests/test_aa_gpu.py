@@ -1,0 +1,93 @@
+"""GPU parity of the archetypal-analysis stage (K9-K11) against the CPU restatement of
+archetypes 0.4.x (oracle/aa.py), from matched initialisation.  Bound (north_star): archetype
+proportions within 1e-3 absolute."""
+import numpy as np
+import pytest
+import torch
+
+import chrysalis_b200 as ch
+from chrysalis_b200 import core
+from chrysalis_b200 import device as dv
+from oracle import aa as oaa
+
+pytestmark = pytest.mark.gpu
+
+
+def simplex_data(n, d, a, seed, noise=0.05):
+    """Points near the convex hull of `a` random vertices in d dimensions (what PCA scores of zoned tissue look like)."""
+    rng = np.random.default_rng(seed)
+    V = rng.normal(size=(a, d)) * 3.0
+    W = rng.dirichlet(np.full(a, 0.4), size=n)
+    return (W @ V + rng.normal(0, noise, (n, d))).astype(np.float32)
+
+
+def one_hot_betas(rows, n):
+    B = np.zeros((len(rows), n))
+    B[np.arange(len(rows)), rows] = 1.0
+    return B
+
+
+@pytest.mark.parametrize("n,d,a", [(600, 5, 4), (1500, 8, 6), (4035, 20, 8)])
+def test_single_iteration_matches_oracle(n, d, a):
+    X = simplex_data(n, d, a, seed=n)
+    rows = np.random.default_rng(1).choice(n, a, replace=False)
+    ref = oaa.fit_single(X, np.zeros((n, a)), one_hot_betas(rows, n), max_iter=1)
+    st = dv.AAState(dv.to_device(X.astype(np.float64), torch.float64), a)
+    st.init_from_rows(rows)
+    rss = st.iterate()
+    assert np.abs(st.alphas.cpu().numpy() - ref["alphas"]).max() < 1e-6
+    assert np.abs(st.Z.cpu().numpy() - ref["archetypes"]).max() < 1e-6 * np.abs(ref["archetypes"]).max()
+    assert abs(rss - ref["rss"]) < 1e-6 * ref["rss"]
+    al = st.alphas.cpu().numpy()
+    assert (al >= 0).all() and np.allclose(al.sum(1), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,a,iters", [(900, 8, 5, 30), (2000, 12, 7, 25)])
+def test_fit_from_matched_init(n, d, a, iters):
+    X = simplex_data(n, d, a, seed=7 * n)
+    rows = [np.random.default_rng(s).choice(n, a, replace=False) for s in range(3)]
+    inits = [(np.zeros((n, a)), one_hot_betas(r, n)) for r in rows]
+    ref = oaa.aa_fit(X, a, n_init=3, max_iter=iters, inits=inits)
+    got = core.aa_stage(X, a, max_iter=iters, init_rows=rows)
+    assert got["n_iter"] == ref["n_iter"]
+    assert abs(got["rss"] - ref["rss"]) < 1e-6 * ref["rss"]
+    assert np.abs(got["alphas"] - ref["alphas"]).max() < 1e-3          # north_star bound
+    assert np.abs(got["archetypes"] - ref["archetypes"]).max() < 1e-3 * np.abs(ref["archetypes"]).max()
+
+
+def test_golden_fixture(golden_pca_aa):
+    z = golden_pca_aa
+    X = z["X_pca"][:, :8]
+    rows = [np.argmax(b, axis=1) for b in z["betas0"]]
+    got = core.aa_stage(X, 5, max_iter=30, init_rows=rows)
+    assert np.abs(got["alphas"] - z["alphas"]).max() < 1e-3
+    assert abs(got["rss"] - float(z["rss"])) < 1e-6 * float(z["rss"])
+    assert got["n_iter"] == int(z["n_iter"])
+
+
+def test_default_initialisation_follows_the_oracle_rng():
+    """No init given: FurthestSum draws from RandomState(42) exactly like the restatement."""
+    X = simplex_data(800, 6, 4, seed=3)
+    ref = oaa.aa_fit(X, 4, n_init=3, max_iter=15)
+    got = core.aa_stage(X, 4, max_iter=15)
+    for (a0, b0), rows in zip(ref["inits"], got["init_rows"]):
+        assert np.array_equal(np.argmax(b0, axis=1), rows)
+    assert np.abs(got["alphas"] - ref["alphas"]).max() < 1e-3
+
+
+def test_aa_drop_in_fields():
+    n, s, d, a = 700, 40, 10, 4
+    rng = np.random.default_rng(0)
+    scores = simplex_data(n, d, a, seed=11)
+    ad = ch.AnnDataLite(np.zeros((n, s), dtype=np.float32), obsm={"spatial": np.zeros((n, 2)), "chr_X_pca": scores})
+    ad.uns["chr_pca"] = {"loadings": rng.normal(size=(d, s)).astype(np.float32)}
+    ch.aa(ad, n_archetypes=a, n_pcs=6, max_iter=10)
+    assert ad.obsm["chr_aa"].shape == (n, a)
+    u = ad.uns["chr_aa"]
+    assert u["archetypes"].shape == (a, 6) and u["alphas"].shape == (n, a) and u["loadings"].shape == (a, s)
+    assert np.allclose(u["loadings"], u["archetypes"] @ ad.uns["chr_pca"]["loadings"][:6, :])
+    assert np.isfinite(u["RSS"]) and u["RSS"] > 0
+    # default n_pcs = n_archetypes - 1, alternative embedding via pca_key
+    ad.obsm["other"] = scores * 2.0
+    ch.aa(ad, n_archetypes=a, pca_key="other", max_iter=5)
+    assert ad.uns["chr_aa"]["archetypes"].shape == (a, a - 1)

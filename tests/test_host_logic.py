@@ -68,3 +68,23 @@ def test_top_svg_rule_branches(golden_hex, monkeypatch):
         ch.detect_svgs(ad, top_svg=top, min_morans=thr)
         exp = osvg.select_svgs(z["morans"], z["gene_mask"], top, thr)
         assert np.array_equal(ad.var["spatially_variable"].to_numpy(), exp), (top, thr)
+
+
+def test_aa_argument_errors_precede_any_device_work():
+    ad = ch.AnnDataLite(np.zeros((4, 3), np.float32), obsm={"spatial": np.zeros((4, 2))})
+    with pytest.raises(TypeError):
+        ch.aa(ad, n_archetypes=8.0)                                  # core.py:176-177
+    with pytest.raises(ValueError, match="n_archetypes cannot be less than 2"):
+        ch.aa(ad, n_archetypes=1)                                    # core.py:178-179
+    with pytest.raises(KeyError):
+        ch.aa(ad, n_archetypes=3)                                    # obsm['chr_X_pca'] missing
+
+
+def test_furthest_sum_matches_oracle_draws():
+    from oracle import aa as oaa
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(500, 7))
+    for a in (3, 8, 15):
+        r1, r2 = np.random.RandomState(42), np.random.RandomState(42)
+        assert np.array_equal(core._furthest_sum(X, a, r1), oaa.furthest_sum(X, a, r2))
+        assert r1.randint(1 << 30) == r2.randint(1 << 30)           # same number of draws consumed
