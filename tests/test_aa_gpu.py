@@ -72,7 +72,12 @@ def test_default_initialisation_follows_the_oracle_rng():
     got = core.aa_stage(X, 4, max_iter=15)
     for (a0, b0), rows in zip(ref["inits"], got["init_rows"]):
         assert np.array_equal(np.argmax(b0, axis=1), rows)
-    assert np.abs(got["alphas"] - ref["alphas"]).max() < 1e-3
+    assert abs(got["rss"] - ref["rss"]) < 1e-6 * ref["rss"]
+    # restarts that reach the same optimum differ by a relabelling of the archetypes and tie in rss to
+    # rounding, so the best-of-3 pick may be another labelling: compare after matching columns
+    perm = [int(np.argmin(np.abs(got["archetypes"] - z).sum(1))) for z in ref["archetypes"]]
+    assert sorted(perm) == list(range(4))
+    assert np.abs(got["alphas"][:, perm] - ref["alphas"]).max() < 1e-3
 
 
 def test_aa_drop_in_fields():
