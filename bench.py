@@ -247,7 +247,7 @@ def run_native(args):
     ms_per_step = total_ms / args.steps
     value = world * g_scored / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (moran_ell_kernel): algorithmic bytes = one read of X
+    # roofline of the dominant kernel: algorithmic bytes = one read of X
     # + W indices + per-split partial sums + outputs  
     ld = X.stride(0)
     alg_bytes = 4.0 * n * g_scored + 4.0 * n * k + 8.0 * g_scored
@@ -260,11 +260,13 @@ def run_native(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
-    kern_lists = {1: ["moran_pilot_kernel", "moran_ell_kernel", "moran_finalize_kernel"],
-                  6: ["moran_pilot_kernel", "moran_pair_plan_kernel", "moran_pair_kernel", "moran_finalize_kernel"]}
-    kern_lists[7] = kern_lists[6]
-    kernels = kern_lists.get(args.variant, ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"])
-    main_kernel = [x for x in kernels if x not in ("moran_pilot_kernel", "moran_pair_plan_kernel", "moran_finalize_kernel")][0]
+    plan_kernels = ["sym_init_kernel"] + ["sym_relax_kernel"] * 8 + ["sym_size_kernel", "sym_scan_kernel", "sym_chunkmax_kernel",
+                                                                       "sym_fill_kernel"]
+    if args.variant == 4:
+        kernels = ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"]
+    else:
+        kernels = ["moran_pilot_kernel"] + plan_kernels + ["moran_sym_kernel", "moran_finalize_kernel"]
+    main_kernel = "moran_stream_kernel" if args.variant == 4 else "moran_sym_kernel"
     roofline = {"bound": "hbm", "kernel": main_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),

@@ -5,17 +5,18 @@
 //
 // Layout: X is [n_spots][ld] float32 row-major (row = spot, spots in a spatially coherent
 // order), W is an ELL kNN list nbr[n_spots][k] with implicit weights 1/k (libpysal
-// transform 'R').  A warp owns one spot at a time and 128 consecutive genes of it (one
-// float4 per lane): the own row and the k neighbour rows are coalesced 512-byte segments,
-// every lane accumulates its four genes over the spots of the CTA's spot range, so there
-// is no cross-thread reduction in the streaming loop.  Re-reads of neighbour rows are
-// served by L1/L2 (spots are Hilbert-ordered by the host), HBM sees X once.
+// transform 'R').  A warp owns 128 consecutive genes (one float4 per lane) of the spots it
+// visits: the own row and the neighbour rows are coalesced 512-byte segments, every lane
+// accumulates its four genes over the spots of the CTA's spot range, so there is no
+// cross-thread reduction in the streaming loop.  Re-reads of neighbour rows are served by
+// L1/L2 (spots are Hilbert-ordered by the host), HBM sees X once.
 //
 // Numerics: values are shifted by a per-gene pilot mean p (mean of a fixed
 // spot sample) before any product, so the one-pass identities
 //     z'z  = S2 - n m'^2,      k z'Wz = SW - m' (k S1 + SS) + m'^2 n k       (m' = S1/n)
 // with S1 = sum x', S2 = sum x'^2, SW = sum_i x'_i s_i, SS = sum_i s_i, s_i = sum_{j in N(i)} x'_j
-// carry no cancellation; partial sums are fp32 over 16 spots per warp, then fp64.
+// carry no cancellation; partial sums are fp32 over 16 spots per warp, then fp32 over the CTA's
+// 2048 spots, then fp64.
 #include "common.cuh"
 
 namespace chr {
@@ -26,12 +27,6 @@ constexpr int kGeneTile = 128;   // genes per CTA = 32 lanes x float4
 constexpr int kChunk = 16;       // spots per warp between fp32 -> fp64 flushes
 constexpr int kNStat = 5;        // S1, S2, SW, SS, SQ (Geary numerator * k)
 constexpr int kPilotSample = 512;
-
-__host__ __device__ inline int64_t moran_spots_per_split(int64_t n) {
-    // depends on n only: the summation tree of a gene is identical however genes are sharded
-    int64_t s = round_up<int64_t>(ceil_div<int64_t>(n, 64), 64);
-    return s < 512 ? 512 : s;
-}
 
 // ---- pilot shift: mean of a fixed sample of spots, per gene --------------------------------
 __global__ void moran_pilot_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t ncol,
@@ -47,128 +42,9 @@ __global__ void moran_pilot_kernel(const float* __restrict__ X, int64_t n, int64
     pilot[col] = s / (float)ns;
 }
 
-__device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-__device__ __forceinline__ void f4_fma(float4& a, const float4& b, const float4& c) {
-    a.x = fmaf(b.x, c.x, a.x); a.y = fmaf(b.y, c.y, a.y); a.z = fmaf(b.z, c.z, a.z); a.w = fmaf(b.w, c.w, a.w);
-}
-__device__ __forceinline__ void f4_sqdiff(float4& a, const float4& x, const float4& v) {
-    float d;
-    d = x.x - v.x; a.x = fmaf(d, d, a.x);
-    d = x.y - v.y; a.y = fmaf(d, d, a.y);
-    d = x.z - v.z; a.z = fmaf(d, d, a.z);
-    d = x.w - v.w; a.w = fmaf(d, d, a.w);
-}
-
-struct Acc4 {
-    double v[4];
-    __device__ __forceinline__ void flush(float4& f) {
-        v[0] += (double)f.x; v[1] += (double)f.y; v[2] += (double)f.z; v[3] += (double)f.w;
-        f = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-};
-
 // one elected lane asks the TMA unit to pull a row segment into L2 ahead of use
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// K = compile-time neighbour count (0: runtime k, any value); MINB = CTAs/SM the register
-// budget is sized for; PF = L2 prefetch distance in warp iterations (0 = off)
-template <int K, bool GEARY, int MINB, int PF>
-__global__ void __launch_bounds__(kMoranThreads, MINB)
-moran_ell_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t ncol, const int32_t* __restrict__ nbr,
-                 int k_rt, const float* __restrict__ pilot, int64_t spots_per_split, double* __restrict__ part,
-                 int64_t gpad) {
-    const int k = K ? K : k_rt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t col = (int64_t)blockIdx.x * kGeneTile + lane * 4;
-    const bool active = col < ncol;   // ncol % 4 == 0: a lane is in or out as a whole
-    const int64_t s_begin = (int64_t)blockIdx.y * spots_per_split;
-    const int64_t s_end = s_begin + spots_per_split < n ? s_begin + spots_per_split : n;
-    const float* __restrict__ Xc = X + (active ? col : 0);
-
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) p = ldg_f4(pilot + col);
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 f1 = zero, f2 = zero, fw = zero, fs = zero, fq = zero;
-    Acc4 a1{}, a2{}, aw{}, as{}, aq{};
-    int cnt = 0;
-
-    // bytes of this CTA's 128-gene slab that exist in the row (16-byte multiple)
-    const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
-    const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
-
-    for (int64_t i = s_begin + warp; i < s_end; i += kMoranWarps) {
-        if (PF > 0 && lane == 0) {
-            const int64_t ip = i + (int64_t)PF * kMoranWarps;
-            if (ip < s_end) l2_prefetch_bulk(X + ip * ld + tile_col, tile_bytes);
-        }
-        float4 x = zero, s = zero;
-        if (active) x = ldg_f4(Xc + i * ld);
-        if constexpr (K > 0 && K <= 32) {
-            int my = 0;
-            if (lane < K) my = __ldg(nbr + i * K + lane);
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const int nj = __shfl_sync(0xffffffffu, my, j);
-                if (active) {
-                    float4 v = ldg_f4(Xc + (int64_t)nj * ld);
-                    if (GEARY) f4_sqdiff(fq, x, v);
-                    v.x -= p.x; v.y -= p.y; v.z -= p.z; v.w -= p.w;
-                    f4_add(s, v);
-                }
-            }
-        } else {
-            for (int jb = 0; jb < k; jb += 32) {
-                int my = 0;
-                if (jb + lane < k) my = __ldg(nbr + i * k + jb + lane);
-                const int kk = k - jb < 32 ? k - jb : 32;
-#pragma unroll 4
-                for (int j = 0; j < kk; ++j) {
-                    const int nj = __shfl_sync(0xffffffffu, my, j);
-                    if (active) {
-                        float4 v = ldg_f4(Xc + (int64_t)nj * ld);
-                        if (GEARY) f4_sqdiff(fq, x, v);
-                        v.x -= p.x; v.y -= p.y; v.z -= p.z; v.w -= p.w;
-                        f4_add(s, v);
-                    }
-                }
-            }
-        }
-        x.x -= p.x; x.y -= p.y; x.z -= p.z; x.w -= p.w;
-        f4_add(f1, x);
-        f4_fma(f2, x, x);
-        f4_fma(fw, x, s);
-        f4_add(fs, s);
-        if (++cnt == kChunk) {
-            cnt = 0;
-            a1.flush(f1); a2.flush(f2); aw.flush(fw); as.flush(fs);
-            if (GEARY) aq.flush(fq);
-        }
-    }
-    a1.flush(f1); a2.flush(f2); aw.flush(fw); as.flush(fs);
-    if (GEARY) aq.flush(fq);
-
-    // cross-warp reduction in fixed order, one statistic at a time
-    __shared__ double red[kMoranWarps][kGeneTile];
-    auto reduce_store = [&](const Acc4& a, int st) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) red[warp][lane * 4 + c] = a.v[c];
-        __syncthreads();
-        if (threadIdx.x < kGeneTile) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < kMoranWarps; ++w) t += red[w][threadIdx.x];
-            const int64_t gcol = (int64_t)blockIdx.x * kGeneTile + threadIdx.x;
-            part[((int64_t)blockIdx.y * kNStat + st) * gpad + gcol] = t;
-        }
-        __syncthreads();
-    };
-    reduce_store(a1, 0);
-    reduce_store(a2, 1);
-    reduce_store(aw, 2);
-    reduce_store(as, 3);
-    if (GEARY) reduce_store(aq, 4);
 }
 
 // =============================================================================================
@@ -368,98 +244,245 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
 }
 
 // =============================================================================================
-// v3 pair kernel.  The r1b capture showed the v2 kernel pinned on the L1 data pipe (72 % of its
-// wavefront peak: 9 x 512-byte row reads per spot).  Consecutive spots of the Hilbert order
-// are spatial neighbours and share most of their neighbourhood (union of two closed
-// neighbourhoods: 12.1 rows instead of 18 on a square lattice, 10 on a hex lattice, 12.1 on
-// random points), so spots are processed in PAIRS (a, b) = (2q, 2q+1) and W is re-expressed
-// per pair as three disjoint lists
-//        only-a | common | only-b        (+ flags  b in N(a),  a in N(b))
-//   s_a = sum(only-a) + sum(common) [+ x_b],   s_b = sum(only-b) + sum(common) [+ x_a]
-// which needs 6 row reads and 5.5 adds per spot instead of 9 and 8.  The plan is built from
-// the kNN lists by moran_pair_plan_kernel; lists with duplicate entries or odd shapes take a
-// generic per-spot path (results are identical either way, only the summation order differs).
+// v4 symmetric quad kernel (default).  The r1b capture showed the v2 kernel pinned on the L1 data
+// pipe (72 % of its wavefront peak: 9 x 512-byte row reads per spot and 97 instructions per
+// row slab).  z'Az only needs every UNORDERED pair {i, j} once:
+//        z'Az = sum_{i<j} (a_ij + a_ji) z_i z_j + sum_i a_ii z_i^2
+// so W is re-expressed, once per W, as a plan over QUADS of 4 consecutive spots (consecutive
+// spots of the Hilbert order are spatial neighbours):
+//   * pairs inside a quad      -> 6 coefficients, served from the registers that hold the 4 rows
+//   * every other pair         -> owned by exactly ONE endpoint: (row, coefficient) in that
+//                                 spot's list; owners are balanced so the 4 lists of a quad have
+//                                 nearly equal length R (the quad is processed in R rounds)
+// which needs ~3.9 row reads per spot instead of 9 (square lattice, k = 8).  The mean shift uses
+// csum_i = sum of the external coefficients of spot i; the cross term sum_j indeg_j x_j replaces
+// sum_i s_i (they are the same number), and Geary's numerator follows from one more sum:
+//   sum_ij a_ij (x_i - x_j)^2 = k sum x_i^2 + sum_j indeg_j x_j^2 - 2 x'Ax.
+// Any neighbour list is legal (duplicates, self loops, asymmetric kNN): coefficients are counts.
 // =============================================================================================
-constexpr int kPairRecPad = 4;   // ints before the index list: meta, 3 x pad (keeps lists 16-byte aligned)
-__host__ __device__ constexpr int pair_stride(int k) { return (2 * k + kPairRecPad + 3) & ~3; }   // ints per pair record
+constexpr int kSymHdrWords = 16;      // R, nvalid, c01 c02 | c03 c12 c13 c23 | csum[4] | indeg[4]
+constexpr int kSymRoundWords = 8;     // row[4] | coef[4]
+constexpr int kSymChunkQuads = 32;    // quads staged at once (128 spots)
+constexpr int kSymQuadsPerWarp = kSymChunkQuads / kMoranWarps;   // 4 -> level-1 accumulation over 16 spots
+constexpr int kSymRelaxIters = 8;
+constexpr int kSymOffPad = 48;        // ints reserved per buffer for the chunk's record offsets (33 used)
 
-__host__ __device__ constexpr int pair_ncm(int K) { return K / 2; }
-__host__ __device__ constexpr int pair_nam(int K) { return K / 2 + (K <= 4 ? 1 : 0); }
-
-// meta: n_a | n_c << 8 | n_b << 16 | fa << 24 | fb << 25 | fast << 26 | has_b << 27
-__global__ void moran_pair_plan_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int ncm, int nam,
-                                       int32_t* __restrict__ plan) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t npairs = (n + 1) / 2;
-    if (q >= npairs) return;
-    const int64_t a = 2 * q, b = 2 * q + 1;
-    const bool hasb = b < n;
-    const int stride = pair_stride(k);
-    int32_t* rec = plan + q * stride;
-    const int32_t* A = nbr + a * k;
-    const int32_t* B = nbr + (hasb ? b : a) * k;
-    bool simple = hasb;
-    for (int i = 0; i < k && simple; ++i)
-        for (int j = i + 1; j < k; ++j)
-            if (A[i] == A[j] || B[i] == B[j]) { simple = false; break; }
-    int na = 0, nc = 0, nb = 0, fa = 0, fb = 0;
-    int32_t* out = rec + kPairRecPad;
-    if (!hasb) {
-        for (int i = 0; i < k; ++i) out[na++] = A[i];
-    } else if (!simple) {
-        for (int i = 0; i < k; ++i) out[na++] = A[i];
-        for (int i = 0; i < k; ++i) out[na + nb++] = B[i];
-    } else {
-        // only-a
-        for (int i = 0; i < k; ++i) {
-            const int32_t x = A[i];
-            if (x == (int32_t)b) { fa = 1; continue; }
-            bool inB = false;
-            for (int j = 0; j < k; ++j) inB |= (B[j] == x);
-            if (!inB) out[na++] = x;
-        }
-        // common (order of A)
-        for (int i = 0; i < k; ++i) {
-            const int32_t x = A[i];
-            if (x == (int32_t)b) continue;
-            bool inB = false;
-            for (int j = 0; j < k; ++j) inB |= (B[j] == x);
-            if (inB) out[na + nc++] = x;
-        }
-        // only-b
-        for (int i = 0; i < k; ++i) {
-            const int32_t x = B[i];
-            if (x == (int32_t)a) { fb = 1; continue; }
-            bool inA = false;
-            for (int j = 0; j < k; ++j) inA |= (A[j] == x && x != (int32_t)b);
-            if (!inA) out[na + nc + nb++] = x;
-        }
-    }
-    for (int i = na + nc + nb; i < stride - kPairRecPad; ++i) out[i] = (int32_t)a;   // padding: a valid row
-    const int fast = (hasb && simple && nc <= ncm && na <= nam && nb <= nam) ? 1 : 0;
-    rec[0] = na | (nc << 8) | (nb << 16) | (fa << 24) | (fb << 25) | (fast << 26) | ((hasb ? 1 : 0) << 27);
-    rec[1] = rec[2] = rec[3] = 0;
+__device__ __forceinline__ uint32_t sym_pair_hash(uint32_t i, uint32_t j) {
+    const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+    uint32_t h = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
 }
 
-constexpr int kV3PairsPerWarp = 8;                               // 16 spots: level-1 accumulation length
-constexpr int kV3ChunkPairs = kV3PairsPerWarp * kMoranWarps;     // 64 pairs = 128 spots per CTA chunk
+// own[i] bit a: spot i owns the pair {i, nbr[i][a]}.  Only first occurrences of a neighbour carry a
+// bit; pairs only one endpoint lists are owned by that endpoint; quad-internal and self pairs carry
+// no bit.  Mutual external pairs start with a hash-chosen owner.  cnt[i] = number of owned pairs.
+__global__ void sym_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, uint64_t* __restrict__ own,
+                                int32_t* __restrict__ cnt, int32_t* __restrict__ indeg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* A = nbr + i * k;
+    uint64_t bits = 0;
+    int c = 0;
+    for (int a = 0; a < k; ++a) {
+        const int32_t j = A[a];
+        atomicAdd(indeg + j, 1);
+        bool first = true;
+        for (int b = 0; b < a; ++b) first &= (A[b] != j);
+        if (!first) continue;
+        if (j == (int32_t)i) { ++c; continue; }                        // self loop: one list entry, no bit
+        if ((j >> 2) == (int32_t)(i >> 2)) continue;                   // quad-internal
+        const int32_t* B = nbr + (int64_t)j * k;
+        bool back = false;
+        for (int b = 0; b < k; ++b) back |= (B[b] == (int32_t)i);
+        bool mine = true;
+        if (back) {
+            const uint32_t lo = (uint32_t)(i < j ? i : j);
+            mine = ((sym_pair_hash((uint32_t)i, (uint32_t)j) & 1u) ? lo : (uint32_t)(i ^ j ^ lo)) == (uint32_t)i;
+        }
+        if (mine) { ++c; bits |= 1ull << a; }
+    }
+    own[i] = bits;
+    cnt[i] = c;
+}
 
-template <int K, bool SHIFT, int MINB>
+// one Jacobi sweep of owner balancing: a mutual pair moves to the other endpoint when that lowers
+// the larger of the two list lengths; both endpoints evaluate the same rule on the same data.
+__global__ void sym_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, const uint64_t* __restrict__ own_in,
+                                 const int32_t* __restrict__ cnt_in, uint64_t* __restrict__ own_out, int32_t* __restrict__ cnt_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* A = nbr + i * k;
+    const uint64_t mine_old = own_in[i];
+    uint64_t bits = mine_old;
+    int c = cnt_in[i];
+    const int ci = c;
+    for (int a = 0; a < k; ++a) {
+        const int32_t j = A[a];
+        if (j == (int32_t)i || (j >> 2) == (int32_t)(i >> 2)) continue;
+        bool first = true;
+        for (int b = 0; b < a; ++b) first &= (A[b] != j);
+        if (!first) continue;
+        const int32_t* B = nbr + (int64_t)j * k;
+        int bpos = -1;
+        for (int b = k - 1; b >= 0; --b) if (B[b] == (int32_t)i) bpos = b;    // first occurrence of i in N(j)
+        if (bpos < 0) continue;                                                 // one-sided pair: fixed owner
+        const bool i_owns = (mine_old >> a) & 1ull;
+        const int cj = cnt_in[j];
+        const int c_owner = i_owns ? ci : cj, c_other = i_owns ? cj : ci;
+        const bool flip = (c_owner > c_other + 1) && ((sym_pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
+        if (flip) {
+            if (i_owns) { bits &= ~(1ull << a); --c; }
+            else { bits |= 1ull << a; ++c; }
+        }
+    }
+    own_out[i] = bits;
+    cnt_out[i] = c;
+}
+
+// record size of every quad in 16-byte units
+__global__ void sym_size_kernel(const int32_t* __restrict__ cnt, int64_t n, int64_t nquads, int32_t* __restrict__ qsize) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquads) return;
+    int r = 0;
+    for (int t = 0; t < 4; ++t) {
+        const int64_t i = 4 * q + t;
+        if (i < n && cnt[i] > r) r = cnt[i];
+    }
+    qsize[q] = (kSymHdrWords + kSymRoundWords * r) / 4;
+}
+
+// single-CTA exclusive scan of m ints; out[m] = total
+__global__ void sym_scan_kernel(const int32_t* __restrict__ in, int64_t m, int32_t* __restrict__ out) {
+    __shared__ int64_t sh[1024];
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int64_t per = (m + nt - 1) / nt;
+    const int64_t b = (int64_t)t * per, e = b + per < m ? b + per : m;
+    int64_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += in[i];
+    sh[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < nt; ++i) { int64_t v = sh[i]; sh[i] = run; run += v; }
+        out[m] = (int32_t)run;
+    }
+    __syncthreads();
+    int64_t run = sh[t];
+    for (int64_t i = b; i < e; ++i) { out[i] = (int32_t)run; run += in[i]; }
+}
+
+// largest staged chunk (16-byte units): chunks start at multiples of kSymChunkQuads
+__global__ void sym_chunkmax_kernel(const int32_t* __restrict__ off, int64_t nquads, int32_t* __restrict__ out_max) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q0 = c * kSymChunkQuads;
+    if (q0 >= nquads) return;
+    const int64_t q1 = q0 + kSymChunkQuads < nquads ? q0 + kSymChunkQuads : nquads;
+    atomicMax(out_max, off[q1] - off[q0]);
+}
+
+// one thread per quad writes its record
+__global__ void sym_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t nquads, const uint64_t* __restrict__ own,
+                                const int32_t* __restrict__ indeg, const int32_t* __restrict__ off, int32_t* __restrict__ rec_base) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquads) return;
+    int32_t* rec = rec_base + (int64_t)off[q] * 4;
+    const int R = ((off[q + 1] - off[q]) * 4 - kSymHdrWords) / kSymRoundWords;
+    const int nvalid = (int)(n - 4 * q < 4 ? n - 4 * q : 4);
+    float* recf = reinterpret_cast<float*>(rec);
+    for (int w = 2; w < kSymHdrWords; ++w) recf[w] = 0.f;
+    rec[0] = R;
+    rec[1] = nvalid;
+    for (int r = 0; r < R; ++r)
+        for (int t = 0; t < 4; ++t) {
+            const int64_t self = 4 * q + (t < nvalid ? t : 0);
+            rec[kSymHdrWords + r * kSymRoundWords + t] = (int32_t)self;      // padding: a valid row, coefficient 0
+            recf[kSymHdrWords + r * kSymRoundWords + 4 + t] = 0.f;
+        }
+    for (int t = 0; t < nvalid; ++t) {
+        const int64_t i = 4 * q + t;
+        const int32_t* A = nbr + i * k;
+        const uint64_t bits = own[i];
+        int slot = 0;
+        float csum = 0.f;
+        for (int a = 0; a < k; ++a) {
+            const int32_t j = A[a];
+            bool first = true;
+            int mult = 0;
+            for (int b = 0; b < k; ++b)
+                if (A[b] == j) { if (b < a) first = false; ++mult; }
+            if (!first) continue;
+            float c;
+            bool ext;
+            if (j == (int32_t)i) {
+                c = (float)mult; ext = true;                                   // a_ii z_i^2: own row with coefficient a_ii
+            } else {
+                const int32_t* B = nbr + (int64_t)j * k;
+                int back = 0;
+                for (int b = 0; b < k; ++b) back += (B[b] == (int32_t)i);
+                c = (float)(mult + back);
+                if ((j >> 2) == (int32_t)(i >> 2)) {
+                    // quad-internal: written once, by the lower spot if it lists the pair, else by the upper one
+                    const int u = t, v = (int)(j & 3);
+                    const bool lower = u < v;
+                    if (lower || back == 0) {
+                        const int lo = lower ? u : v, hi = lower ? v : u;
+                        const int idx = lo == 0 ? hi - 1 : (lo == 1 ? hi + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+                        recf[2 + idx] = c;
+                    }
+                    continue;
+                }
+                ext = (bits >> a) & 1ull;
+            }
+            if (!ext || slot >= R) continue;
+            rec[kSymHdrWords + slot * kSymRoundWords + t] = j;
+            recf[kSymHdrWords + slot * kSymRoundWords + 4 + t] = c;
+            csum += c;
+            ++slot;
+        }
+        recf[8 + t] = csum;
+        recf[12 + t] = (float)indeg[i];
+    }
+}
+
+__device__ __forceinline__ f2_t f2_dup(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ void r4_fmac(Row4& s, float c, const Row4& v) {   // s += c * v
+    const f2_t cc = f2_dup(c);
+    s.a = f2_fma(cc, v.a, s.a);
+    s.b = f2_fma(cc, v.b, s.b);
+}
+
+// padded list slots have coefficient 0: their row load is skipped (predicated, no branch)
+__device__ __forceinline__ void ld_row4_if(Row4& v, const char* p, float c) {
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.neu.f32 q, %3, 0f00000000;\n"
+        "@q ld.global.nc.v2.b64 {%0, %1}, [%2];\n"
+        "}\n"
+        : "+l"(v.a), "+l"(v.b)
+        : "l"(p), "f"(c));
+}
+
+template <bool GEARY, bool SHIFT, int MINB>
 __global__ void __launch_bounds__(kMoranThreads, MINB)
-moran_pair_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ plan,
-                  int k_rt, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
-    const int k = K ? K : k_rt;
-    const int stride = pair_stride(k);                            // ints per pair record (multiple of 4)
+moran_sym_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ plan_off,
+                 const int4* __restrict__ plan_rec, int buf_units, const float* __restrict__ pilot, double* __restrict__ part,
+                 int64_t gpad) {
+    constexpr int NST = GEARY ? 5 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t* s_plan = reinterpret_cast<int32_t*>(smem_raw);       // [2][kV3ChunkPairs * stride]
+    // [2][kSymOffPad ints + buf_units x 16 B]  |  level-2 accumulators [NST][256] float4
+    const int buf_bytes = kSymOffPad * 4 + buf_units * 16;
+    float4* s_l2 = reinterpret_cast<float4*>(smem_raw + 2 * buf_bytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
     int64_t col = tile_col + lane * 4;
-    if (col >= ncol) col = tile_col;
+    if (col >= ncol) col = tile_col;                                  // idle lanes shadow lane 0 (results unused)
     const char* __restrict__ base = reinterpret_cast<const char*>(X + col);
-    const int64_t s_begin = (int64_t)blockIdx.y * kV2SpotsPerCta;
-    const int64_t s_end = s_begin + kV2SpotsPerCta < n ? s_begin + kV2SpotsPerCta : n;
-    const int64_t q_begin = s_begin / 2, q_end = (s_end + 1) / 2;  // kV2SpotsPerCta is even
+    const int64_t nquads = (n + 3) >> 2;
+    const int64_t q_begin = (int64_t)blockIdx.y * (kV2SpotsPerCta / 4);
+    const int64_t q_end = q_begin + kV2SpotsPerCta / 4 < nquads ? q_begin + kV2SpotsPerCta / 4 : nquads;
     const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
 
     Row4 p;
@@ -470,116 +493,153 @@ moran_pair_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, in
         p.b = f2_pack(pf.z, pf.w);
     }
     const f2_t z2 = f2_pack(0.f, 0.f);
-    Row4 l1[4], l2[4];
+    Row4 l1[NST];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) { l1[s].a = l1[s].b = z2; l2[s].a = l2[s].b = z2; }
+    for (int s = 0; s < NST; ++s) {
+        l1[s].a = l1[s].b = z2;
+        s_l2[s * kMoranThreads + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // row registers of the two rounds in flight; a skipped (coefficient 0) load leaves the previous finite
+    // row in place, which then contributes 0 * finite = 0
+    Row4 va[4], vb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) va[t].a = va[t].b = vb[t].a = vb[t].b = z2;
 
-    auto ld_shifted = [&](uint32_t row) {
-        Row4 v = ld_row4(base + (uint64_t)row * row_bytes);
-        if (SHIFT) r4_sub(v, p);
-        return v;
-    };
-    auto accumulate = [&](const Row4& x, const Row4& s) {
-        r4_add(l1[0], x);
-        r4_fma(l1[1], x, x);
-        r4_fma(l1[2], x, s);
-        r4_add(l1[3], s);
-    };
-    // each warp stages the records of its own 8 pairs of a chunk (no CTA barrier on the way)
-    const int warp_ints = kV3PairsPerWarp * stride;
-    auto stage = [&](int buf, int64_t q0) {
-        int32_t* dst = s_plan + (buf * kV3ChunkPairs + warp * kV3PairsPerWarp) * stride;
-        const int64_t qw = q0 + warp * kV3PairsPerWarp;
-        int64_t rem = (q_end - qw) * stride;
-        if (rem > warp_ints) rem = warp_ints;
-        const int32_t* src = plan + qw * stride;
-        for (int t = lane * 4; t < rem; t += 128) cp_async_16(dst + t, src + t);
+    auto stage = [&](int buf, int64_t q0) {   // offsets and records of quads [q0, q0 + chunk) -> smem
+        unsigned char* dst = smem_raw + buf * buf_bytes;
+        const int nq = (int)(q_end - q0 < kSymChunkQuads ? q_end - q0 : kSymChunkQuads);
+        if ((int)threadIdx.x <= nq) cp_async_4(dst + threadIdx.x * 4, plan_off + q0 + threadIdx.x);
+        const int u0 = __ldg(plan_off + q0), u1 = __ldg(plan_off + q0 + nq);
+        const int4* src = plan_rec + u0;
+        int4* d4 = reinterpret_cast<int4*>(dst + kSymOffPad * 4);
+        for (int u = threadIdx.x; u < u1 - u0; u += kMoranThreads) cp_async_16(d4 + u, src + u);
         cp_async_commit();
     };
 
     stage(0, q_begin);
-    int buf = 0, chunk_no = 0;
-    for (int64_t q0 = q_begin; q0 < q_end; q0 += kV3ChunkPairs, buf ^= 1, ++chunk_no) {
+    int buf = 0;
+    for (int64_t q0 = q_begin; q0 < q_end; q0 += kSymChunkQuads, buf ^= 1) {
         cp_async_wait_all();
-        __syncwarp();
-        if ((chunk_no & 3) == 3) __syncthreads();                 // keep the warps of a CTA within 4 chunks of each other (L1 sharing)
-        if (q0 + kV3ChunkPairs < q_end) stage(buf ^ 1, q0 + kV3ChunkPairs);
-        const int32_t* my = s_plan + (buf * kV3ChunkPairs + warp * kV3PairsPerWarp) * stride;
-        const int64_t qw = q0 + warp * kV3PairsPerWarp;
-        if (lane < 2 * kV3PairsPerWarp) {                          // own rows of this warp's slice of the next chunk -> L2
-            const int64_t ip = 2 * (qw + kV3ChunkPairs) + lane;
-            if (ip < s_end) l2_prefetch_bulk(reinterpret_cast<const char*>(X + tile_col) + (uint64_t)ip * row_bytes, tile_bytes);
+        __syncthreads();                                              // chunk `buf` visible; previous chunk fully consumed
+        if (q0 + kSymChunkQuads < q_end) stage(buf ^ 1, q0 + kSymChunkQuads);
+        const int32_t* s_off = reinterpret_cast<const int32_t*>(smem_raw + buf * buf_bytes);
+        const int4* s_rec = reinterpret_cast<const int4*>(smem_raw + buf * buf_bytes + kSymOffPad * 4);
+        const int off0 = s_off[0];
+        const int64_t qw = q0 + warp * kSymQuadsPerWarp;
+        // pull this warp's own rows of the next chunk towards L2 while the current one is consumed
+        if (lane < 4 * kSymQuadsPerWarp) {
+            const int64_t ip = 4 * (qw + kSymChunkQuads) + lane;
+            if (ip < 4 * q_end && ip < n)
+                l2_prefetch_bulk(reinterpret_cast<const char*>(X + tile_col) + (uint64_t)ip * row_bytes, tile_bytes);
         }
 #pragma unroll 1
-        for (int pi = 0; pi < kV3PairsPerWarp; ++pi) {
-            const int64_t q = qw + pi;
+        for (int qi = 0; qi < kSymQuadsPerWarp; ++qi) {
+            const int64_t q = qw + qi;
             if (q >= q_end) break;
-            const int32_t* rec = my + pi * stride;
-            const int meta = rec[0];
-            const int na = meta & 0xff, nc = (meta >> 8) & 0xff, nb = (meta >> 16) & 0xff;
-            const bool fa = (meta >> 24) & 1, fb = (meta >> 25) & 1, fast = (meta >> 26) & 1, hasb = (meta >> 27) & 1;
-            const int32_t* idx = rec + kPairRecPad;
-            const uint32_t ra = (uint32_t)(2 * q), rb = hasb ? ra + 1 : ra;
-            const Row4 xa = ld_shifted(ra);
-            const Row4 xb = ld_shifted(rb);
-            Row4 sa, sb;
-            sa.a = sa.b = sb.a = sb.b = z2;
-            bool done = false;
-            if constexpr (K > 0) {
-                if (fast) {
-                    constexpr int NCM = pair_ncm(K), NAM = pair_nam(K);
-                    Row4 va[NAM], vc[NCM], vb[NAM];
+            const int4* rec = s_rec + (s_off[warp * kSymQuadsPerWarp + qi] - off0);
+            const int4 h0 = rec[0];
+            const int R = h0.x, nvalid = h0.y;
+            const uint32_t r0 = (uint32_t)(4 * q);
+            Row4 x[4], s[4];
 #pragma unroll
-                    for (int j = 0; j < NAM; ++j) if (j < na) va[j] = ld_shifted((uint32_t)idx[j]);
+            for (int t = 0; t < 4; ++t) {
+                x[t] = ld_row4(base + (uint64_t)(r0 + (t < nvalid ? t : 0)) * row_bytes);
+                s[t].a = s[t].b = z2;
+            }
+            // two rounds per trip: 8 independent row loads in flight, then 16 multiply-adds
+            int r = 0;
+#pragma unroll 1
+            for (; r + 1 < R; r += 2) {
+                const int4 rows0 = rec[4 + 2 * r], rows1 = rec[6 + 2 * r];
+                const float4 cf0 = *reinterpret_cast<const float4*>(rec + 5 + 2 * r);
+                const float4 cf1 = *reinterpret_cast<const float4*>(rec + 7 + 2 * r);
+                const int rr0[4] = {rows0.x, rows0.y, rows0.z, rows0.w}, rr1[4] = {rows1.x, rows1.y, rows1.z, rows1.w};
+                const float cc0[4] = {cf0.x, cf0.y, cf0.z, cf0.w}, cc1[4] = {cf1.x, cf1.y, cf1.z, cf1.w};
 #pragma unroll
-                    for (int j = 0; j < NCM; ++j) if (j < nc) vc[j] = ld_shifted((uint32_t)idx[na + j]);
+                for (int t = 0; t < 4; ++t) ld_row4_if(va[t], base + (uint64_t)(uint32_t)rr0[t] * row_bytes, cc0[t]);
 #pragma unroll
-                    for (int j = 0; j < NAM; ++j) if (j < nb) vb[j] = ld_shifted((uint32_t)idx[na + nc + j]);
-                    Row4 sc;
-                    sc.a = sc.b = z2;
+                for (int t = 0; t < 4; ++t) ld_row4_if(vb[t], base + (uint64_t)(uint32_t)rr1[t] * row_bytes, cc1[t]);
 #pragma unroll
-                    for (int j = 0; j < NCM; ++j) if (j < nc) r4_add(sc, vc[j]);
-                    sa = sc;
-                    sb = sc;
+                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc0[t], va[t]);
 #pragma unroll
-                    for (int j = 0; j < NAM; ++j) if (j < na) r4_add(sa, va[j]);
+                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc1[t], vb[t]);
+            }
+            if (r < R) {
+                const int4 rows0 = rec[4 + 2 * r];
+                const float4 cf0 = *reinterpret_cast<const float4*>(rec + 5 + 2 * r);
+                const int rr0[4] = {rows0.x, rows0.y, rows0.z, rows0.w};
+                const float cc0[4] = {cf0.x, cf0.y, cf0.z, cf0.w};
 #pragma unroll
-                    for (int j = 0; j < NAM; ++j) if (j < nb) r4_add(sb, vb[j]);
-                    if (fa) r4_add(sa, xb);
-                    if (fb) r4_add(sb, xa);
-                    done = true;
+                for (int t = 0; t < 4; ++t) ld_row4_if(va[t], base + (uint64_t)(uint32_t)rr0[t] * row_bytes, cc0[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc0[t], va[t]);
+            }
+            const float4 h1 = *reinterpret_cast<const float4*>(rec + 1);   // c03 c12 c13 c23
+            const float4 cs = *reinterpret_cast<const float4*>(rec + 2);   // csum
+            const float4 dg = *reinterpret_cast<const float4*>(rec + 3);   // indeg
+            if (SHIFT) {
+                const float ncs[4] = {-cs.x, -cs.y, -cs.z, -cs.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    r4_sub(x[t], p);
+                    r4_fmac(s[t], ncs[t], p);
                 }
             }
-            if (!done) {   // generic per-spot path: a reads only-a|common, b reads common|only-b
-                const int la = na + nc, lb = nc + nb;
-#pragma unroll 4
-                for (int j = 0; j < la; ++j) r4_add(sa, ld_shifted((uint32_t)idx[j]));
-#pragma unroll 4
-                for (int j = 0; j < lb; ++j) r4_add(sb, ld_shifted((uint32_t)idx[na + j]));
-                if (fa) r4_add(sa, xb);
-                if (fb) r4_add(sb, xa);
-            }
-            accumulate(xa, sa);
-            if (hasb) accumulate(xb, sb);
-        }
+            // pairs inside the quad
+            r4_fmac(s[0], __int_as_float(h0.z), x[1]);
+            r4_fmac(s[0], __int_as_float(h0.w), x[2]);
+            r4_fmac(s[0], h1.x, x[3]);
+            r4_fmac(s[1], h1.y, x[2]);
+            r4_fmac(s[1], h1.z, x[3]);
+            r4_fmac(s[2], h1.w, x[3]);
+            const float dgs[4] = {dg.x, dg.y, dg.z, dg.w};
+            auto accumulate = [&](int t) {
+                r4_add(l1[0], x[t]);
+                r4_fma(l1[1], x[t], x[t]);
+                r4_fma(l1[2], x[t], s[t]);
+                if (GEARY) {
+                    Row4 dx;
+                    const f2_t dd = f2_dup(dgs[t]);
+                    dx.a = f2_fma(dd, x[t].a, z2);
+                    dx.b = f2_fma(dd, x[t].b, z2);
+                    r4_add(l1[3], dx);
+                    r4_fma(l1[4], dx, x[t]);
+                } else {
+                    r4_fmac(l1[3], dgs[t], x[t]);
+                }
+            };
+            if (nvalid == 4) {                                        // every quad but the last one of a ragged n
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            r4_add(l2[s], l1[s]);
-            l1[s].a = l1[s].b = z2;
+                for (int t = 0; t < 4; ++t) accumulate(t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t < nvalid) accumulate(t);
+            }
+        }
+        // level-1 -> level-2 (every 16 spots of this warp)
+#pragma unroll
+        for (int st = 0; st < NST; ++st) {
+            float4 acc = s_l2[st * kMoranThreads + threadIdx.x];
+            float f0, f1, f2, f3;
+            f2_unpack(l1[st].a, f0, f1);
+            f2_unpack(l1[st].b, f2, f3);
+            acc.x += f0; acc.y += f1; acc.z += f2; acc.w += f3;
+            s_l2[st * kMoranThreads + threadIdx.x] = acc;
+            l1[st].a = l1[st].b = z2;
         }
     }
 
+    // level-2 -> fp64, cross-warp reduction in fixed order, one statistic at a time
     __syncthreads();
-    double* red = reinterpret_cast<double*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw);               // [kMoranWarps][kGeneTile] (reuses the staging buffers)
 #pragma unroll
-    for (int st = 0; st < 4; ++st) {
-        float f0, f1, f2, f3;
-        f2_unpack(l2[st].a, f0, f1);
-        f2_unpack(l2[st].b, f2, f3);
-        red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
-        red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
-        red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
-        red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
+    for (int st = 0; st < NST; ++st) {
+        const float4 acc = s_l2[st * kMoranThreads + threadIdx.x];
+        red[warp * kGeneTile + lane * 4 + 0] = (double)acc.x;
+        red[warp * kGeneTile + lane * 4 + 1] = (double)acc.y;
+        red[warp * kGeneTile + lane * 4 + 2] = (double)acc.z;
+        red[warp * kGeneTile + lane * 4 + 3] = (double)acc.w;
         __syncthreads();
         if (threadIdx.x < kGeneTile) {
             double t = 0.0;
@@ -593,7 +653,7 @@ moran_pair_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, in
 
 // ---- finalize: fixed-order sum of the split partials, then the statistic in fp64 ------------
 __global__ void moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad, int64_t g, int64_t n, int k,
-                                      const float* __restrict__ pilot, bool geary, double* __restrict__ out_I,
+                                      const float* __restrict__ pilot, bool geary, bool sym, double* __restrict__ out_I,
                                       double* __restrict__ out_C, double* __restrict__ out_stats) {
     int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= g) return;
@@ -607,45 +667,45 @@ __global__ void moran_finalize_kernel(const double* __restrict__ part, int nspli
     const double zwz = (S[2] - m * (dk * S[0] + S[3]) + m * m * dn * dk) / dk;  // z' W z, W = Adj / k
     // I = (n / s0) * z'Wz / z'z with s0 = n for row-standardised kNN weights
     out_I[col] = zwz / zz;
-    if (geary && out_C) out_C[col] = (dn - 1.0) * (S[4] / dk) / (2.0 * dn * zz);
+    // Geary numerator * k = sum_ij adj_ij (x_i - x_j)^2: accumulated directly (stream kernel) or from
+    // k sum x^2 + sum_j indeg_j x_j^2 - 2 x'Ax (symmetric kernel; S[4] = sum_j indeg_j x_j^2)
+    const double gnum = geary ? (sym ? dk * S[1] + S[4] - 2.0 * S[2] : S[4]) : 0.0;
+    if (geary && out_C) out_C[col] = (dn - 1.0) * (gnum / dk) / (2.0 * dn * zz);
     if (out_stats) {
         out_stats[0 * g + col] = m + (double)pilot[col];   // pilot is all-zero for pre-shifted input
         out_stats[1 * g + col] = zz;
         out_stats[2 * g + col] = zwz;
-        out_stats[3 * g + col] = geary ? S[4] / dk : 0.0;
+        out_stats[3 * g + col] = gnum / dk;
     }
 }
 
 struct MoranPlan {
-    int64_t spots_per_split, gpad;
+    int64_t gpad, nquads;
     int nsplit, ntile;
-    size_t pilot_off, part_off, pair_off, total;
+    size_t pilot_off, part_off, own_off[2], cnt_off[2], indeg_off, qsize_off, qoff_off, scal_off, rec_off, rec_bytes, total;
 };
 
-static MoranPlan moran_plan(int64_t n, int64_t g, int64_t ld, bool v2, int k) {
+static MoranPlan moran_plan(int64_t n, int64_t ld, int k) {
     MoranPlan p;
-    p.spots_per_split = v2 ? kV2SpotsPerCta : moran_spots_per_split(n);
-    p.nsplit = (int)ceil_div<int64_t>(n, p.spots_per_split);
+    p.nsplit = (int)ceil_div<int64_t>(n, kV2SpotsPerCta);
     p.ntile = (int)ceil_div<int64_t>(ld, kGeneTile);
     p.gpad = (int64_t)p.ntile * kGeneTile;
-    p.pilot_off = 0;
-    p.part_off = round_up<size_t>((size_t)p.gpad * sizeof(float), 256);
-    p.pair_off = round_up<size_t>(p.part_off + (size_t)p.nsplit * kNStat * p.gpad * sizeof(double), 256);
-    p.total = p.pair_off + (size_t)((n + 1) / 2) * pair_stride(k) * sizeof(int32_t);
+    p.nquads = (n + 3) / 4;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += round_up<size_t>(b, 256); return r; };
+    p.pilot_off = take((size_t)p.gpad * sizeof(float));
+    p.part_off = take((size_t)p.nsplit * kNStat * p.gpad * sizeof(double));
+    // symmetric-plan scratch: owner masks and list lengths (ping-pong), in-degrees, record sizes / offsets, records
+    for (int b = 0; b < 2; ++b) { p.own_off[b] = take((size_t)n * 8); p.cnt_off[b] = take((size_t)n * 4); }
+    p.indeg_off = take((size_t)n * 4);
+    p.qsize_off = take((size_t)(p.nquads + 1) * 4);
+    p.qoff_off = take((size_t)(p.nquads + 1) * 4);
+    p.scal_off = take(256);
+    // every pair is owned once and a spot owns at most k pairs: sum of rounds over quads <= n * k
+    p.rec_bytes = (size_t)p.nquads * kSymHdrWords * 4 + (size_t)n * (size_t)(k < 64 ? k : 64) * kSymRoundWords * 4;
+    p.rec_off = take(p.rec_bytes);
+    p.total = o;
     return p;
-}
-
-template <bool GEARY, int MINB, int PF>
-static void launch_ell(int k, dim3 grid, cudaStream_t st, const float* X, int64_t n, int64_t ld, int64_t ncol,
-                       const int32_t* nbr, const float* pilot, int64_t sps, double* part, int64_t gpad) {
-#define CHR_ELL(KK) moran_ell_kernel<KK, GEARY, MINB, PF><<<grid, kMoranThreads, 0, st>>>(X, n, ld, ncol, nbr, k, pilot, sps, part, gpad)
-    switch (k) {
-        case 4: CHR_ELL(4); break;
-        case 6: CHR_ELL(6); break;
-        case 8: CHR_ELL(8); break;
-        default: CHR_ELL(0); break;
-    }
-#undef CHR_ELL
 }
 
 }  // namespace chr
@@ -655,10 +715,7 @@ extern "C" {
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags) {
     (void)flags;
     if (n_spots <= 0 || n_genes <= 0) return 256;
-    const int64_t ldc = chr::round_up<int64_t>(n_genes, 4);
-    const int kk = k > 0 ? k : 1;
-    const size_t a = chr::moran_plan(n_spots, n_genes, ldc, false, kk).total, b = chr::moran_plan(n_spots, n_genes, ldc, true, kk).total;
-    return (a > b ? a : b) + 512;
+    return chr::moran_plan(n_spots, chr::round_up<int64_t>(n_genes, 4), k > 0 ? k : 1).total + 512;
 }
 
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld, const int32_t* nbr, int k,
@@ -672,73 +729,83 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     CHR_REQUIRE(ld >= n_genes && ld % 4 == 0, "chr_moran_dense_f32: ld (%lld) must be >= n_genes and a multiple of 4", (long long)ld);
     CHR_REQUIRE(((uintptr_t)X & 15) == 0, "chr_moran_dense_f32: X must be 16-byte aligned");
     CHR_REQUIRE(X && nbr && out_I && workspace, "chr_moran_dense_f32: null pointer argument");
+    CHR_REQUIRE(n_spots < (1LL << 31) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: needs n_spots < 2^31, row bytes < 2^32");
     const bool geary = flags & CHR_FLAG_GEARY;
     CHR_REQUIRE(!geary || out_C, "chr_moran_dense_f32: CHR_FLAG_GEARY needs out_C");
     const bool timing = flags & CHR_FLAG_TIMING;
 
-    // the kernel reads ld columns; statistics are kept for the first round_up(n_genes,4) <= ld
-    const int64_t ldc = round_up<int64_t>(n_genes, 4);
+    // the kernels read round_up(n_genes, 4) <= ld columns
+    const int64_t ncol = round_up<int64_t>(n_genes, 4);
     const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
     const bool preshifted = flags & CHR_FLAG_PRESHIFTED;
-    // variant 0/4: stream kernel (v2, default).  1: v1 ELL kernel, 6/7: v3 pair kernel (kept for regression / tuning)
-    const bool v1 = variant == 1 && !geary;
-    const bool v3 = !geary && (variant == 6 || variant == 7);
-    const bool v2 = !v1;   // v2 and v3 share the 2048-spot split structure
-    CHR_REQUIRE(!preshifted || !v1, "chr_moran_dense_f32: CHR_FLAG_PRESHIFTED is not supported by the v1 kernel");
-    MoranPlan p = moran_plan(n_spots, n_genes, ldc, v2, k);
+    // variant 0: symmetric quad kernel (v4, k <= 64).  variant 4 / k > 64: per-spot stream kernel (v2)
+    const bool sym = variant != 4 && k <= 64;
+    MoranPlan p = moran_plan(n_spots, ncol, k);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* pilot = (float*)(ws + p.pilot_off);
     double* part = (double*)(ws + p.part_off);
 
-    // columns the kernels touch: [0, ncol), ncol % 4 == 0, ncol <= ld and <= gpad
-    const int64_t ncol = ldc;
     if (preshifted) CHR_CUDA(cudaMemsetAsync(pilot, 0, (size_t)p.gpad * sizeof(float), st));
     else moran_pilot_kernel<<<(unsigned)ceil_div<int64_t>(ncol, 256), 256, 0, st>>>(X, n_spots, ld, ncol, pilot);
     CHR_LAUNCH_CHECK();
 
     dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
-#define CHR_ARGS k, grid, st, X, n_spots, ld, ncol, nbr, pilot, p.spots_per_split, part, p.gpad
-    if (v3) {
-        CHR_REQUIRE(n_spots < (1LL << 31) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: pair kernel needs n_spots < 2^31, row bytes < 2^32");
-        CHR_REQUIRE(k <= 120, "chr_moran_dense_f32: pair kernel supports k <= 120");
-        int32_t* pair_plan = (int32_t*)(ws + p.pair_off);
-        const int64_t npairs = (n_spots + 1) / 2;
-        const int ncm = (k == 4 || k == 6 || k == 8) ? pair_ncm(k) : -1, nam = (k == 4 || k == 6 || k == 8) ? pair_nam(k) : -1;
-        moran_pair_plan_kernel<<<(unsigned)ceil_div<int64_t>(npairs, 128), 128, 0, st>>>(nbr, n_spots, k, ncm, nam, pair_plan);
+    const uint32_t rb = (uint32_t)(ld * 4);
+    if (sym) {
+        // ---- W -> symmetric quad plan (depends on W only)
+        uint64_t* own[2] = {(uint64_t*)(ws + p.own_off[0]), (uint64_t*)(ws + p.own_off[1])};
+        int32_t* cnt[2] = {(int32_t*)(ws + p.cnt_off[0]), (int32_t*)(ws + p.cnt_off[1])};
+        int32_t* indeg = (int32_t*)(ws + p.indeg_off);
+        int32_t* qsize = (int32_t*)(ws + p.qsize_off);
+        int32_t* qoff = (int32_t*)(ws + p.qoff_off);
+        int32_t* scal = (int32_t*)(ws + p.scal_off);
+        int32_t* rec = (int32_t*)(ws + p.rec_off);
+        const unsigned gs = (unsigned)ceil_div<int64_t>(n_spots, 128), gq = (unsigned)ceil_div<int64_t>(p.nquads, 128);
+        CHR_CUDA(cudaMemsetAsync(indeg, 0, (size_t)n_spots * 4, st));
+        CHR_CUDA(cudaMemsetAsync(scal, 0, 256, st));
+        sym_init_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, own[0], cnt[0], indeg);
+        int cur = 0;
+        for (int it = 0; it < kSymRelaxIters; ++it, cur ^= 1)
+            sym_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
+        sym_size_kernel<<<gq, 128, 0, st>>>(cnt[cur], n_spots, p.nquads, qsize);
+        sym_scan_kernel<<<1, 1024, 0, st>>>(qsize, p.nquads, qoff);
+        sym_chunkmax_kernel<<<(unsigned)ceil_div<int64_t>(ceil_div<int64_t>(p.nquads, kSymChunkQuads), 128), 128, 0, st>>>(qoff, p.nquads, scal);
+        sym_fill_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, p.nquads, own[cur], indeg, qoff, rec);
         CHR_LAUNCH_CHECK();
-        size_t smem = (size_t)2 * kV3ChunkPairs * pair_stride(k) * sizeof(int32_t);
-        if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
-        const uint32_t rb = (uint32_t)(ld * 4);
+        int chunk_units = 0;
+        CHR_CUDA(cudaMemcpyAsync(&chunk_units, scal, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CHR_CUDA(cudaStreamSynchronize(st));
+        const int buf_units = chunk_units < 256 ? 256 : chunk_units;      // the final reduction reuses >= 8 KB of the buffers
+        const int nst = geary ? 5 : 4;
+        const size_t smem = (size_t)2 * (kSymOffPad * 4 + (size_t)buf_units * 16) + (size_t)nst * kMoranThreads * 16;
+        CHR_REQUIRE(smem <= 200 * 1024, "chr_moran_dense_f32: neighbour lists too long for the staged plan (%zu B of shared memory)", smem);
         timer_begin(CHR_FAMILY_MORAN, timing, st);
-#define CHR_V3(KK, SH, MB)                                                                                          \
+#define CHR_V4(GG, SH)                                                                                              \
     do {                                                                                                            \
-        auto kern = moran_pair_kernel<KK, SH, MB>;                                                                 \
-        if (smem > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, pair_plan, k, pilot, part, p.gpad);         \
+        if (variant == 5) CHR_V4M(GG, SH, 1); else CHR_V4M(GG, SH, 2);                                             \
     } while (0)
-#define CHR_V3K(SH, MB)                                  \
-    switch (k) {                                         \
-        case 4: CHR_V3(4, SH, MB); break;                \
-        case 6: CHR_V3(6, SH, MB); break;                \
-        case 8: CHR_V3(8, SH, MB); break;                \
-        default: CHR_V3(0, SH, MB); break;               \
-    }
-        if (preshifted) { CHR_V3K(false, 2) }
-        else if (variant == 7) { CHR_V3K(true, 1) }
-        else { CHR_V3K(true, 2) }
-#undef CHR_V3K
-#undef CHR_V3
-    } else if (v2) {
-        CHR_REQUIRE(n_spots < (1LL << 32) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: v2 kernel needs n_spots, row bytes < 2^32");
+#define CHR_V4M(GG, SH, MB)                                                                                         \
+    do {                                                                                                            \
+        auto kern = moran_sym_kernel<GG, SH, MB>;                                                                    \
+        CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, qoff, (const int4*)rec, buf_units, pilot, part, p.gpad); \
+    } while (0)
+        if (geary && preshifted) CHR_V4(true, false);
+        else if (geary) CHR_V4(true, true);
+        else if (preshifted) CHR_V4(false, false);
+        else CHR_V4(false, true);
+#undef CHR_V4
+#undef CHR_V4M
+    } else {
         const int vec16 = (k % 4 == 0) && (((uintptr_t)nbr & 15) == 0);
         size_t smem = (size_t)2 * kV2Chunk * k * sizeof(int32_t);
         if (smem < sizeof(double) * kMoranWarps * kGeneTile) smem = sizeof(double) * kMoranWarps * kGeneTile;
-        const uint32_t rb = (uint32_t)(ld * 4);
+        CHR_REQUIRE(smem <= 200 * 1024, "chr_moran_dense_f32: k too large (%d)", k);
         timer_begin(CHR_FAMILY_MORAN, timing, st);
 #define CHR_V2(KK, GG, MB, SH)                                                                                      \
     do {                                                                                                            \
-        auto kern = moran_stream_kernel<KK, GG, MB, SH>;                                                               \
+        auto kern = moran_stream_kernel<KK, GG, MB, SH>;                                                           \
         if (smem > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, nbr, k, vec16, pilot, part, p.gpad);        \
     } while (0)
@@ -755,16 +822,12 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
         else { CHR_V2K(false, 2, true) }
 #undef CHR_V2K
 #undef CHR_V2
-    } else {
-        timer_begin(CHR_FAMILY_MORAN, timing, st);
-        launch_ell<false, 2, 8>(CHR_ARGS);
     }
-#undef CHR_ARGS
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();
 
     moran_finalize_kernel<<<(unsigned)ceil_div<int64_t>(n_genes, 256), 256, 0, st>>>(
-        part, p.nsplit, p.gpad, n_genes, n_spots, k, pilot, geary, out_I, out_C, out_stats);
+        part, p.nsplit, p.gpad, n_genes, n_spots, k, pilot, geary, sym, out_I, out_C, out_stats);
     CHR_LAUNCH_CHECK();
     return 0;
 }
