@@ -66,10 +66,11 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     rank = torch.empty_like(order)
     rank[order] = torch.arange(n, device=order.device)
     nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
+    plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
     # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
     dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank, apply_log1p=not already_log1p)
     # core.py:71-76  the gene loop
-    I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing)
+    I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
     return keep.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
 
 

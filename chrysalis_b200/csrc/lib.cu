@@ -1,5 +1,5 @@
 // Library-level plumbing of the C ABI: version, thread-local error string, kernel timers.
-#include "common.cuh"
+#include "async.cuh"
 
 namespace chr {
 
@@ -32,6 +32,18 @@ void timer_end(int family, bool on, cudaStream_t s) {
     KernelTimer& t = timer(family);
     cudaEventRecord(t.b, s);
     t.armed = true;
+}
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
 }
 
 }  // namespace chr

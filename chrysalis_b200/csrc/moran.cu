@@ -4,83 +4,66 @@
 // [+ esda.geary.Geary(...).C]  of /root/reference/chrysalis/core.py:71-76.
 //
 // Layout: X is [n_spots][ld] float32 row-major (row = spot, spots in a spatially coherent
-// order), W is an ELL kNN list nbr[n_spots][k] with implicit weights 1/k (libpysal
-// transform 'R').  A warp owns 128 consecutive genes (one float4 per lane) of the spots it
-// visits: the own row and the neighbour rows are coalesced 512-byte segments, every lane
-// accumulates its four genes over the spots of the CTA's spot range, so there is no
-// cross-thread reduction in the streaming loop.  Re-reads of neighbour rows are served by
-// L1/L2 (spots are Hilbert-ordered by the host), HBM sees X once.
+// order).  A CTA owns a 128-gene column slab and a range of spots; a warp owns one row slab at
+// a time (128 genes = one float4 per lane = one coalesced 512-byte segment), every lane
+// accumulates its four genes over the spots it visits, so there is no cross-thread reduction in
+// the streaming loop.
+//
+// Default kernel (moran_tile_kernel): the slab is streamed HBM -> shared memory by TMA in tiles of
+// 128 spots x 128 genes (64 KB, double buffered, a producer warp and mbarriers - no CTA barrier in
+// the loop) together with the tile's slice of the quad plan of W (moran_plan.cu).  16 compute
+// warps walk the quads of the tile: own rows and in-tile neighbour rows are read from the staged
+// tile, the few out-of-tile rows through L1/L2.  HBM sees X once.
 //
 // Numerics: values are shifted by a per-gene pilot mean p (mean of a fixed
 // spot sample) before any product, so the one-pass identities
-//     z'z  = S2 - n m'^2,      k z'Wz = SW - m' (k S1 + SS) + m'^2 n k       (m' = S1/n)
-// with S1 = sum x', S2 = sum x'^2, SW = sum_i x'_i s_i, SS = sum_i s_i, s_i = sum_{j in N(i)} x'_j
-// carry no cancellation; partial sums are fp32 over 16 spots per warp, then fp32 over the CTA's
-// 2048 spots, then fp64.
-#include "common.cuh"
+//     z'z  = S2 - n m'^2,      k z'Wz = SW - m' (k S1 + SC) + m'^2 n k       (m' = S1/n)
+// with S1 = sum x', S2 = sum x'^2, SW = x''A x', SC = 1'A x' = sum_j indeg_j x'_j
+// carry no cancellation; partial sums are fp32 over the 8 spots a warp visits per tile, then fp32
+// over the CTA's tiles, then fp64.
+#include "async.cuh"
+#include "moran.cuh"
 
 namespace chr {
 
 constexpr int kMoranThreads = 256;
 constexpr int kMoranWarps = kMoranThreads / 32;
-constexpr int kGeneTile = 128;   // genes per CTA = 32 lanes x float4
-constexpr int kChunk = 16;       // spots per warp between fp32 -> fp64 flushes
-constexpr int kNStat = 5;        // S1, S2, SW, SS, SQ (Geary numerator * k)
 constexpr int kPilotSample = 512;
+constexpr int kPilotSplit = 8;
 
-// ---- pilot shift: mean of a fixed sample of spots, per gene --------------------------------
-__global__ void moran_pilot_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t ncol,
-                                   float* __restrict__ pilot) {
-    int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncol) return;
+// ---- pilot shift: mean of a fixed sample of spots, per gene (fixed summation order) -----------
+__global__ void __launch_bounds__(64 * kPilotSplit)
+moran_pilot_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t ncol, float* __restrict__ pilot) {
+    __shared__ float red[kPilotSplit][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int64_t col = (int64_t)blockIdx.x * 64 + tx;
     const int ns = n < kPilotSample ? (int)n : kPilotSample;
     float s = 0.f;
-    for (int t = 0; t < ns; ++t) {
-        int64_t i = (int64_t)t * n / ns;
-        s += __ldg(X + i * ld + col);
+    if (col < ncol) {
+#pragma unroll 8
+        for (int t = ty; t < ns; t += kPilotSplit) {
+            const int64_t i = (int64_t)t * n / ns;
+            s += __ldg(X + i * ld + col);
+        }
     }
-    pilot[col] = s / (float)ns;
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && col < ncol) {
+        float a = 0.f;
+#pragma unroll
+        for (int y = 0; y < kPilotSplit; ++y) a += red[y][tx];
+        pilot[col] = a / (float)ns;
+    }
 }
 
+// =============================================================================================
+// per-spot stream kernel (variant 4; fallback for k > 64).  W's neighbour lists are staged in
+// shared memory 128 spots at a time by cp.async; every warp works on 2 spots at once (18
+// independent 512-byte row loads in flight); packed f32x2 arithmetic; rows served by L1/L2.
+// =============================================================================================
 // one elected lane asks the TMA unit to pull a row segment into L2 ahead of use
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// =============================================================================================
-// v2 streaming kernel.  Same mathematics, restructured after the first ncu capture
-// (profiles/r1a: 243 instructions and ~1700 cycles per spot-row, issue 57 %, 16 warps/SM):
-//   * W's neighbour lists are staged in shared memory, 128 spots at a time, by cp.async one
-//     chunk ahead, so the gather addresses never wait on a global load
-//   * every warp works on U = 2 spots at once: 18 independent 512-byte row loads in flight
-//   * all arithmetic is packed f32x2 (FADD2 / FFMA2): half the issue slots of scalar FP32
-//   * accumulation is two-level fp32 in registers (16 spots, then 16 x 16 spots); a CTA covers
-//     only 2048 spots, partial sums leave the CTA as fp64 - no fp64 and no F2F in the loop
-//   * row addresses are one IMAD.WIDE.U32 each (row index x row bytes + base)
-// =============================================================================================
-typedef unsigned long long f2_t;  // two packed fp32 values in a 64-bit register pair
-
-__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
-__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) { f2_t c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
-__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2_t f2_pack(float x, float y) { f2_t c; asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(x), "f"(y)); return c; }
-__device__ __forceinline__ void f2_unpack(f2_t v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
-
-struct Row4 {  // four consecutive genes of one spot
-    f2_t a, b;
-};
-__device__ __forceinline__ Row4 ld_row4(const char* p) {
-    Row4 r;
-    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void r4_add(Row4& s, const Row4& v) { s.a = f2_add(s.a, v.a); s.b = f2_add(s.b, v.b); }
-__device__ __forceinline__ void r4_sub(Row4& s, const Row4& v) { s.a = f2_sub(s.a, v.a); s.b = f2_sub(s.b, v.b); }
-__device__ __forceinline__ void r4_fma(Row4& s, const Row4& x, const Row4& y) { s.a = f2_fma(x.a, y.a, s.a); s.b = f2_fma(x.b, y.b, s.b); }
-__device__ __forceinline__ void r4_sqdiff(Row4& q, const Row4& x, const Row4& v) {
-    Row4 d = x;
-    r4_sub(d, v);
-    r4_fma(q, d, d);
 }
 
 constexpr int kV2Chunk = 128;                 // spots whose neighbour lists are staged at once
@@ -244,219 +227,61 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
 }
 
 // =============================================================================================
-// v4 symmetric quad kernel (default).  The r1b capture showed the v2 kernel pinned on the L1 data
-// pipe (72 % of its wavefront peak: 9 x 512-byte row reads per spot and 97 instructions per
-// row slab).  z'Az only needs every UNORDERED pair {i, j} once:
-//        z'Az = sum_{i<j} (a_ij + a_ji) z_i z_j + sum_i a_ii z_i^2
-// so W is re-expressed, once per W, as a plan over QUADS of 4 consecutive spots (consecutive
-// spots of the Hilbert order are spatial neighbours):
-//   * pairs inside a quad      -> 6 coefficients, served from the registers that hold the 4 rows
-//   * every other pair         -> owned by exactly ONE endpoint: (row, coefficient) in that
-//                                 spot's list; owners are balanced so the 4 lists of a quad have
-//                                 nearly equal length R (the quad is processed in R rounds)
-// which needs ~3.9 row reads per spot instead of 9 (square lattice, k = 8).  The mean shift uses
-// csum_i = sum of the external coefficients of spot i; the cross term sum_j indeg_j x_j replaces
-// sum_i s_i (they are the same number), and Geary's numerator follows from one more sum:
-//   sum_ij a_ij (x_i - x_j)^2 = k sum x_i^2 + sum_j indeg_j x_j^2 - 2 x'Ax.
-// Any neighbour list is legal (duplicates, self loops, asymmetric kNN): coefficients are counts.
+// tile kernel (default): 128-spot x 128-gene tiles staged in shared memory + the quad plan of W
 // =============================================================================================
-constexpr int kSymHdrWords = 16;      // R, nvalid, c01 c02 | c03 c12 c13 c23 | csum[4] | indeg[4]
-constexpr int kSymRoundWords = 8;     // row[4] | coef[4]
-constexpr int kSymChunkQuads = 32;    // quads staged at once (128 spots)
-constexpr int kSymQuadsPerWarp = kSymChunkQuads / kMoranWarps;   // 4 -> level-1 accumulation over 16 spots
-constexpr int kSymRelaxIters = 8;
-constexpr int kSymOffPad = 48;        // ints reserved per buffer for the chunk's record offsets (33 used)
+// The 16 warps of a CTA are symmetric.  For every tile c of its spot range a warp
+//   1. waits until stage (c + 2) % 3 has been released by every warp (tile c - 1 consumed),
+//      then issues its share of tile c + 2: 8 rows by cp.async (one coalesced 512-byte segment
+//      per warp instruction, zero fill outside the matrix) and 1/16 of the tile's plan slice;
+//      the copies arrive on the stage's "full" mbarrier when they land - nothing waits on them
+//   2. waits for tile c's "full" barrier and walks its 2 quads out of shared memory
+//   3. arrives on tile c's "empty" barrier.
+// Two tiles (128 KB) are always in flight per SM and there is no CTA-wide barrier in the loop.
+// (A TMA tensor-map producer was measured first: with 512-byte box rows it delivered a tile too
+//  slowly to keep 16 warps fed - profiles/r1n; plain 512-byte LDG streams reach 7.3 TB/s.)
+constexpr int kTileWarps = 16;
+constexpr int kTileThreads = 32 * kTileWarps;
+constexpr int kTileQuadsPerWarp = kTileQuads / kTileWarps;       // 2
+constexpr int kTileRowsPerWarp = kTileSpots / kTileWarps;        // 8 rows of every tile are fetched by each warp
+constexpr int kTileBytes = kTileSpots * kGeneTile * 4;           // 64 KB
+constexpr int kTileMaxStages = 3;                                // 3 stages: two tiles in flight while one is consumed
+constexpr int kTileOffBytes = 256;                               // 36 ints of the record-offset table per tile
 
-__device__ __forceinline__ uint32_t sym_pair_hash(uint32_t i, uint32_t j) {
-    const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
-    uint32_t h = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u);
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 12;
-    return h;
+__host__ __device__ constexpr int tile_stage_bytes(int buf_units) { return kTileBytes + kTileOffBytes + ((buf_units * 16 + 127) & ~127); }
+
+__device__ __forceinline__ Row4 lds_row4(uint32_t addr) {
+    Row4 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.a), "=l"(r.b) : "r"(addr));
+    return r;
 }
-
-// own[i] bit a: spot i owns the pair {i, nbr[i][a]}.  Only first occurrences of a neighbour carry a
-// bit; pairs only one endpoint lists are owned by that endpoint; quad-internal and self pairs carry
-// no bit.  Mutual external pairs start with a hash-chosen owner.  cnt[i] = number of owned pairs.
-__global__ void sym_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, uint64_t* __restrict__ own,
-                                int32_t* __restrict__ cnt, int32_t* __restrict__ indeg) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t* A = nbr + i * k;
-    uint64_t bits = 0;
-    int c = 0;
-    for (int a = 0; a < k; ++a) {
-        const int32_t j = A[a];
-        atomicAdd(indeg + j, 1);
-        bool first = true;
-        for (int b = 0; b < a; ++b) first &= (A[b] != j);
-        if (!first) continue;
-        if (j == (int32_t)i) { ++c; continue; }                        // self loop: one list entry, no bit
-        if ((j >> 2) == (int32_t)(i >> 2)) continue;                   // quad-internal
-        const int32_t* B = nbr + (int64_t)j * k;
-        bool back = false;
-        for (int b = 0; b < k; ++b) back |= (B[b] == (int32_t)i);
-        bool mine = true;
-        if (back) {
-            const uint32_t lo = (uint32_t)(i < j ? i : j);
-            mine = ((sym_pair_hash((uint32_t)i, (uint32_t)j) & 1u) ? lo : (uint32_t)(i ^ j ^ lo)) == (uint32_t)i;
-        }
-        if (mine) { ++c; bits |= 1ull << a; }
-    }
-    own[i] = bits;
-    cnt[i] = c;
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
 }
-
-// one Jacobi sweep of owner balancing: a mutual pair moves to the other endpoint when that lowers
-// the larger of the two list lengths; both endpoints evaluate the same rule on the same data.
-__global__ void sym_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, const uint64_t* __restrict__ own_in,
-                                 const int32_t* __restrict__ cnt_in, uint64_t* __restrict__ own_out, int32_t* __restrict__ cnt_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t* A = nbr + i * k;
-    const uint64_t mine_old = own_in[i];
-    uint64_t bits = mine_old;
-    int c = cnt_in[i];
-    const int ci = c;
-    for (int a = 0; a < k; ++a) {
-        const int32_t j = A[a];
-        if (j == (int32_t)i || (j >> 2) == (int32_t)(i >> 2)) continue;
-        bool first = true;
-        for (int b = 0; b < a; ++b) first &= (A[b] != j);
-        if (!first) continue;
-        const int32_t* B = nbr + (int64_t)j * k;
-        int bpos = -1;
-        for (int b = k - 1; b >= 0; --b) if (B[b] == (int32_t)i) bpos = b;    // first occurrence of i in N(j)
-        if (bpos < 0) continue;                                                 // one-sided pair: fixed owner
-        const bool i_owns = (mine_old >> a) & 1ull;
-        const int cj = cnt_in[j];
-        const int c_owner = i_owns ? ci : cj, c_other = i_owns ? cj : ci;
-        const bool flip = (c_owner > c_other + 1) && ((sym_pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
-        if (flip) {
-            if (i_owns) { bits &= ~(1ull << a); --c; }
-            else { bits |= 1ull << a; ++c; }
-        }
-    }
-    own_out[i] = bits;
-    cnt_out[i] = c;
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
 }
-
-// record size of every quad in 16-byte units
-__global__ void sym_size_kernel(const int32_t* __restrict__ cnt, int64_t n, int64_t nquads, int32_t* __restrict__ qsize) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nquads) return;
-    int r = 0;
-    for (int t = 0; t < 4; ++t) {
-        const int64_t i = 4 * q + t;
-        if (i < n && cnt[i] > r) r = cnt[i];
-    }
-    qsize[q] = (kSymHdrWords + kSymRoundWords * r) / 4;
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
 }
-
-// single-CTA exclusive scan of m ints; out[m] = total
-__global__ void sym_scan_kernel(const int32_t* __restrict__ in, int64_t m, int32_t* __restrict__ out) {
-    __shared__ int64_t sh[1024];
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int64_t per = (m + nt - 1) / nt;
-    const int64_t b = (int64_t)t * per, e = b + per < m ? b + per : m;
-    int64_t s = 0;
-    for (int64_t i = b; i < e; ++i) s += in[i];
-    sh[t] = s;
-    __syncthreads();
-    if (t == 0) {
-        int64_t run = 0;
-        for (int i = 0; i < nt; ++i) { int64_t v = sh[i]; sh[i] = run; run += v; }
-        out[m] = (int32_t)run;
-    }
-    __syncthreads();
-    int64_t run = sh[t];
-    for (int64_t i = b; i < e; ++i) { out[i] = (int32_t)run; run += in[i]; }
+// padded list slots have coefficient 0: their row load is skipped (predicated, no branch); the
+// register keeps its previous finite content, which then contributes 0 * finite = 0
+__device__ __forceinline__ void lds_row4_if(Row4& v, uint32_t addr, float c) {
+    asm volatile("{\n"
+        ".reg .pred q;\n"
+        "setp.neu.f32 q, %3, 0f00000000;\n"
+        "@q ld.shared.v2.b64 {%0, %1}, [%2];\n"
+        "}\n"
+        : "+l"(v.a), "+l"(v.b)
+        : "r"(addr), "f"(c));
 }
-
-// largest staged chunk (16-byte units): chunks start at multiples of kSymChunkQuads
-__global__ void sym_chunkmax_kernel(const int32_t* __restrict__ off, int64_t nquads, int32_t* __restrict__ out_max) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t q0 = c * kSymChunkQuads;
-    if (q0 >= nquads) return;
-    const int64_t q1 = q0 + kSymChunkQuads < nquads ? q0 + kSymChunkQuads : nquads;
-    atomicMax(out_max, off[q1] - off[q0]);
-}
-
-// one thread per quad writes its record
-__global__ void sym_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t nquads, const uint64_t* __restrict__ own,
-                                const int32_t* __restrict__ indeg, const int32_t* __restrict__ off, int32_t* __restrict__ rec_base) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nquads) return;
-    int32_t* rec = rec_base + (int64_t)off[q] * 4;
-    const int R = ((off[q + 1] - off[q]) * 4 - kSymHdrWords) / kSymRoundWords;
-    const int nvalid = (int)(n - 4 * q < 4 ? n - 4 * q : 4);
-    float* recf = reinterpret_cast<float*>(rec);
-    for (int w = 2; w < kSymHdrWords; ++w) recf[w] = 0.f;
-    rec[0] = R;
-    rec[1] = nvalid;
-    for (int r = 0; r < R; ++r)
-        for (int t = 0; t < 4; ++t) {
-            const int64_t self = 4 * q + (t < nvalid ? t : 0);
-            rec[kSymHdrWords + r * kSymRoundWords + t] = (int32_t)self;      // padding: a valid row, coefficient 0
-            recf[kSymHdrWords + r * kSymRoundWords + 4 + t] = 0.f;
-        }
-    for (int t = 0; t < nvalid; ++t) {
-        const int64_t i = 4 * q + t;
-        const int32_t* A = nbr + i * k;
-        const uint64_t bits = own[i];
-        int slot = 0;
-        float csum = 0.f;
-        for (int a = 0; a < k; ++a) {
-            const int32_t j = A[a];
-            bool first = true;
-            int mult = 0;
-            for (int b = 0; b < k; ++b)
-                if (A[b] == j) { if (b < a) first = false; ++mult; }
-            if (!first) continue;
-            float c;
-            bool ext;
-            if (j == (int32_t)i) {
-                c = (float)mult; ext = true;                                   // a_ii z_i^2: own row with coefficient a_ii
-            } else {
-                const int32_t* B = nbr + (int64_t)j * k;
-                int back = 0;
-                for (int b = 0; b < k; ++b) back += (B[b] == (int32_t)i);
-                c = (float)(mult + back);
-                if ((j >> 2) == (int32_t)(i >> 2)) {
-                    // quad-internal: written once, by the lower spot if it lists the pair, else by the upper one
-                    const int u = t, v = (int)(j & 3);
-                    const bool lower = u < v;
-                    if (lower || back == 0) {
-                        const int lo = lower ? u : v, hi = lower ? v : u;
-                        const int idx = lo == 0 ? hi - 1 : (lo == 1 ? hi + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
-                        recf[2 + idx] = c;
-                    }
-                    continue;
-                }
-                ext = (bits >> a) & 1ull;
-            }
-            if (!ext || slot >= R) continue;
-            rec[kSymHdrWords + slot * kSymRoundWords + t] = j;
-            recf[kSymHdrWords + slot * kSymRoundWords + 4 + t] = c;
-            csum += c;
-            ++slot;
-        }
-        recf[8 + t] = csum;
-        recf[12 + t] = (float)indeg[i];
-    }
-}
-
-__device__ __forceinline__ f2_t f2_dup(float c) { return f2_pack(c, c); }
-__device__ __forceinline__ void r4_fmac(Row4& s, float c, const Row4& v) {   // s += c * v
-    const f2_t cc = f2_dup(c);
-    s.a = f2_fma(cc, v.a, s.a);
-    s.b = f2_fma(cc, v.b, s.b);
-}
-
-// padded list slots have coefficient 0: their row load is skipped (predicated, no branch)
-__device__ __forceinline__ void ld_row4_if(Row4& v, const char* p, float c) {
-    asm("{\n"
+__device__ __forceinline__ void ldg_row4_if(Row4& v, const char* p, float c) {
+    asm volatile("{\n"
         ".reg .pred q;\n"
         "setp.neu.f32 q, %3, 0f00000000;\n"
         "@q ld.global.nc.v2.b64 {%0, %1}, [%2];\n"
@@ -464,26 +289,89 @@ __device__ __forceinline__ void ld_row4_if(Row4& v, const char* p, float c) {
         : "+l"(v.a), "+l"(v.b)
         : "l"(p), "f"(c));
 }
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a lost completion becomes a trap (an error code), never a hung GPU
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
 
-template <bool GEARY, bool SHIFT, int MINB>
-__global__ void __launch_bounds__(kMoranThreads, MINB)
-moran_sym_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int64_t ncol, const int32_t* __restrict__ plan_off,
-                 const int4* __restrict__ plan_rec, int buf_units, const float* __restrict__ pilot, double* __restrict__ part,
-                 int64_t gpad) {
+template <bool GEARY, bool SHIFT>
+__global__ void __launch_bounds__(kTileThreads, 1)
+moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int ncol, const int32_t* __restrict__ plan_off,
+                  const int4* __restrict__ plan_rec, int buf_units, int nstages, int tiles_per_cta,
+                  const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
     constexpr int NST = GEARY ? 5 : 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // [2][kSymOffPad ints + buf_units x 16 B]  |  level-2 accumulators [NST][256] float4
-    const int buf_bytes = kSymOffPad * 4 + buf_units * 16;
-    float4* s_l2 = reinterpret_cast<float4*>(smem_raw + 2 * buf_bytes);
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    const uint32_t smem0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // everything below is addressed in the shared window
+    const uint32_t stage_bytes = (uint32_t)tile_stage_bytes(buf_units);
+    const uint32_t full_bar = smem0 + nstages * stage_bytes, empty_bar = full_bar + 8 * kTileMaxStages;
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile_col = (int64_t)blockIdx.x * kGeneTile;
-    int64_t col = tile_col + lane * 4;
-    if (col >= ncol) col = tile_col;                                  // idle lanes shadow lane 0 (results unused)
+    const int tile_col = blockIdx.x * kGeneTile;
+    const int nquads = (n + 3) >> 2;
+    const int ntiles = (nquads + kTileQuads - 1) / kTileQuads;
+    const int t_begin = blockIdx.y * tiles_per_cta;
+    const int t_end = t_begin + tiles_per_cta < ntiles ? t_begin + tiles_per_cta : ntiles;
+    const int my_tiles = t_end - t_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(kTileThreads) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(kTileWarps) : "memory");
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int col = tile_col + lane * 4;
+    const bool col_ok = col < ncol;
+    if (!col_ok) col = tile_col;                                      // idle lanes shadow lane 0 (results unused)
     const char* __restrict__ base = reinterpret_cast<const char*>(X + col);
-    const int64_t nquads = (n + 3) >> 2;
-    const int64_t q_begin = (int64_t)blockIdx.y * (kV2SpotsPerCta / 4);
-    const int64_t q_end = q_begin + kV2SpotsPerCta / 4 < nquads ? q_begin + kV2SpotsPerCta / 4 : nquads;
-    const uint32_t tile_bytes = (uint32_t)((ncol - tile_col < kGeneTile ? ncol - tile_col : kGeneTile) * 4);
+    const int col_bytes = col_ok ? 16 : 0;
+
+    // this thread's share of tile c (local index) -> stage s
+    auto issue_tile = [&](int c, int s) {
+        const uint32_t st = smem0 + s * stage_bytes;
+        const int t = t_begin + c;
+        const int row0 = t * kTileSpots + warp * kTileRowsPerWarp;
+        const uint32_t dst = st + (uint32_t)(warp * kTileRowsPerWarp) * (kGeneTile * 4) + lane * 16;
+#pragma unroll
+        for (int r = 0; r < kTileRowsPerWarp; ++r) {
+            const int row = row0 + r;
+            const bool ok = row < n;
+            cp_async_16_zfill(dst + r * (kGeneTile * 4), base + (uint64_t)(uint32_t)(ok ? row : 0) * row_bytes, ok ? col_bytes : 0);
+        }
+        const int q0 = t * kTileQuads;
+        const int nq = nquads - q0 < kTileQuads ? nquads - q0 : kTileQuads;
+        const int u0 = __ldg(plan_off + q0), u1 = __ldg(plan_off + q0 + nq);
+        if (threadIdx.x < 9) cp_async_16_zfill(st + kTileBytes + threadIdx.x * 16, plan_off + q0 + threadIdx.x * 4, 16);
+        for (int u = threadIdx.x; u < u1 - u0; u += kTileThreads)
+            cp_async_16_zfill(st + kTileBytes + kTileOffBytes + u * 16, plan_rec + u0 + u, 16);
+        cp_async_mbar_arrive(full_bar + 8 * s);
+    };
 
     Row4 p;
     p.a = p.b = f2_pack(0.f, 0.f);
@@ -493,90 +381,81 @@ moran_sym_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int
         p.b = f2_pack(pf.z, pf.w);
     }
     const f2_t z2 = f2_pack(0.f, 0.f);
-    Row4 l1[NST];
+    Row4 l1[NST], l2[NST];
 #pragma unroll
-    for (int s = 0; s < NST; ++s) {
-        l1[s].a = l1[s].b = z2;
-        s_l2[s * kMoranThreads + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // row registers of the two rounds in flight; a skipped (coefficient 0) load leaves the previous finite
-    // row in place, which then contributes 0 * finite = 0
-    Row4 va[4], vb[4];
+    for (int s = 0; s < NST; ++s) { l1[s].a = l1[s].b = z2; l2[s].a = l2[s].b = z2; }
+    Row4 va[4], vg[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) va[t].a = va[t].b = vb[t].a = vb[t].b = z2;
+    for (int t = 0; t < 4; ++t) va[t].a = va[t].b = vg[t].a = vg[t].b = z2;
 
-    auto stage = [&](int buf, int64_t q0) {   // offsets and records of quads [q0, q0 + chunk) -> smem
-        unsigned char* dst = smem_raw + buf * buf_bytes;
-        const int nq = (int)(q_end - q0 < kSymChunkQuads ? q_end - q0 : kSymChunkQuads);
-        if ((int)threadIdx.x <= nq) cp_async_4(dst + threadIdx.x * 4, plan_off + q0 + threadIdx.x);
-        const int u0 = __ldg(plan_off + q0), u1 = __ldg(plan_off + q0 + nq);
-        const int4* src = plan_rec + u0;
-        int4* d4 = reinterpret_cast<int4*>(dst + kSymOffPad * 4);
-        for (int u = threadIdx.x; u < u1 - u0; u += kMoranThreads) cp_async_16(d4 + u, src + u);
-        cp_async_commit();
-    };
+    for (int c = 0; c < nstages - 1 && c < my_tiles; ++c) issue_tile(c, c);
 
-    stage(0, q_begin);
-    int buf = 0;
-    for (int64_t q0 = q_begin; q0 < q_end; q0 += kSymChunkQuads, buf ^= 1) {
-        cp_async_wait_all();
-        __syncthreads();                                              // chunk `buf` visible; previous chunk fully consumed
-        if (q0 + kSymChunkQuads < q_end) stage(buf ^ 1, q0 + kSymChunkQuads);
-        const int32_t* s_off = reinterpret_cast<const int32_t*>(smem_raw + buf * buf_bytes);
-        const int4* s_rec = reinterpret_cast<const int4*>(smem_raw + buf * buf_bytes + kSymOffPad * 4);
-        const int off0 = s_off[0];
-        const int64_t qw = q0 + warp * kSymQuadsPerWarp;
-        // pull this warp's own rows of the next chunk towards L2 while the current one is consumed
-        if (lane < 4 * kSymQuadsPerWarp) {
-            const int64_t ip = 4 * (qw + kSymChunkQuads) + lane;
-            if (ip < 4 * q_end && ip < n)
-                l2_prefetch_bulk(reinterpret_cast<const char*>(X + tile_col) + (uint64_t)ip * row_bytes, tile_bytes);
-        }
+    // stage / phase of the tile being consumed (c) and of the tile that was consumed last (c - 1), kept
+    // incrementally: no division in the loop
+    int sidx = 0, prev_sidx = nstages - 1;
+    uint32_t phase = 0, prev_phase = 0;
 #pragma unroll 1
-        for (int qi = 0; qi < kSymQuadsPerWarp; ++qi) {
-            const int64_t q = qw + qi;
-            if (q >= q_end) break;
-            const int4* rec = s_rec + (s_off[warp * kSymQuadsPerWarp + qi] - off0);
-            const int4 h0 = rec[0];
-            const int R = h0.x, nvalid = h0.y;
-            const uint32_t r0 = (uint32_t)(4 * q);
+    for (int c = 0; c < my_tiles; ++c) {
+        mbar_wait_u32(full_bar + 8 * sidx, phase);
+        const uint32_t st = smem0 + sidx * stage_bytes;
+        const uint32_t tile_lane = st + lane * 16;
+        const uint32_t s_off = st + kTileBytes, s_rec = st + kTileBytes + kTileOffBytes;
+        const int q0 = (t_begin + c) * kTileQuads;
+        const int nq = nquads - q0 < kTileQuads ? nquads - q0 : kTileQuads;
+        const int off0 = lds_i32(s_off);
+#pragma unroll 1
+        for (int qi = 0; qi < kTileQuadsPerWarp; ++qi) {
+            const int ql = warp * kTileQuadsPerWarp + qi;
+            if (ql >= nq) break;
+            const uint32_t rec = s_rec + (uint32_t)(lds_i32(s_off + 4 * ql) - off0) * 16;
+            const int4 h0 = lds_i4(rec);
+            const float4 h1 = lds_f4(rec + 16);                       // c12 c13 c23 -
+            const int RL = h0.x & 0xff, RG = (h0.x >> 8) & 0xff, nvalid = h0.x >> 16;
             Row4 x[4], s[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                x[t] = ld_row4(base + (uint64_t)(r0 + (t < nvalid ? t : 0)) * row_bytes);
+                x[t] = lds_row4(tile_lane + (uint32_t)(4 * ql + t) * (kGeneTile * 4));
                 s[t].a = s[t].b = z2;
             }
-            // two rounds per trip: 8 independent row loads in flight, then 16 multiply-adds
-            int r = 0;
+            // the first out-of-tile round is issued before the in-tile rounds so its latency hides behind them
+            const uint32_t grec = rec + 16 * (kPlanHdrUnits + kPlanRoundUnits * RL);
+            float cg[4] = {0.f, 0.f, 0.f, 0.f};
+            if (RG > 0) {
+                const int4 rows = lds_i4(grec);
+                const float4 cf = lds_f4(grec + 16);
+                const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                cg[0] = cf.x; cg[1] = cf.y; cg[2] = cf.z; cg[3] = cf.w;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cg[t]);
+            }
+#pragma unroll 2
+            for (int r = 0; r < RL; ++r) {
+                const int4 offs = lds_i4(rec + 16 * (kPlanHdrUnits + 2 * r));
+                const float4 cf = lds_f4(rec + 16 * (kPlanHdrUnits + 2 * r + 1));
+                const int oo[4] = {offs.x, offs.y, offs.z, offs.w};
+                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) lds_row4_if(va[t], tile_lane + (uint32_t)oo[t], cc[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], va[t]);
+            }
+            if (RG > 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cg[t], vg[t]);
 #pragma unroll 1
-            for (; r + 1 < R; r += 2) {
-                const int4 rows0 = rec[4 + 2 * r], rows1 = rec[6 + 2 * r];
-                const float4 cf0 = *reinterpret_cast<const float4*>(rec + 5 + 2 * r);
-                const float4 cf1 = *reinterpret_cast<const float4*>(rec + 7 + 2 * r);
-                const int rr0[4] = {rows0.x, rows0.y, rows0.z, rows0.w}, rr1[4] = {rows1.x, rows1.y, rows1.z, rows1.w};
-                const float cc0[4] = {cf0.x, cf0.y, cf0.z, cf0.w}, cc1[4] = {cf1.x, cf1.y, cf1.z, cf1.w};
+                for (int r = 1; r < RG; ++r) {
+                    const int4 rows = lds_i4(grec + 32 * r);
+                    const float4 cf = lds_f4(grec + 32 * r + 16);
+                    const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                    const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
-                for (int t = 0; t < 4; ++t) ld_row4_if(va[t], base + (uint64_t)(uint32_t)rr0[t] * row_bytes, cc0[t]);
+                    for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cc[t]);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) ld_row4_if(vb[t], base + (uint64_t)(uint32_t)rr1[t] * row_bytes, cc1[t]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc0[t], va[t]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc1[t], vb[t]);
+                    for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], vg[t]);
+                }
             }
-            if (r < R) {
-                const int4 rows0 = rec[4 + 2 * r];
-                const float4 cf0 = *reinterpret_cast<const float4*>(rec + 5 + 2 * r);
-                const int rr0[4] = {rows0.x, rows0.y, rows0.z, rows0.w};
-                const float cc0[4] = {cf0.x, cf0.y, cf0.z, cf0.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) ld_row4_if(va[t], base + (uint64_t)(uint32_t)rr0[t] * row_bytes, cc0[t]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc0[t], va[t]);
-            }
-            const float4 h1 = *reinterpret_cast<const float4*>(rec + 1);   // c03 c12 c13 c23
-            const float4 cs = *reinterpret_cast<const float4*>(rec + 2);   // csum
-            const float4 dg = *reinterpret_cast<const float4*>(rec + 3);   // indeg
+            const float4 cs = lds_f4(rec + 32);                       // csum
+            const float4 dg = lds_f4(rec + 48);                       // indeg
             if (SHIFT) {
                 const float ncs[4] = {-cs.x, -cs.y, -cs.z, -cs.w};
 #pragma unroll
@@ -586,12 +465,12 @@ moran_sym_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int
                 }
             }
             // pairs inside the quad
-            r4_fmac(s[0], __int_as_float(h0.z), x[1]);
-            r4_fmac(s[0], __int_as_float(h0.w), x[2]);
-            r4_fmac(s[0], h1.x, x[3]);
-            r4_fmac(s[1], h1.y, x[2]);
-            r4_fmac(s[1], h1.z, x[3]);
-            r4_fmac(s[2], h1.w, x[3]);
+            r4_fmac(s[0], __int_as_float(h0.y), x[1]);
+            r4_fmac(s[0], __int_as_float(h0.z), x[2]);
+            r4_fmac(s[0], __int_as_float(h0.w), x[3]);
+            r4_fmac(s[1], h1.x, x[2]);
+            r4_fmac(s[1], h1.y, x[3]);
+            r4_fmac(s[2], h1.z, x[3]);
             const float dgs[4] = {dg.x, dg.y, dg.z, dg.w};
             auto accumulate = [&](int t) {
                 r4_add(l1[0], x[t]);
@@ -617,50 +496,74 @@ moran_sym_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, int
                     if (t < nvalid) accumulate(t);
             }
         }
-        // level-1 -> level-2 (every 16 spots of this warp)
+        // this warp is done with the stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(empty_bar + 8 * sidx);
+        // tile c + nstages - 1 goes into the stage tile c - 1 occupied: by now every warp has usually released it
+        if (c + nstages - 1 < my_tiles) {
+            if (c > 0) mbar_wait_u32(empty_bar + 8 * prev_sidx, prev_phase);
+            issue_tile(c + nstages - 1, prev_sidx);
+        }
+        prev_sidx = sidx;
+        prev_phase = phase;
+        if (++sidx == nstages) { sidx = 0; phase ^= 1; }
+        // level-1 (16 spots: two tiles of this warp) -> level-2
+        if (c & 1) {
 #pragma unroll
-        for (int st = 0; st < NST; ++st) {
-            float4 acc = s_l2[st * kMoranThreads + threadIdx.x];
-            float f0, f1, f2, f3;
-            f2_unpack(l1[st].a, f0, f1);
-            f2_unpack(l1[st].b, f2, f3);
-            acc.x += f0; acc.y += f1; acc.z += f2; acc.w += f3;
-            s_l2[st * kMoranThreads + threadIdx.x] = acc;
-            l1[st].a = l1[st].b = z2;
+            for (int stt = 0; stt < NST; ++stt) {
+                r4_add(l2[stt], l1[stt]);
+                l1[stt].a = l1[stt].b = z2;
+            }
         }
     }
-
-    // level-2 -> fp64, cross-warp reduction in fixed order, one statistic at a time
-    __syncthreads();
-    double* red = reinterpret_cast<double*>(smem_raw);               // [kMoranWarps][kGeneTile] (reuses the staging buffers)
 #pragma unroll
-    for (int st = 0; st < NST; ++st) {
-        const float4 acc = s_l2[st * kMoranThreads + threadIdx.x];
-        red[warp * kGeneTile + lane * 4 + 0] = (double)acc.x;
-        red[warp * kGeneTile + lane * 4 + 1] = (double)acc.y;
-        red[warp * kGeneTile + lane * 4 + 2] = (double)acc.z;
-        red[warp * kGeneTile + lane * 4 + 3] = (double)acc.w;
+    for (int stt = 0; stt < NST; ++stt) r4_add(l2[stt], l1[stt]);
+
+    // per-thread fp32 sums -> fp64, cross-warp reduction in fixed order, one statistic at a time
+    __syncthreads();                                                  // every tile consumed: the stages are free
+    double* red = reinterpret_cast<double*>(smem_dyn + (smem0 - smem_u32(smem_dyn)));   // [kTileWarps][kGeneTile]
+#pragma unroll
+    for (int stt = 0; stt < NST; ++stt) {
+        float f0, f1, f2, f3;
+        f2_unpack(l2[stt].a, f0, f1);
+        f2_unpack(l2[stt].b, f2, f3);
+        red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
+        red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
+        red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
+        red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
         __syncthreads();
         if (threadIdx.x < kGeneTile) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < kMoranWarps; ++w) t += red[w * kGeneTile + threadIdx.x];
-            part[((int64_t)blockIdx.y * kNStat + st) * gpad + tile_col + threadIdx.x] = t;
+            for (int w = 0; w < kTileWarps; ++w) t += red[w * kGeneTile + threadIdx.x];
+            part[((int64_t)blockIdx.y * kNStat + stt) * gpad + tile_col + threadIdx.x] = t;
         }
         __syncthreads();
     }
 }
 
 // ---- finalize: fixed-order sum of the split partials, then the statistic in fp64 ------------
-__global__ void moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad, int64_t g, int64_t n, int k,
-                                      const float* __restrict__ pilot, bool geary, bool sym, double* __restrict__ out_I,
-                                      double* __restrict__ out_C, double* __restrict__ out_stats) {
-    int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= g) return;
-    double S[kNStat] = {0, 0, 0, 0, 0};
+constexpr int kFinSplit = 8;
+__global__ void __launch_bounds__(64 * kFinSplit)
+moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad, int64_t g, int64_t n, int k,
+                      const float* __restrict__ pilot, bool geary, bool sym, double* __restrict__ out_I,
+                      double* __restrict__ out_C, double* __restrict__ out_stats) {
+    __shared__ double red[kFinSplit][kNStat][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int64_t col = (int64_t)blockIdx.x * 64 + tx;
     const int ns = geary ? kNStat : kNStat - 1;
-    for (int sp = 0; sp < nsplit; ++sp)
-        for (int st = 0; st < ns; ++st) S[st] += part[((int64_t)sp * kNStat + st) * gpad + col];
+    double S[kNStat] = {0, 0, 0, 0, 0};
+    if (col < g)
+        for (int sp = ty; sp < nsplit; sp += kFinSplit)
+            for (int st = 0; st < ns; ++st) S[st] += part[((int64_t)sp * kNStat + st) * gpad + col];
+    for (int st = 0; st < kNStat; ++st) red[ty][st][tx] = S[st];
+    __syncthreads();
+    if (ty != 0 || col >= g) return;
+    for (int st = 0; st < kNStat; ++st) {
+        double a = 0.0;
+        for (int y = 0; y < kFinSplit; ++y) a += red[y][st][tx];
+        S[st] = a;
+    }
     const double dn = (double)n, dk = (double)k;
     const double m = S[0] / dn;                                   // mean of shifted values
     const double zz = S[1] - dn * m * m;                          // sum (x - mean)^2
@@ -668,7 +571,7 @@ __global__ void moran_finalize_kernel(const double* __restrict__ part, int nspli
     // I = (n / s0) * z'Wz / z'z with s0 = n for row-standardised kNN weights
     out_I[col] = zwz / zz;
     // Geary numerator * k = sum_ij adj_ij (x_i - x_j)^2: accumulated directly (stream kernel) or from
-    // k sum x^2 + sum_j indeg_j x_j^2 - 2 x'Ax (symmetric kernel; S[4] = sum_j indeg_j x_j^2)
+    // k sum x^2 + sum_j indeg_j x_j^2 - 2 x'Ax (tile kernel; S[4] = sum_j indeg_j x_j^2)
     const double gnum = geary ? (sym ? dk * S[1] + S[4] - 2.0 * S[2] : S[4]) : 0.0;
     if (geary && out_C) out_C[col] = (dn - 1.0) * (gnum / dk) / (2.0 * dn * zz);
     if (out_stats) {
@@ -679,31 +582,31 @@ __global__ void moran_finalize_kernel(const double* __restrict__ part, int nspli
     }
 }
 
-struct MoranPlan {
-    int64_t gpad, nquads;
+// spots per CTA of the tile kernel: depends on n only, so the summation tree of a gene is identical
+// however genes are sharded.  Long CTAs amortise the pipeline fill; small n keeps enough CTAs.
+static int tile_tiles_per_cta(int64_t n) {
+    const int64_t ntiles = ceil_div<int64_t>(n, kTileSpots);
+    if (ntiles >= 64 * 16) return 64;       // 8192 spots
+    if (ntiles >= 16 * 8) return 16;        // 2048 spots
+    return 4;
+}
+
+struct MoranWs {
+    int64_t gpad;
     int nsplit, ntile;
-    size_t pilot_off, part_off, own_off[2], cnt_off[2], indeg_off, qsize_off, qoff_off, scal_off, rec_off, rec_bytes, total;
+    size_t pilot_off, part_off, total;
 };
 
-static MoranPlan moran_plan(int64_t n, int64_t ld, int k) {
-    MoranPlan p;
-    p.nsplit = (int)ceil_div<int64_t>(n, kV2SpotsPerCta);
-    p.ntile = (int)ceil_div<int64_t>(ld, kGeneTile);
+static MoranWs moran_ws(int64_t n, int64_t ncol, bool tile) {
+    MoranWs p;
+    const int64_t spots_per_cta = tile ? (int64_t)tile_tiles_per_cta(n) * kTileSpots : kV2SpotsPerCta;
+    p.nsplit = (int)ceil_div<int64_t>(n, spots_per_cta);
+    p.ntile = (int)ceil_div<int64_t>(ncol, kGeneTile);
     p.gpad = (int64_t)p.ntile * kGeneTile;
-    p.nquads = (n + 3) / 4;
     size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o += round_up<size_t>(b, 256); return r; };
     p.pilot_off = take((size_t)p.gpad * sizeof(float));
     p.part_off = take((size_t)p.nsplit * kNStat * p.gpad * sizeof(double));
-    // symmetric-plan scratch: owner masks and list lengths (ping-pong), in-degrees, record sizes / offsets, records
-    for (int b = 0; b < 2; ++b) { p.own_off[b] = take((size_t)n * 8); p.cnt_off[b] = take((size_t)n * 4); }
-    p.indeg_off = take((size_t)n * 4);
-    p.qsize_off = take((size_t)(p.nquads + 1) * 4);
-    p.qoff_off = take((size_t)(p.nquads + 1) * 4);
-    p.scal_off = take(256);
-    // every pair is owned once and a spot owns at most k pairs: sum of rounds over quads <= n * k
-    p.rec_bytes = (size_t)p.nquads * kSymHdrWords * 4 + (size_t)n * (size_t)(k < 64 ? k : 64) * kSymRoundWords * 4;
-    p.rec_off = take(p.rec_bytes);
     p.total = o;
     return p;
 }
@@ -713,14 +616,16 @@ static MoranPlan moran_plan(int64_t n, int64_t ld, int k) {
 extern "C" {
 
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags) {
-    (void)flags;
+    (void)flags; (void)k;
     if (n_spots <= 0 || n_genes <= 0) return 256;
-    return chr::moran_plan(n_spots, chr::round_up<int64_t>(n_genes, 4), k > 0 ? k : 1).total + 512;
+    const int64_t ncol = chr::round_up<int64_t>(n_genes, 4);
+    const size_t a = chr::moran_ws(n_spots, ncol, false).total, b = chr::moran_ws(n_spots, ncol, true).total;
+    return (a > b ? a : b) + 512;
 }
 
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld, const int32_t* nbr, int k,
-                        unsigned flags, double* out_I, double* out_C, double* out_stats, void* workspace,
-                        size_t workspace_bytes, chr_stream_t stream) {
+                        const void* plan, int plan_chunk_units, unsigned flags, double* out_I, double* out_C,
+                        double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
     using namespace chr;
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(n_spots > 1 && n_genes > 0, "chr_moran_dense_f32: need n_spots > 1 and n_genes > 0 (got %lld, %lld)",
@@ -728,7 +633,7 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     CHR_REQUIRE(k > 0 && k < n_spots, "chr_moran_dense_f32: need 0 < k < n_spots (k=%d)", k);
     CHR_REQUIRE(ld >= n_genes && ld % 4 == 0, "chr_moran_dense_f32: ld (%lld) must be >= n_genes and a multiple of 4", (long long)ld);
     CHR_REQUIRE(((uintptr_t)X & 15) == 0, "chr_moran_dense_f32: X must be 16-byte aligned");
-    CHR_REQUIRE(X && nbr && out_I && workspace, "chr_moran_dense_f32: null pointer argument");
+    CHR_REQUIRE(X && out_I && workspace && (nbr || plan), "chr_moran_dense_f32: null pointer argument");
     CHR_REQUIRE(n_spots < (1LL << 31) && ld * 4 < (1LL << 32), "chr_moran_dense_f32: needs n_spots < 2^31, row bytes < 2^32");
     const bool geary = flags & CHR_FLAG_GEARY;
     CHR_REQUIRE(!geary || out_C, "chr_moran_dense_f32: CHR_FLAG_GEARY needs out_C");
@@ -738,65 +643,49 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     const int64_t ncol = round_up<int64_t>(n_genes, 4);
     const unsigned variant = (flags >> CHR_VARIANT_SHIFT) & 0xffu;
     const bool preshifted = flags & CHR_FLAG_PRESHIFTED;
-    // variant 0: symmetric quad kernel (v4, k <= 64).  variant 4 / k > 64: per-spot stream kernel (v2)
-    const bool sym = variant != 4 && k <= 64;
-    MoranPlan p = moran_plan(n_spots, ncol, k);
+    // variant 0: tile kernel over the quad plan of W.  variant 4 / no plan: per-spot stream kernel over nbr
+    bool tile = variant != 4 && plan != nullptr;
+    // shared memory of the tile kernel: 3 (or 2) stages of {64 KB tile, record offsets, plan slice}; very long
+    // neighbour lists do not fit and take the stream kernel
+    int nstages = kTileMaxStages;
+    auto tile_smem = [&](int ns) { return (size_t)1024 + (size_t)ns * tile_stage_bytes(plan_chunk_units) + 16 * kTileMaxStages; };
+    if (tile && tile_smem(nstages) > 227 * 1024) nstages = 2;
+    if (tile && tile_smem(nstages) > 227 * 1024 && nbr) tile = false;
+    CHR_REQUIRE(tile || nbr, "chr_moran_dense_f32: the stream kernel needs the neighbour lists");
+    MoranWs p = moran_ws(n_spots, ncol, tile);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* pilot = (float*)(ws + p.pilot_off);
     double* part = (double*)(ws + p.part_off);
 
     if (preshifted) CHR_CUDA(cudaMemsetAsync(pilot, 0, (size_t)p.gpad * sizeof(float), st));
-    else moran_pilot_kernel<<<(unsigned)ceil_div<int64_t>(ncol, 256), 256, 0, st>>>(X, n_spots, ld, ncol, pilot);
+    else moran_pilot_kernel<<<(unsigned)ceil_div<int64_t>(ncol, 64), 64 * kPilotSplit, 0, st>>>(X, n_spots, ld, ncol, pilot);
     CHR_LAUNCH_CHECK();
 
     dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
     const uint32_t rb = (uint32_t)(ld * 4);
-    if (sym) {
-        // ---- W -> symmetric quad plan (depends on W only)
-        uint64_t* own[2] = {(uint64_t*)(ws + p.own_off[0]), (uint64_t*)(ws + p.own_off[1])};
-        int32_t* cnt[2] = {(int32_t*)(ws + p.cnt_off[0]), (int32_t*)(ws + p.cnt_off[1])};
-        int32_t* indeg = (int32_t*)(ws + p.indeg_off);
-        int32_t* qsize = (int32_t*)(ws + p.qsize_off);
-        int32_t* qoff = (int32_t*)(ws + p.qoff_off);
-        int32_t* scal = (int32_t*)(ws + p.scal_off);
-        int32_t* rec = (int32_t*)(ws + p.rec_off);
-        const unsigned gs = (unsigned)ceil_div<int64_t>(n_spots, 128), gq = (unsigned)ceil_div<int64_t>(p.nquads, 128);
-        CHR_CUDA(cudaMemsetAsync(indeg, 0, (size_t)n_spots * 4, st));
-        CHR_CUDA(cudaMemsetAsync(scal, 0, 256, st));
-        sym_init_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, own[0], cnt[0], indeg);
-        int cur = 0;
-        for (int it = 0; it < kSymRelaxIters; ++it, cur ^= 1)
-            sym_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
-        sym_size_kernel<<<gq, 128, 0, st>>>(cnt[cur], n_spots, p.nquads, qsize);
-        sym_scan_kernel<<<1, 1024, 0, st>>>(qsize, p.nquads, qoff);
-        sym_chunkmax_kernel<<<(unsigned)ceil_div<int64_t>(ceil_div<int64_t>(p.nquads, kSymChunkQuads), 128), 128, 0, st>>>(qoff, p.nquads, scal);
-        sym_fill_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, p.nquads, own[cur], indeg, qoff, rec);
-        CHR_LAUNCH_CHECK();
-        int chunk_units = 0;
-        CHR_CUDA(cudaMemcpyAsync(&chunk_units, scal, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CHR_CUDA(cudaStreamSynchronize(st));
-        const int buf_units = chunk_units < 256 ? 256 : chunk_units;      // the final reduction reuses >= 8 KB of the buffers
-        const int nst = geary ? 5 : 4;
-        const size_t smem = (size_t)2 * (kSymOffPad * 4 + (size_t)buf_units * 16) + (size_t)nst * kMoranThreads * 16;
-        CHR_REQUIRE(smem <= 200 * 1024, "chr_moran_dense_f32: neighbour lists too long for the staged plan (%zu B of shared memory)", smem);
+    if (tile) {
+        CHR_REQUIRE(((uintptr_t)plan & 255) == 0 && plan_chunk_units > 0, "chr_moran_dense_f32: bad plan (build it with chr_moran_plan_build)");
+        const int64_t nquads = (n_spots + 3) / 4;
+        const char* pb = (const char*)plan;
+        const int32_t* plan_off = (const int32_t*)(pb + kPlanHeaderBytes);
+        const int4* plan_rec = (const int4*)(pb + kPlanHeaderBytes + round_up<size_t>((size_t)(nquads + 1 + kPlanOffPad) * 4, 256));
+        const size_t smem = tile_smem(nstages);
+        CHR_REQUIRE(smem <= 227 * 1024, "chr_moran_dense_f32: neighbour lists too long for the staged plan (%zu B of shared memory)", smem);
+        const int tpc = tile_tiles_per_cta(n_spots);
         timer_begin(CHR_FAMILY_MORAN, timing, st);
-#define CHR_V4(GG, SH)                                                                                              \
+#define CHR_TILE(GG, SH)                                                                                            \
     do {                                                                                                            \
-        if (variant == 5) CHR_V4M(GG, SH, 1); else CHR_V4M(GG, SH, 2);                                             \
-    } while (0)
-#define CHR_V4M(GG, SH, MB)                                                                                         \
-    do {                                                                                                            \
-        auto kern = moran_sym_kernel<GG, SH, MB>;                                                                    \
+        auto kern = moran_tile_kernel<GG, SH>;                                                                     \
         CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        kern<<<grid, kMoranThreads, smem, st>>>(X, n_spots, rb, ncol, qoff, (const int4*)rec, buf_units, pilot, part, p.gpad); \
+        kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_spots, rb, (int)ncol, plan_off, plan_rec, plan_chunk_units, nstages, tpc, pilot, part, \
+                                               p.gpad);                                                            \
     } while (0)
-        if (geary && preshifted) CHR_V4(true, false);
-        else if (geary) CHR_V4(true, true);
-        else if (preshifted) CHR_V4(false, false);
-        else CHR_V4(false, true);
-#undef CHR_V4
-#undef CHR_V4M
+        if (geary && preshifted) CHR_TILE(true, false);
+        else if (geary) CHR_TILE(true, true);
+        else if (preshifted) CHR_TILE(false, false);
+        else CHR_TILE(false, true);
+#undef CHR_TILE
     } else {
         const int vec16 = (k % 4 == 0) && (((uintptr_t)nbr & 15) == 0);
         size_t smem = (size_t)2 * kV2Chunk * k * sizeof(int32_t);
@@ -826,8 +715,8 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();
 
-    moran_finalize_kernel<<<(unsigned)ceil_div<int64_t>(n_genes, 256), 256, 0, st>>>(
-        part, p.nsplit, p.gpad, n_genes, n_spots, k, pilot, geary, sym, out_I, out_C, out_stats);
+    moran_finalize_kernel<<<(unsigned)ceil_div<int64_t>(n_genes, 64), 64 * kFinSplit, 0, st>>>(
+        part, p.nsplit, p.gpad, n_genes, n_spots, k, pilot, geary, tile, out_I, out_C, out_stats);
     CHR_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,331 @@
+// K1b - the device representation of the row-standardised kNN weights W that the Moran kernel
+// streams against ("GPU CSR build of W").  Input: nbr[n][k], the kNN lists that replace
+//     w = weights.KNN.from_array(points, k=neighbors); w.transform = 'R'
+// of /root/reference/chrysalis/core.py:64-65 (every weight is 1/k).  Built once per W, reused for
+// every gene / gene shard / permutation.
+//
+// z'Az needs every UNORDERED pair {i, j} once:
+//        z'Az = sum_{i<j} (a_ij + a_ji) z_i z_j + sum_i a_ii z_i^2
+// so the adjacency counts are re-expressed over QUADS of 4 consecutive spots (consecutive spots
+// of the Hilbert order are spatial neighbours):
+//   * pairs inside a quad  -> 6 coefficients (the kernel holds the 4 rows in registers)
+//   * every other pair     -> owned by exactly ONE endpoint, as (row, coefficient) in that spot's
+//     list.  Pairs only one endpoint lists stay with it; mutual pairs start with a hash-chosen
+//     owner and are moved by a few Jacobi sweeps so that the 4 lists of a quad get nearly equal
+//     length R: the kernel walks a quad in R rounds of 4 rows.
+//   * list entries are split into rows inside the quad's 128-spot tile (served from the tile the
+//     kernel stages in shared memory) and rows outside it (global loads): R = R_loc + R_glob.
+// On a square lattice with k = 8 a spot reads ~2.9 list rows instead of 8.  Any list is legal
+// (duplicates, self loops, asymmetric kNN): coefficients are multiplicities.  k <= 64 (one
+// 64-bit owner mask per spot).
+#include "moran.cuh"
+
+namespace chr {
+
+constexpr int kRelaxIters = 8;
+
+__device__ __forceinline__ uint32_t pair_hash(uint32_t i, uint32_t j) {
+    const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+    uint32_t h = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
+}
+
+// own[i] bit a: spot i owns the pair {i, nbr[i][a]}.  Only first occurrences of a neighbour carry a
+// bit; quad-internal and self pairs carry none.  cnt[i] = number of list entries of spot i.
+__global__ void plan_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, uint64_t* __restrict__ own,
+                                 int32_t* __restrict__ cnt, int32_t* __restrict__ indeg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* A = nbr + i * k;
+    uint64_t bits = 0;
+    int c = 0;
+    for (int a = 0; a < k; ++a) {
+        const int32_t j = A[a];
+        atomicAdd(indeg + j, 1);
+        bool first = true;
+        for (int b = 0; b < a; ++b) first &= (A[b] != j);
+        if (!first) continue;
+        if (j == (int32_t)i) { ++c; continue; }                        // self loop: one list entry, no bit
+        if ((j >> 2) == (int32_t)(i >> 2)) continue;                   // quad-internal
+        const int32_t* B = nbr + (int64_t)j * k;
+        bool back = false;
+        for (int b = 0; b < k; ++b) back |= (B[b] == (int32_t)i);
+        bool mine = true;                                              // a pair only i lists stays with i
+        if (back) {
+            const uint32_t lo = (uint32_t)(i < j ? i : j), hi = (uint32_t)(i < j ? j : i);
+            mine = ((pair_hash((uint32_t)i, (uint32_t)j) & 1u) ? lo : hi) == (uint32_t)i;
+        }
+        if (mine) { ++c; bits |= 1ull << a; }
+    }
+    own[i] = bits;
+    cnt[i] = c;
+}
+
+// one Jacobi sweep of owner balancing: a mutual pair moves to the other endpoint when that lowers
+// the larger of the two list lengths; both endpoints evaluate the same rule on the same data.
+__global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, const uint64_t* __restrict__ own_in,
+                                  const int32_t* __restrict__ cnt_in, uint64_t* __restrict__ own_out, int32_t* __restrict__ cnt_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* A = nbr + i * k;
+    const uint64_t mine_old = own_in[i];
+    uint64_t bits = mine_old;
+    int c = cnt_in[i];
+    const int ci = c;
+    for (int a = 0; a < k; ++a) {
+        const int32_t j = A[a];
+        if (j == (int32_t)i || (j >> 2) == (int32_t)(i >> 2)) continue;
+        bool first = true;
+        for (int b = 0; b < a; ++b) first &= (A[b] != j);
+        if (!first) continue;
+        const int32_t* B = nbr + (int64_t)j * k;
+        bool back = false;
+        for (int b = 0; b < k; ++b) back |= (B[b] == (int32_t)i);
+        if (!back) continue;                                           // one-sided pair: fixed owner
+        const bool i_owns = (mine_old >> a) & 1ull;
+        const int cj = cnt_in[j];
+        const int c_owner = i_owns ? ci : cj, c_other = i_owns ? cj : ci;
+        const bool flip = (c_owner > c_other + 1) && ((pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
+        if (flip) {
+            if (i_owns) { bits &= ~(1ull << a); --c; }
+            else { bits |= 1ull << a; ++c; }
+        }
+    }
+    own_out[i] = bits;
+    cnt_out[i] = c;
+}
+
+// walks the list entries spot i owns: f(j, coefficient, in_tile)
+template <typename F>
+__device__ __forceinline__ void plan_for_each_entry(const int32_t* __restrict__ nbr, int k, int64_t i, uint64_t bits, F f) {
+    const int32_t* A = nbr + i * k;
+    for (int a = 0; a < k; ++a) {
+        const int32_t j = A[a];
+        bool first = true;
+        int mult = 0;
+        for (int b = 0; b < k; ++b)
+            if (A[b] == j) { if (b < a) first = false; ++mult; }
+        if (!first) continue;
+        if (j == (int32_t)i) { f(j, (float)mult, true); continue; }     // a_ii z_i^2: own row with coefficient a_ii
+        if ((j >> 2) == (int32_t)(i >> 2)) continue;
+        if (!((bits >> a) & 1ull)) continue;
+        const int32_t* B = nbr + (int64_t)j * k;
+        int back = 0;
+        for (int b = 0; b < k; ++b) back += (B[b] == (int32_t)i);
+#ifdef CHR_EXPERIMENT_DROP_GLOBAL   /* timing experiment only: wrong statistics */
+        if ((j / kTileSpots) != (int32_t)(i / kTileSpots)) continue;
+#endif
+        f(j, (float)(mult + back), (j / kTileSpots) == (int32_t)(i / kTileSpots));
+    }
+}
+
+// record size of every quad in 16-byte units (R_loc / R_glob = longest in-tile / out-of-tile list of its spots)
+__global__ void plan_size_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t nquads, const uint64_t* __restrict__ own,
+                                 int32_t* __restrict__ qsize, int32_t* __restrict__ qrounds) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquads) return;
+    int rl = 0, rg = 0;
+    for (int t = 0; t < 4; ++t) {
+        const int64_t i = 4 * q + t;
+        if (i >= n) break;
+        int cl = 0, cg = 0;
+        plan_for_each_entry(nbr, k, i, own[i], [&](int32_t, float, bool in_tile) { if (in_tile) ++cl; else ++cg; });
+        rl = cl > rl ? cl : rl;
+        rg = cg > rg ? cg : rg;
+    }
+    qrounds[q] = rl | (rg << 8);
+    qsize[q] = kPlanHdrUnits + kPlanRoundUnits * (rl + rg);
+}
+
+// single-CTA exclusive scan of m ints; out[m .. m + pad) = total
+__global__ void plan_scan_kernel(const int32_t* __restrict__ in, int64_t m, int32_t* __restrict__ out, int pad) {
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t total;
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int64_t per = (m + nt - 1) / nt;
+    const int64_t b = (int64_t)t * per, e = b + per < m ? b + per : m;
+    int64_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += in[i];
+    sh[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < nt; ++i) { int64_t v = sh[i]; sh[i] = run; run += v; }
+        total = run;
+    }
+    __syncthreads();
+    int64_t run = sh[t];
+    for (int64_t i = b; i < e; ++i) { out[i] = (int32_t)run; run += in[i]; }
+    for (int i = t; i < pad; i += nt) out[m + i] = (int32_t)total;
+}
+
+// largest tile (16-byte units) and the plan header
+__global__ void plan_header_kernel(const int32_t* __restrict__ off, int64_t n, int k, int64_t nquads, PlanHeader* __restrict__ hdr,
+                                   int64_t off_bytes, int64_t rec_bytes) {
+    __shared__ int smax[256];
+    int m = 0;
+    const int64_t ntiles = (nquads + kTileQuads - 1) / kTileQuads;
+    for (int64_t c = threadIdx.x; c < ntiles; c += blockDim.x) {
+        const int64_t q0 = c * kTileQuads, q1 = q0 + kTileQuads < nquads ? q0 + kTileQuads : nquads;
+        const int u = off[q1] - off[q0];
+        m = u > m ? u : m;
+    }
+    smax[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < (int)blockDim.x; ++t) m = smax[t] > m ? smax[t] : m;
+        hdr->magic = kPlanMagic;
+        hdr->k = k;
+        hdr->n = n;
+        hdr->nquads = nquads;
+        hdr->chunk_units_max = m;
+        hdr->total_units = off[nquads];
+        hdr->off_bytes = off_bytes;
+        hdr->rec_bytes = rec_bytes;
+    }
+}
+
+// one thread per quad writes its record
+__global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t nquads, const uint64_t* __restrict__ own,
+                                 const int32_t* __restrict__ indeg, const int32_t* __restrict__ off, const int32_t* __restrict__ qrounds,
+                                 int32_t* __restrict__ rec_base) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquads) return;
+    int32_t* rec = rec_base + (int64_t)off[q] * 4;
+    float* recf = reinterpret_cast<float*>(rec);
+    const int RL = qrounds[q] & 0xff, RG = qrounds[q] >> 8;
+    const int nvalid = (int)(n - 4 * q < 4 ? n - 4 * q : 4);
+    for (int w = 1; w < kPlanHdrUnits * 4; ++w) recf[w] = 0.f;
+    rec[0] = RL | (RG << 8) | (nvalid << 16);
+    const int tile_row0 = (int)((4 * q) % kTileSpots);                 // row of the quad's first spot inside its tile
+    int32_t* loc = rec + kPlanHdrUnits * 4;
+    int32_t* glob = loc + RL * kPlanRoundUnits * 4;
+    for (int r = 0; r < RL; ++r)
+        for (int t = 0; t < 4; ++t) {
+            loc[r * 8 + t] = (tile_row0 + (t < nvalid ? t : 0)) * (kGeneTile * 4);   // padding: own row, coefficient 0
+            loc[r * 8 + 4 + t] = 0;
+        }
+    for (int r = 0; r < RG; ++r)
+        for (int t = 0; t < 4; ++t) {
+            glob[r * 8 + t] = (int32_t)(4 * q + (t < nvalid ? t : 0));
+            glob[r * 8 + 4 + t] = 0;
+        }
+    for (int t = 0; t < nvalid; ++t) {
+        const int64_t i = 4 * q + t;
+        int sl = 0, sg = 0;
+        float csum = 0.f;
+        plan_for_each_entry(nbr, k, i, own[i], [&](int32_t j, float c, bool in_tile) {
+            if (in_tile) {
+                if (sl < RL) { loc[sl * 8 + t] = (j % kTileSpots) * (kGeneTile * 4); reinterpret_cast<float*>(loc)[sl * 8 + 4 + t] = c; }
+                ++sl;
+            } else {
+                if (sg < RG) { glob[sg * 8 + t] = j; reinterpret_cast<float*>(glob)[sg * 8 + 4 + t] = c; }
+                ++sg;
+            }
+            csum += c;
+        });
+        recf[8 + t] = csum;
+        recf[12 + t] = (float)indeg[i];
+        // pairs inside the quad: written by the lower spot when it lists the pair, else by the upper one
+        const int32_t* A = nbr + i * k;
+        for (int a = 0; a < k; ++a) {
+            const int32_t j = A[a];
+            if (j == (int32_t)i || (j >> 2) != (int32_t)(i >> 2)) continue;
+            int mult = 0, back = 0;
+            for (int b = 0; b < k; ++b) mult += (A[b] == j);
+            const int32_t* B = nbr + (int64_t)j * k;
+            for (int b = 0; b < k; ++b) back += (B[b] == (int32_t)i);
+            const int u = t, v = (int)(j & 3);
+            const int lo = u < v ? u : v, hi = u < v ? v : u;
+            const int idx = lo == 0 ? hi - 1 : (lo == 1 ? hi + 1 : 5);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+            recf[1 + idx] = (float)(mult + back);                            // words 1..3 (unit 0), 4..6 (unit 1)
+        }
+    }
+}
+
+struct PlanScratch {
+    size_t own[2], cnt[2], indeg, qsize, qrounds, total;
+};
+static PlanScratch plan_scratch(int64_t n) {
+    PlanScratch p;
+    const int64_t nquads = (n + 3) / 4;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += round_up<size_t>(b, 256); return r; };
+    for (int b = 0; b < 2; ++b) { p.own[b] = take((size_t)n * 8); p.cnt[b] = take((size_t)n * 4); }
+    p.indeg = take((size_t)n * 4);
+    p.qsize = take((size_t)nquads * 4);
+    p.qrounds = take((size_t)nquads * 4);
+    p.total = o;
+    return p;
+}
+
+}  // namespace chr
+
+extern "C" {
+
+size_t chr_moran_plan_bytes(int64_t n_spots, int k) {
+    if (n_spots <= 0 || k <= 0) return chr::kPlanHeaderBytes;
+    const int64_t nquads = (n_spots + 3) / 4;
+    return chr::kPlanHeaderBytes + chr::round_up<size_t>((size_t)(nquads + 1 + chr::kPlanOffPad) * 4, 256) +
+           chr::plan_rec_capacity_bytes(n_spots, k) + 256;
+}
+
+size_t chr_moran_plan_workspace_bytes(int64_t n_spots, int k) {
+    (void)k;
+    return chr::plan_scratch(n_spots > 0 ? n_spots : 1).total + 512;
+}
+
+int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan, size_t plan_bytes, int32_t* info_host,
+                         void* workspace, size_t workspace_bytes, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(nbr && plan && workspace, "chr_moran_plan_build: null pointer argument");
+    CHR_REQUIRE(n_spots > 1 && n_spots < (1LL << 31), "chr_moran_plan_build: need 1 < n_spots < 2^31 (got %lld)", (long long)n_spots);
+    CHR_REQUIRE(k > 0 && k <= 64 && k < n_spots, "chr_moran_plan_build: need 0 < k <= 64 and k < n_spots (k=%d)", k);
+    CHR_REQUIRE(((uintptr_t)plan & 255) == 0, "chr_moran_plan_build: plan must be 256-byte aligned");
+    CHR_REQUIRE(plan_bytes >= chr_moran_plan_bytes(n_spots, k), "chr_moran_plan_build: plan buffer too small (%zu < %zu)", plan_bytes,
+                chr_moran_plan_bytes(n_spots, k));
+    PlanScratch sc = plan_scratch(n_spots);
+    CHR_REQUIRE(workspace_bytes >= sc.total + 256, "chr_moran_plan_build: workspace too small (%zu < %zu)", workspace_bytes, sc.total + 256);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint64_t* own[2] = {(uint64_t*)(ws + sc.own[0]), (uint64_t*)(ws + sc.own[1])};
+    int32_t* cnt[2] = {(int32_t*)(ws + sc.cnt[0]), (int32_t*)(ws + sc.cnt[1])};
+    int32_t* indeg = (int32_t*)(ws + sc.indeg);
+    int32_t* qsize = (int32_t*)(ws + sc.qsize);
+    int32_t* qrounds = (int32_t*)(ws + sc.qrounds);
+    const int64_t nquads = (n_spots + 3) / 4;
+    const int64_t off_bytes = kPlanHeaderBytes;
+    const int64_t rec_bytes = off_bytes + (int64_t)round_up<size_t>((size_t)(nquads + 1 + kPlanOffPad) * 4, 256);
+    PlanHeader* hdr = (PlanHeader*)plan;
+    int32_t* off = (int32_t*)((char*)plan + off_bytes);
+    int32_t* rec = (int32_t*)((char*)plan + rec_bytes);
+
+    const unsigned gs = (unsigned)ceil_div<int64_t>(n_spots, 128), gq = (unsigned)ceil_div<int64_t>(nquads, 128);
+    timer_begin(CHR_FAMILY_KNN, true, st);
+    CHR_CUDA(cudaMemsetAsync(indeg, 0, (size_t)n_spots * 4, st));
+    plan_init_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, own[0], cnt[0], indeg);
+    int cur = 0;
+    for (int it = 0; it < kRelaxIters; ++it, cur ^= 1)
+        plan_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
+    plan_size_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, nquads, own[cur], qsize, qrounds);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(qsize, nquads, off, 1 + kPlanOffPad);
+    plan_header_kernel<<<1, 256, 0, st>>>(off, n_spots, k, nquads, hdr, off_bytes, rec_bytes);
+    plan_fill_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, nquads, own[cur], indeg, off, qrounds, rec);
+    timer_end(CHR_FAMILY_KNN, true, st);
+    CHR_LAUNCH_CHECK();
+    if (info_host) {
+        PlanHeader h;
+        CHR_CUDA(cudaMemcpyAsync(&h, hdr, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CHR_CUDA(cudaStreamSynchronize(st));
+        info_host[0] = h.chunk_units_max;
+        info_host[1] = h.total_units;
+        info_host[2] = (int32_t)nquads;
+        info_host[3] = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

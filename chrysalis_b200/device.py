@@ -154,11 +154,48 @@ def knn_build(xy: torch.Tensor, k: int, bbox: torch.Tensor | None = None) -> tor
 
 # ---- K3 / K4 -----------------------------------------------------------------------------
 
+@dataclass
+class MoranPlan:
+    """Device representation of W for the Moran tile kernel (``chr_moran_plan_build``)."""
+    buf: torch.Tensor      # uint8 plan buffer
+    chunk_units: int       # largest tile slice (16-byte units) - sizes the kernel's staging buffers
+    total_units: int
+    n: int
+    k: int
+
+
+def moran_plan(nbr: torch.Tensor) -> MoranPlan | None:
+    """Quad plan of the kNN lists ``nbr`` [n, k] int32 (built once per W).  ``None`` for k > 64
+    (the per-spot stream kernel handles those straight from ``nbr``)."""
+    import ctypes
+
+    assert nbr.dtype == torch.int32 and nbr.is_contiguous() and nbr.dim() == 2
+    n, k = nbr.shape
+    if k > 64:
+        return None
+    nbytes = _lib.query("chr_moran_plan_bytes", n, k)
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=nbr.device)
+    pad = (-buf.data_ptr()) % 256
+    buf = buf[pad:pad + nbytes]
+    ws_bytes = _lib.query("chr_moran_plan_workspace_bytes", n, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=nbr.device)
+    info = (ctypes.c_int32 * 4)()
+    _lib.call("chr_moran_plan_build", _ptr(nbr), n, k, _ptr(buf), nbytes, ctypes.addressof(info), _ptr(ws), ws_bytes, _stream())
+    # keep only the used part of the (worst-case sized) buffer
+    used = 256 + ((n + 3) // 4 + 1 + 64) * 4 + 256 + int(info[1]) * 16 + 256
+    keep = buf[:min(nbytes, used)].clone() if used < nbytes // 2 else buf
+    if keep.data_ptr() % 256:
+        keep = buf
+    return MoranPlan(keep, int(info[0]), int(info[1]), n, k)
+
+
 def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, geary: bool = False,
-                timing: bool = False, want_stats: bool = False, variant: int | None = None, preshifted: bool = False):
+                timing: bool = False, want_stats: bool = False, variant: int | None = None, preshifted: bool = False,
+                plan: MoranPlan | None = None):
     """Moran's I (and Geary's C) of every column of the dense [n, ld] float32 matrix ``X``.
 
     Returns ``(I, C, stats)`` float64 device tensors (``C``/``stats`` None unless requested).
+    ``plan``: the quad plan of ``nbr`` (built here when not given; reuse it across calls with the same W).
     ``preshifted``: the columns of ``X`` already have (near-)zero mean, skip the in-kernel shift.
     """
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
@@ -169,6 +206,8 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     g = X.shape[1] if n_genes is None else n_genes
     if variant is None:
         variant = int(os.environ.get("CHR_MORAN_VARIANT", "0"))   # kernel-variant override for tuning runs
+    if plan is None and variant != 4:
+        plan = moran_plan(nbr)
     flags = ((_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) |
              (_lib.FLAG_PRESHIFTED if preshifted else 0) | (variant << _lib.VARIANT_SHIFT))
     ws_bytes = _lib.query("chr_moran_workspace_bytes", n, g, k, flags)
@@ -176,7 +215,8 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     out_I = torch.empty(g, dtype=torch.float64, device=X.device)
     out_C = torch.empty(g, dtype=torch.float64, device=X.device) if geary else None
     stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
-    _lib.call("chr_moran_dense_f32", _ptr(X), n, g, ld, _ptr(nbr), k, flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
+    _lib.call("chr_moran_dense_f32", _ptr(X), n, g, ld, _ptr(nbr), k, _ptr(plan.buf) if plan is not None else 0,
+              plan.chunk_units if plan is not None else 0, flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
               _ptr(ws), ws_bytes, _stream())
     return out_I, out_C, stats
 

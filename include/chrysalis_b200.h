@@ -80,19 +80,37 @@ int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const f
                           const int32_t* gene_col, const double* scale, const int64_t* row_of_spot,
                           float* dense, int64_t ld, int apply_log1p, chr_stream_t stream);
 
+/* ---- K1b: W as a device plan ------------------------------------------------------------
+ * the device representation of the row-standardised kNN weights (core.py:64-65) that the
+ * Moran kernel streams against: every unordered pair {i, j} once with coefficient
+ * a_ij + a_ji, grouped by quads of 4 consecutive spots, each pair owned by one endpoint, the
+ * owners balanced, entries split into rows inside / outside the quad's 128-spot tile.
+ * Built once per W (k <= 64; any list: duplicates, self loops, asymmetric kNN).
+ * plan: device buffer of chr_moran_plan_bytes(), 256-byte aligned.  info_host (HOST, int32[4],
+ * may be NULL): {largest tile slice in 16-byte units (pass to chr_moran_dense_f32), total units,
+ * quads, 0}; reading it back synchronises the stream. */
+size_t chr_moran_plan_bytes(int64_t n_spots, int k);
+size_t chr_moran_plan_workspace_bytes(int64_t n_spots, int k);
+int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan, size_t plan_bytes,
+                         int32_t* info_host, void* workspace, size_t workspace_bytes,
+                         chr_stream_t stream);
+
 /* ---- K3/K4: Moran's I (and Geary's C) ------------------------------------------------
  * replaces  the gene loop  esda.moran.Moran(gene_matrix[c], w, permutations=0).I
  *           [+ esda.geary.Geary(...).C]      (/root/reference/chrysalis/core.py:71-76)
  * X: [n_spots][ld] float32 dense expression (ld % 4 == 0, X 16-byte aligned, columns
- *    n_genes..ld-1 readable), nbr: [n_spots][k] int32 (K1 output or any kNN list).
+ *    n_genes..round_up(n_genes,4)-1 readable), nbr: [n_spots][k] int32 (K1 output or any kNN
+ *    list), plan + plan_chunk_units: chr_moran_plan_build's output for the same nbr.
+ *    With a plan the TMA tile kernel runs (nbr may be NULL); without one (plan NULL, any k) the
+ *    per-spot stream kernel runs from nbr.
  * out_I / out_C: [n_genes] float64 (out_C may be NULL without CHR_FLAG_GEARY).
  * out_stats: optional [4][n_genes] float64 = {mean, z'z, z'Wz, geary numerator}.
- * One pass over X; per-gene accumulators fp32 in 16-spot chunks -> fp64. */
+ * One pass over X; per-gene accumulators fp32 over <= 8/16 spots, fp32 per CTA, then fp64. */
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags);
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld,
-                        const int32_t* nbr, int k, unsigned flags, double* out_I, double* out_C,
-                        double* out_stats, void* workspace, size_t workspace_bytes,
-                        chr_stream_t stream);
+                        const int32_t* nbr, int k, const void* plan, int plan_chunk_units,
+                        unsigned flags, double* out_I, double* out_C, double* out_stats,
+                        void* workspace, size_t workspace_bytes, chr_stream_t stream);
 
 /* ---- K6-K8: PCA of the SVG matrix ------------------------------------------------------
  * replaces  PCA(n_components=n_pcs, svd_solver='arpack', random_state=42).fit_transform(pcs)

@@ -44,14 +44,17 @@ def test_workspace_queries_need_no_gpu(lib):
     assert lib.chr_moran_workspace_bytes(4035, 13000, 6, 0) > 4035
     assert lib.chr_moran_workspace_bytes(700000, 18000, 8, 0) < (1 << 30)
     assert lib.chr_knn_workspace_bytes(700000, 8) > 700000 * 8
+    assert 700000 * 8 < lib.chr_moran_plan_bytes(700000, 8) < (1 << 30)
 
 
 def test_argument_validation_precedes_any_cuda_call(lib):
     # null / inconsistent arguments are rejected with a message before touching the device
-    rc = lib.chr_moran_dense_f32(None, 100, 10, 10, None, 6, 0, None, None, None, None, 0, None)
+    rc = lib.chr_moran_dense_f32(None, 100, 10, 10, None, 6, None, 0, 0, None, None, None, None, 0, None)
     assert rc != 0 and b"chr_moran_dense_f32" in lib.chr_last_error()
     rc = lib.chr_knn_build(None, 10, 3, None, None, None, 0, None)
     assert rc != 0 and b"chr_knn_build" in lib.chr_last_error()
+    rc = lib.chr_moran_plan_build(None, 10, 3, None, 0, None, None, 0, None)
+    assert rc != 0 and b"chr_moran_plan_build" in lib.chr_last_error()
 
 
 def test_no_cpu_fallback_without_cuda():
