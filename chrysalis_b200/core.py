@@ -12,6 +12,7 @@ import pandas as pd
 import torch
 
 from . import device as dv
+from . import distributed as dd
 
 
 def _make_unique(names) -> pd.Index:
@@ -42,36 +43,50 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
 
     Returns host arrays ``(keep_mask (G,), I (G',), C (G',) or None)``; also usable directly
     (bench, multi-GPU driver).  Mirrors core.py:53-76.
+
+    Under an initialised ``torch.distributed`` group (one process per GPU) every rank takes a
+    contiguous range of the genes: the filter is per gene (local), the per-spot totals of
+    ``normalize_total`` are all-reduced, W is built on every rank, Moran's I needs no exchange,
+    and the per-gene results are all-gathered so every rank returns the full arrays.
     """
-    n = X.shape[0]
-    csr = dv.upload_csr(X)
+    n, g_all = X.shape
+    rank, size = dd.world()
+    lo, hi = dd.shard_range(g_all, rank, size)
+    csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
     gene_nnz = dv.csr_gene_nnz(csr)
     keep = gene_nnz >= int(n * min_spots)
     gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
                            torch.full_like(gene_nnz, -1))
     n_keep = int(keep.sum().item())
-    if n_keep == 0:
-        return keep.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
+    keep_all = dd.allgather_ragged(keep, g_all)
+    if int(keep_all.sum().item()) == 0:
+        return keep_all.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
     # core.py:55-57  normalize_total + log1p on the filtered copy unless the caller already did
     scale = None
     if not already_log1p:
-        scale = dv.median_scale(dv.csr_spot_totals(csr, gene_col))
+        scale = dv.median_scale(dd.allreduce_sum_(dv.csr_spot_totals(csr, gene_col)))
     # core.py:61-65  kNN weights on (x, -y), row-standardised
     pts = np.array(spatial, dtype=np.float64, copy=True)
     pts[:, 1] = pts[:, 1] * -1
     xy = dv.to_device(pts, torch.float64)
     bbox = dv.spatial_bbox(xy)
     order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
-    rank = torch.empty_like(order)
-    rank[order] = torch.arange(n, device=order.device)
+    rank_of = torch.empty_like(order)
+    rank_of[order] = torch.arange(n, device=order.device)
     nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
     plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
-    # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
-    dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank, apply_log1p=not already_log1p)
-    # core.py:71-76  the gene loop
-    I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
-    return keep.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
+    if n_keep > 0:
+        # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
+        dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p)
+        # core.py:71-76  the gene loop
+        I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
+    else:
+        I = torch.empty(0, dtype=torch.float64, device=keep.device)
+        C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None
+    I = dd.allgather_ragged(I)
+    C = dd.allgather_ragged(C) if geary else None
+    return keep_all.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
 
 
 def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
@@ -120,6 +135,10 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     eigensolver -> scores.  Returns host arrays (scores (n, r) float32, components (r, S) float32,
     explained_variance_ratio (r,) float32).  Mirrors sklearn's PCA(arpack) as called at core.py:127-128:
     centre, top-r right singular vectors, ``svd_flip`` (v-based), scores = U * S.
+
+    Under an initialised ``torch.distributed`` group every rank takes a contiguous range of the
+    SPOTS: column sums and the partial Grams are all-reduced, the small eigenproblem is solved on
+    every rank, the scores of the local spots are all-gathered.
     """
     n = X.shape[0]
     s = int(sel.sum())
@@ -127,13 +146,15 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     if not 0 < n_pcs < min(n, s):
         raise ValueError(f"n_components={n_pcs} must be strictly less than min(n_samples, n_features)={min(n, s)} "
                          "with svd_solver='arpack'")
-    csr = dv.upload_csr(X)
+    rank, size = dd.world()
+    lo, hi = dd.shard_range(n, rank, size)
+    csr = dv.upload_csr(X if size == 1 else X[lo:hi])
     sel_d = dv.to_device(sel.astype(np.bool_))
     gene_col = torch.where(sel_d, torch.cumsum(sel_d.to(torch.int32), 0, dtype=torch.int32) - 1,
                            torch.full((sel_d.numel(),), -1, dtype=torch.int32, device=sel_d.device))
     P = dv.csr_densify(csr, gene_col, s, None, None, apply_log1p=False)     # core.py:126  .X.todense()
-    mean = dv.column_sums(P, s) / n
-    C = dv.gram_centered(P, s, mean, timing=timing) / (n - 1)               # covariance (ddof=1)
+    mean = dd.allreduce_sum_(dv.column_sums(P, s)) / n
+    C = dd.allreduce_sum_(dv.gram_centered(P, s, mean, timing=timing)) / (n - 1)   # covariance (ddof=1)
     total_var = torch.diagonal(C).sum()
     evals, V, _ = dv.eigh_topk(C, n_pcs)
     # svd_flip(u, v, u_based_decision=False): largest-|.| entry of every component is positive
@@ -141,7 +162,7 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     signs = torch.sign(V[torch.arange(V.shape[0], device=V.device), idx])
     signs[signs == 0] = 1.0
     V = V * signs[:, None]
-    scores = dv.pca_scores(P, s, mean, V)
+    scores = dd.allgather_ragged(dv.pca_scores(P, s, mean, V), n)
     ratio = (evals / total_var).to(torch.float32)
     return scores.cpu().numpy(), V.to(torch.float32).cpu().numpy(), ratio.cpu().numpy()
 
