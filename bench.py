@@ -298,7 +298,7 @@ def run_native(args):
         e_steps = max(2, min(args.steps, 5))
 
         def e2e_step():
-            keep, I_h, _ = core.svg_stage(host, xy_host, MIN_SPOTS, k, False, already_log1p=False)
+            keep, I_h, _ = core.svg_stage(host, xy_host, MIN_SPOTS, k, False, already_log1p=False, shard=False)
             return I_h
 
         I_h = e2e_step()

@@ -38,7 +38,8 @@ def _make_unique(names) -> pd.Index:
     return pd.Index(out)
 
 
-def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False):
+def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False,
+              shard: bool = True):
     """Device part of ``detect_svgs``: filter -> normalise/log1p -> kNN W -> Moran's I.
 
     Returns host arrays ``(keep_mask (G,), I (G',), C (G',) or None)``; also usable directly
@@ -48,9 +49,10 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     contiguous range of the genes: the filter is per gene (local), the per-spot totals of
     ``normalize_total`` are all-reduced, W is built on every rank, Moran's I needs no exchange,
     and the per-gene results are all-gathered so every rank returns the full arrays.
+    ``shard=False`` keeps the call local to this rank (every rank works on its own matrix).
     """
     n, g_all = X.shape
-    rank, size = dd.world()
+    rank, size = dd.world() if shard else (0, 1)
     lo, hi = dd.shard_range(g_all, rank, size)
     csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
@@ -59,13 +61,15 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
                            torch.full_like(gene_nnz, -1))
     n_keep = int(keep.sum().item())
-    keep_all = dd.allgather_ragged(keep, g_all)
+    gather = dd.allgather_ragged if size > 1 else (lambda t, n_total=None: t)
+    reduce_ = dd.allreduce_sum_ if size > 1 else (lambda t: t)
+    keep_all = gather(keep, g_all)
     if int(keep_all.sum().item()) == 0:
         return keep_all.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
     # core.py:55-57  normalize_total + log1p on the filtered copy unless the caller already did
     scale = None
     if not already_log1p:
-        scale = dv.median_scale(dd.allreduce_sum_(dv.csr_spot_totals(csr, gene_col)))
+        scale = dv.median_scale(reduce_(dv.csr_spot_totals(csr, gene_col)))
     # core.py:61-65  kNN weights on (x, -y), row-standardised
     pts = np.array(spatial, dtype=np.float64, copy=True)
     pts[:, 1] = pts[:, 1] * -1
@@ -84,8 +88,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     else:
         I = torch.empty(0, dtype=torch.float64, device=keep.device)
         C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None
-    I = dd.allgather_ragged(I)
-    C = dd.allgather_ragged(C) if geary else None
+    I = gather(I)
+    C = gather(C) if geary else None
     return keep_all.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
 
 

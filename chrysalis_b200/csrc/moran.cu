@@ -476,15 +476,13 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                 r4_add(l1[0], x[t]);
                 r4_fma(l1[1], x[t], x[t]);
                 r4_fma(l1[2], x[t], s[t]);
-                if (GEARY) {
+                r4_fmac(l1[3], dgs[t], x[t]);
+                if (GEARY) {                                          // same I with or without Geary's C
                     Row4 dx;
                     const f2_t dd = f2_dup(dgs[t]);
                     dx.a = f2_fma(dd, x[t].a, z2);
                     dx.b = f2_fma(dd, x[t].b, z2);
-                    r4_add(l1[3], dx);
                     r4_fma(l1[4], dx, x[t]);
-                } else {
-                    r4_fmac(l1[3], dgs[t], x[t]);
                 }
             };
             if (nvalid == 4) {                                        // every quad but the last one of a ragged n

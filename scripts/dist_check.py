@@ -43,7 +43,7 @@ def main():
         dd.world = lambda: (0, 1)
         try:
             ad1 = ch.AnnDataLite(X, obsm={"spatial": z["xy"]})
-            ch.detect_svgs(ad1, neighbors=int(z["k"]), top_svg=int(z["top_svg"]), min_morans=float(z["min_morans"]))
+            ch.detect_svgs(ad1, neighbors=int(z["k"]), top_svg=int(z["top_svg"]), min_morans=float(z["min_morans"]), geary=True)
             ref = torch.from_numpy(ad1.var["Moran's I"].to_numpy().copy()).cuda()
         finally:
             dd.world = saved

@@ -286,3 +286,12 @@ def test_cfg1_shape_selection_identical():
     m = ref["gene_mask"]
     assert_close(ad.var["Moran's I"].to_numpy()[m], ref["morans"][m])
     assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+
+
+def test_morans_I_does_not_depend_on_the_geary_flag(golden_random):
+    z = golden_random
+    m = z["gene_mask"]
+    d = dense_from(golden_csr(z), m)
+    I0, _, _ = gpu_moran(d, z["nbr"])
+    I1, _, _ = gpu_moran(d, z["nbr"], geary=True)
+    assert np.array_equal(I0, I1)
