@@ -200,7 +200,9 @@ def pca(adata, n_pcs: int = 50):
 
 def _furthest_sum(X: np.ndarray, n_archetypes: int, rs: np.random.RandomState) -> np.ndarray:
     """FurthestSum seeding (Morup & Hansen 2012) as archetypes 0.4.x draws it: a random start, greedy
-    picks of the point with the largest summed distance to the chosen set, then 10 re-pick rounds."""
+    picks of the point with the largest summed distance to the chosen set, then 10 re-pick rounds.
+    Host statement of what ``chr_aa_furthest_sum`` does on the device (``aa_stage`` uses the device
+    kernel; this stays as the readable definition the tests pin it against)."""
     X = np.asarray(X, dtype=np.float64)
     n = X.shape[0]
     sq = np.einsum("ij,ij->i", X, X)
@@ -241,7 +243,7 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
         if init_rows is not None:
             rows = np.asarray(init_rows[r], dtype=np.int64)
         else:
-            rows = _furthest_sum(X, n_archetypes, rs)
+            rows = dv.aa_furthest_sum(Xd, n_archetypes, int(rs.randint(n)))
             rs.choice(n_archetypes, n, replace=True)            # alphas0 draw: unused by the updates, keeps the RNG stream
         used.append(rows)
         st = dv.AAState(Xd, n_archetypes)

@@ -164,6 +164,17 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
     for (int e = threadIdx.x; e < nacc; e += blockDim.x) part[(size_t)blockIdx.x * nacc + e] = acc[e];
 }
 
+// fixed-order reduction of the per-CTA partials  A^T A | A^T X  in chunks of 64 CTAs (second level in aa_pinv_kernel)
+constexpr int kAaRedChunk = 64;
+__global__ void aa_partial_reduce_kernel(const double* __restrict__ part, int nparts, int nacc, double* __restrict__ part2) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nacc) return;
+    const int p0 = blockIdx.y * kAaRedChunk, p1 = p0 + kAaRedChunk < nparts ? p0 + kAaRedChunk : nparts;
+    double a = 0.0;
+    for (int p = p0; p < p1; ++p) a += part[(size_t)p * nacc + e];
+    part2[(size_t)blockIdx.y * nacc + e] = a;
+}
+
 // ---- pinv step (single CTA): Zhat = pinv(alphas) X via eigen-decomposition of A^T A ---------------------
 __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int na, int d, int64_t n, double* __restrict__ Zhat) {
     extern __shared__ double sh[];
@@ -465,9 +476,64 @@ __global__ void aa_gather_rows_kernel(const double* __restrict__ X, int d, const
     if (e < na * d) Z[e] = X[rows[e / d] * d + e % d];
 }
 
+// ---- FurthestSum seeding (Morup & Hansen 2012; the initialisation archetypes 0.4.x draws) -----------------
+//   total[i] += sign * || x_i - x_c ||   for one chosen point c; then arg-max over the points not chosen yet
+__global__ void __launch_bounds__(256)
+aa_fs_update_kernel(const double* __restrict__ X, int64_t n, int d, int64_t c, double sign, double* __restrict__ total) {
+    extern __shared__ double xc[];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) xc[t] = X[c * d + t];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // same arithmetic as the host formulation: sqrt(max(|x_i|^2 - 2 x_i.x_c + |x_c|^2, 0))
+    double sq = 0.0, dot = 0.0, sc = 0.0;
+    const double* __restrict__ x = X + i * d;
+    for (int t = 0; t < d; ++t) { sq += x[t] * x[t]; dot += x[t] * xc[t]; sc += xc[t] * xc[t]; }
+    const double v = sq - 2.0 * dot + sc;
+    total[i] += sign * sqrt(v > 0.0 ? v : 0.0);
+}
+
+// arg-max of total[] over the points with avail[i] != 0; lowest index wins ties (numpy.argmax semantics)
+__global__ void __launch_bounds__(256)
+aa_fs_argmax_partial_kernel(const double* __restrict__ total, const unsigned char* __restrict__ avail, int64_t n,
+                            double* __restrict__ cand_w, int64_t* __restrict__ cand_i) {
+    __shared__ double rw[8];
+    __shared__ int64_t ri[8];
+    double bw = -1e300;
+    int64_t bi = -1;
+    const int64_t i0 = (int64_t)blockIdx.x * 4096, i1 = i0 + 4096 < n ? i0 + 4096 : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+        if (avail[i] && (total[i] > bw || bi < 0)) { bw = total[i]; bi = i; }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ow = __shfl_xor_sync(0xffffffffu, bw, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ow > bw || (ow == bw && oi < bi))) { bw = ow; bi = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { rw[warp] = bw; ri[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (ri[w] >= 0 && (bi < 0 || rw[w] > bw || (rw[w] == bw && ri[w] < bi))) { bw = rw[w]; bi = ri[w]; }
+        cand_w[blockIdx.x] = bw;
+        cand_i[blockIdx.x] = bi;
+    }
+}
+
+__global__ void aa_fs_argmax_final_kernel(const double* __restrict__ cand_w, const int64_t* __restrict__ cand_i, int nb,
+                                          unsigned char* __restrict__ avail, int64_t* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double bw = -1e300;
+    int64_t bi = -1;
+    for (int b = 0; b < nb; ++b)
+        if (cand_i[b] >= 0 && (bi < 0 || cand_w[b] > bw || (cand_w[b] == bw && cand_i[b] < bi))) { bw = cand_w[b]; bi = cand_i[b]; }
+    *out = bi;
+    if (bi >= 0) avail[bi] = 0;
+}
+
 struct AaPlan {
     int alpha_blocks, grad_blocks, rss_blocks, nacc;
-    size_t off_part, off_zhat, off_R, off_state, off_pidx, off_bcoef, off_candw, off_candi, off_scr, off_rsspart, total;
+    size_t off_part, off_part2, off_zhat, off_R, off_state, off_pidx, off_bcoef, off_candw, off_candi, off_scr, off_rsspart, total;
 };
 
 static AaPlan aa_plan(int64_t n, int d, int na) {
@@ -479,6 +545,7 @@ static AaPlan aa_plan(int64_t n, int d, int na) {
     size_t o = 0;
     auto take = [&](size_t b) { size_t x = o; o += round_up<size_t>(b, 256); return x; };
     p.off_part = take((size_t)p.alpha_blocks * p.nacc * 8);
+    p.off_part2 = take((size_t)ceil_div(p.alpha_blocks, kAaRedChunk) * p.nacc * 8);
     p.off_zhat = take((size_t)na * d * 8);
     p.off_R = take((size_t)na * (d + 1) * 8);
     p.off_state = take(sizeof(BetaState));
@@ -510,6 +577,59 @@ int chr_aa_init_archetypes(const double* X, int64_t n, int d, const int64_t* row
     return 0;
 }
 
+size_t chr_aa_furthest_sum_workspace_bytes(int64_t n) {
+    const int64_t nb = chr::ceil_div<int64_t>(n > 0 ? n : 1, 4096);
+    return chr::round_up<size_t>((size_t)(n > 0 ? n : 1) * 8, 256) + chr::round_up<size_t>((size_t)(n > 0 ? n : 1), 256) +
+           2 * chr::round_up<size_t>((size_t)nb * 8, 256) + 256 + 512;
+}
+
+// FurthestSum: `first` is the random starting point (drawn by the host RNG); rows_out (HOST, int64[n_archetypes])
+// receives the chosen data points in the order the host algorithm produces them.
+int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int64_t first, int64_t* rows_out,
+                        void* workspace, size_t workspace_bytes, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(X && rows_out && workspace, "chr_aa_furthest_sum: null pointer argument");
+    CHR_REQUIRE(n > 0 && d > 0 && n_archetypes >= 1 && n_archetypes < n && first >= 0 && first < n, "chr_aa_furthest_sum: bad arguments");
+    CHR_REQUIRE(workspace_bytes >= chr_aa_furthest_sum_workspace_bytes(n) - 256, "chr_aa_furthest_sum: workspace too small");
+    const int nb = (int)ceil_div<int64_t>(n, 4096);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double* total = (double*)ws;
+    unsigned char* avail = (unsigned char*)(ws + round_up<size_t>((size_t)n * 8, 256));
+    double* cand_w = (double*)((char*)avail + round_up<size_t>((size_t)n, 256));
+    int64_t* cand_i = (int64_t*)((char*)cand_w + round_up<size_t>((size_t)nb * 8, 256));
+    int64_t* pick = (int64_t*)((char*)cand_i + round_up<size_t>((size_t)nb * 8, 256));
+    CHR_CUDA(cudaMemsetAsync(total, 0, (size_t)n * 8, st));
+    CHR_CUDA(cudaMemsetAsync(avail, 1, (size_t)n, st));
+    CHR_CUDA(cudaMemsetAsync(avail + first, 0, 1, st));
+    const unsigned gu = (unsigned)ceil_div<int64_t>(n, 256);
+    const size_t sm = (size_t)d * 8;
+    // the host algorithm (chrysalis_b200/core.py:_furthest_sum): picks = [first]; for step in 1 .. A + 10:
+    //   if step > A - 1: drop the oldest pick (subtract its distances, make it available again)
+    //   add the distances to the current point; next = arg-max over available points; append
+    int64_t picks[kAaMaxA + 16];
+    int np = 0, head = 0;
+    picks[np++] = first;
+    int64_t cur = first;
+    for (int step = 1; step < n_archetypes + 11; ++step) {
+        if (step > n_archetypes - 1) {
+            const int64_t oldest = picks[head++];
+            aa_fs_update_kernel<<<gu, 256, sm, st>>>(X, n, d, oldest, -1.0, total);
+            CHR_CUDA(cudaMemsetAsync(avail + oldest, 1, 1, st));
+        }
+        aa_fs_update_kernel<<<gu, 256, sm, st>>>(X, n, d, cur, 1.0, total);
+        aa_fs_argmax_partial_kernel<<<nb, 256, 0, st>>>(total, avail, n, cand_w, cand_i);
+        aa_fs_argmax_final_kernel<<<1, 32, 0, st>>>(cand_w, cand_i, nb, avail, pick);
+        CHR_LAUNCH_CHECK();
+        CHR_CUDA(cudaMemcpyAsync(&cur, pick, 8, cudaMemcpyDeviceToHost, st));
+        CHR_CUDA(cudaStreamSynchronize(st));
+        CHR_REQUIRE(cur >= 0, "chr_aa_furthest_sum: no available point left");
+        picks[np++] = cur;
+    }
+    for (int a = 0; a < n_archetypes; ++a) rows_out[a] = picks[head + a];
+    return 0;
+}
+
 // one full iteration:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);  Z <- betas X;  rss
 int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, double* Z, double* alphas,
                    double* rss_out, int* beta_passes_out, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
@@ -523,6 +643,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     CHR_REQUIRE(workspace_bytes >= p.total + 256, "chr_aa_iterate: workspace too small (%zu < %zu)", workspace_bytes, p.total + 256);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     double* part = (double*)(ws + p.off_part);
+    double* part2 = (double*)(ws + p.off_part2);
     double* Zhat = (double*)(ws + p.off_zhat);
     double* R = (double*)(ws + p.off_R);
     BetaState* bst = (BetaState*)(ws + p.off_state);
@@ -548,7 +669,9 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     // ---- Zhat = pinv(alphas) X
     const size_t sm_pinv = (size_t)(2 * na * na + na * d) * 8;
     if (sm_pinv > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pinv));
-    aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part, p.alpha_blocks, na, d, n, Zhat);
+    const int nred = ceil_div(p.alpha_blocks, kAaRedChunk);
+    aa_partial_reduce_kernel<<<dim3((unsigned)ceil_div(p.nacc, 128), (unsigned)nred), 128, 0, st>>>(part, p.alpha_blocks, p.nacc, part2);
+    aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part2, nred, na, d, n, Zhat);
     CHR_LAUNCH_CHECK();
     // ---- betas: active-set passes, every archetype advances one step per pass
     aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, R);

@@ -253,32 +253,62 @@ __global__ void rayleigh_residual_kernel(const double* __restrict__ C, const dou
 }
 
 // ---- scores:  Y[i][c] = sum_g (P[i][g] - mean[g]) V[c][g] ------------------------------------
-template <int RB>   // components per pass
+// skinny GEMM on CUDA cores (r <= 50 columns): a CTA owns 64 spots, walks the genes in chunks of 32
+// (centred Z tile and V^T tile in shared memory), every thread accumulates 8 components of one spot.
+// One pass over P per 32 components: HBM-bound (4 N S bytes).
+constexpr int kScRows = 64, kScK = 32, kScComp = 32;
 __global__ void __launch_bounds__(256)
 pca_scores_kernel(const float* __restrict__ P, int64_t n, int64_t s, int64_t ld, const float* __restrict__ meanf,
-                  const float* __restrict__ V, int r, float* __restrict__ Y, int64_t ldy) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp0; i < n; i += nwarp) {
-        const float* __restrict__ row = P + i * ld;
-        for (int c0 = 0; c0 < r; c0 += RB) {
-            float acc[RB];
+                  const float* __restrict__ Vt /* [s][ncpad] */, int ncpad, int r, float* __restrict__ Y, int64_t ldy) {
+    __shared__ float Zs[kScRows][kScK + 1];
+    __shared__ __align__(16) float Vs[kScK][kScComp];
+    const int row_l = threadIdx.x & 63, cgrp = threadIdx.x >> 6;
+    const int64_t i0 = (int64_t)blockIdx.x * kScRows;
+    for (int c0 = 0; c0 < r; c0 += kScComp) {
+        float acc[8];
 #pragma unroll
-            for (int c = 0; c < RB; ++c) acc[c] = 0.f;
-            for (int64_t g = lane; g < s; g += 32) {
-                const float z = __ldg(row + g) - __ldg(meanf + g);
-#pragma unroll
-                for (int c = 0; c < RB; ++c)
-                    if (c0 + c < r) acc[c] = fmaf(z, __ldg(V + (int64_t)(c0 + c) * s + g), acc[c]);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int64_t g0 = 0; g0 < s; g0 += kScK) {
+            for (int e = threadIdx.x; e < kScRows * kScK; e += 256) {
+                const int rr = e >> 5, kk = e & 31;
+                const int64_t i = i0 + rr, g = g0 + kk;
+                Zs[rr][kk] = (i < n && g < s) ? __ldg(P + i * ld + g) - __ldg(meanf + g) : 0.f;
             }
-#pragma unroll
-            for (int c = 0; c < RB; ++c) {
-                const float t = warp_sum(acc[c]);
-                if (lane == 0 && c0 + c < r) Y[i * ldy + c0 + c] = t;
+            for (int e = threadIdx.x; e < kScK * kScComp; e += 256) {
+                const int kk = e >> 5, c = e & 31;
+                const int64_t g = g0 + kk;
+                Vs[kk][c] = (g < s && c0 + c < ncpad) ? __ldg(Vt + g * ncpad + c0 + c) : 0.f;
             }
+            __syncthreads();
+#pragma unroll 8
+            for (int k = 0; k < kScK; ++k) {
+                const float z = Zs[row_l][k];
+                const float4 v0 = *reinterpret_cast<const float4*>(&Vs[k][cgrp * 8]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&Vs[k][cgrp * 8 + 4]);
+                acc[0] = fmaf(z, v0.x, acc[0]); acc[1] = fmaf(z, v0.y, acc[1]);
+                acc[2] = fmaf(z, v0.z, acc[2]); acc[3] = fmaf(z, v0.w, acc[3]);
+                acc[4] = fmaf(z, v1.x, acc[4]); acc[5] = fmaf(z, v1.y, acc[5]);
+                acc[6] = fmaf(z, v1.z, acc[6]); acc[7] = fmaf(z, v1.w, acc[7]);
+            }
+            __syncthreads();
         }
+        const int64_t i = i0 + row_l;
+        if (i < n)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + cgrp * 8 + j;
+                if (c < r) Y[i * ldy + c] = acc[j];
+            }
     }
+}
+
+// Vt[g][c] = (float) V[c][g], zero padded to ncpad components
+__global__ void transpose_v_kernel(const double* __restrict__ V, int r, int64_t s, int ncpad, float* __restrict__ Vt) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= s * ncpad) return;
+    const int64_t g = e / ncpad;
+    const int c = (int)(e % ncpad);
+    Vt[e] = c < r ? (float)V[(int64_t)c * s + g] : 0.f;
 }
 
 __global__ void f64_to_f32_kernel(const double* __restrict__ a, float* __restrict__ b, int64_t n) {
@@ -375,20 +405,21 @@ int chr_pca_scores_f32(const float* P, int64_t n, int64_t s, int64_t ld, const d
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(P && mean && V && Y && workspace, "chr_pca_scores_f32: null pointer argument");
     CHR_REQUIRE(n > 0 && s > 0 && r > 0 && ld >= s && ldy >= r, "chr_pca_scores_f32: bad shape");
-    const size_t need = round_up<size_t>((size_t)s * 4, 256) + (size_t)r * s * 4 + 256;
+    const size_t need = round_up<size_t>((size_t)s * 4, 256) + (size_t)round_up<int64_t>(r, kScComp) * s * 4 + 256;
     CHR_REQUIRE(workspace_bytes >= need, "chr_pca_scores_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* meanf = (float*)ws;
-    float* Vf = (float*)(ws + round_up<size_t>((size_t)s * 4, 256));
+    float* Vt = (float*)(ws + round_up<size_t>((size_t)s * 4, 256));
+    const int ncpad = (int)round_up<int64_t>(r, kScComp);
     f64_to_f32_kernel<<<(unsigned)ceil_div<int64_t>(s, 256), 256, 0, st>>>(mean, meanf, s);
-    f64_to_f32_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)r * s, 256), 256, 0, st>>>(V, Vf, (int64_t)r * s);
-    pca_scores_kernel<16><<<kNumSMs * 8, 256, 0, st>>>(P, n, s, ld, meanf, Vf, r, Y, ldy);
+    transpose_v_kernel<<<(unsigned)ceil_div<int64_t>(s * ncpad, 256), 256, 0, st>>>(V, r, s, ncpad, Vt);
+    pca_scores_kernel<<<(unsigned)ceil_div<int64_t>(n, kScRows), 256, 0, st>>>(P, n, s, ld, meanf, Vt, ncpad, r, Y, ldy);
     CHR_LAUNCH_CHECK();
     return 0;
 }
 
 size_t chr_pca_scores_workspace_bytes(int64_t s, int r) {
-    return chr::round_up<size_t>((size_t)(s > 0 ? s : 1) * 4, 256) + (size_t)(r > 0 ? r : 1) * (size_t)(s > 0 ? s : 1) * 4 + 512;
+    return chr::round_up<size_t>((size_t)(s > 0 ? s : 1) * 4, 256) + (size_t)chr::round_up<int64_t>(r > 0 ? r : 1, 32) * (size_t)(s > 0 ? s : 1) * 4 + 512;
 }
 
 }  // extern "C"

@@ -292,6 +292,20 @@ def pca_scores(P: torch.Tensor, s: int, mean: torch.Tensor, V: torch.Tensor) -> 
 AA_PENALTY_M = 200.0   # weight of the sum-to-one row in the penalised NNLS problems (archetypes 0.4.x)
 
 
+def aa_furthest_sum(X: torch.Tensor, n_archetypes: int, first: int) -> np.ndarray:
+    """FurthestSum seeding on the device: indices (int64 [n_archetypes]) of the initial archetypes."""
+    import ctypes
+
+    assert X.dtype == torch.float64 and X.is_contiguous() and X.dim() == 2
+    n, d = X.shape
+    ws_bytes = _lib.query("chr_aa_furthest_sum_workspace_bytes", n)
+    ws = _workspace(ws_bytes, X.device)
+    rows = (ctypes.c_int64 * n_archetypes)()
+    _lib.call("chr_aa_furthest_sum", _ptr(X), n, d, n_archetypes, int(first), ctypes.addressof(rows), _ptr(ws), ws_bytes,
+              _stream())
+    return np.array(list(rows), dtype=np.int64)
+
+
 class AAState:
     """Device buffers of one AA restart: data X [n, d] float64, archetypes Z, coefficients alphas."""
 

@@ -155,6 +155,13 @@ size_t chr_aa_workspace_bytes(int64_t n, int d, int n_archetypes);
 /* Z[a] = X[rows[a]]  (one-hot betas0: the initial archetypes are data points); rows: device int64 */
 int chr_aa_init_archetypes(const double* X, int64_t n, int d, const int64_t* rows, int n_archetypes,
                            double* Z, chr_stream_t stream);
+/* FurthestSum seeding (the initialisation archetypes 0.4.x draws): from the random start `first`
+ * greedily pick the point with the largest summed distance to the chosen set, then 10 re-pick
+ * rounds.  rows_out: HOST int64[n_archetypes].  Synchronises the stream once per pick. */
+size_t chr_aa_furthest_sum_workspace_bytes(int64_t n);
+int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int64_t first,
+                        int64_t* rows_out, void* workspace, size_t workspace_bytes,
+                        chr_stream_t stream);
 /* one iteration, in place:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);
  * Z <- betas X;  *rss_out (device) = ||X - alphas Z||_F^2.  beta_passes_out: HOST int (may be
  * NULL), number of active-set passes of the beta step.  Synchronises the stream (the beta

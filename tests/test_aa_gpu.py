@@ -96,3 +96,14 @@ def test_aa_drop_in_fields():
     ad.obsm["other"] = scores * 2.0
     ch.aa(ad, n_archetypes=a, pca_key="other", max_iter=5)
     assert ad.uns["chr_aa"]["archetypes"].shape == (a, a - 1)
+
+
+@pytest.mark.parametrize("n,d,a", [(500, 7, 3), (5000, 20, 8), (20000, 12, 15)])
+def test_device_furthest_sum_matches_host_statement(n, d, a):
+    X = np.random.default_rng(n).normal(size=(n, d))
+    rs = np.random.RandomState(42)
+    ref = oaa.furthest_sum(X, a, rs)
+    first = int(np.random.RandomState(42).randint(n))
+    got = dv.aa_furthest_sum(dv.to_device(X, torch.float64), a, first)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got, core._furthest_sum(X, a, np.random.RandomState(42)))
