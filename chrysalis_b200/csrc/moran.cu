@@ -229,20 +229,23 @@ moran_stream_kernel(const float* __restrict__ X, int64_t n, uint32_t row_bytes, 
 // =============================================================================================
 // tile kernel (default): 128-spot x 128-gene tiles staged in shared memory + the quad plan of W
 // =============================================================================================
-// The 16 warps of a CTA are symmetric.  For every tile c of its spot range a warp
-//   1. waits until stage (c + 2) % 3 has been released by every warp (tile c - 1 consumed),
-//      then issues its share of tile c + 2: 8 rows by cp.async (one coalesced 512-byte segment
-//      per warp instruction, zero fill outside the matrix) and 1/16 of the tile's plan slice;
-//      the copies arrive on the stage's "full" mbarrier when they land - nothing waits on them
-//   2. waits for tile c's "full" barrier and walks its 2 quads out of shared memory
-//   3. arrives on tile c's "empty" barrier.
-// Two tiles (128 KB) are always in flight per SM and there is no CTA-wide barrier in the loop.
+// A CTA has 14 compute warps and 2 producer warps.  For every tile c of the CTA's spot range
+//   * a producer warp waits until stage c % 3 has been released by all compute warps (tile c - 3
+//     consumed), then issues its half of tile c right away: 56 rows by cp.async (one coalesced
+//     512-byte segment per warp instruction, zero fill outside the matrix) and half of the tile's
+//     plan slice; the copies arrive on the stage's "full" mbarrier when they land
+//   * a compute warp waits for tile c's "full" barrier, walks its 2 quads out of shared memory and
+//     arrives on tile c's "empty" barrier.
+// Two tiles are always in flight per SM, the loads of a tile start the moment its stage is free
+// (not when some compute warp gets round to it), and there is no CTA-wide barrier in the loop.
 // (A TMA tensor-map producer was measured first: with 512-byte box rows it delivered a tile too
-//  slowly to keep 16 warps fed - profiles/r1n; plain 512-byte LDG streams reach 7.3 TB/s.)
-constexpr int kTileWarps = 16;
-constexpr int kTileThreads = 32 * kTileWarps;
+//  slowly to keep the compute warps fed - gpurun_out r1k/r1n; plain 512-byte LDG streams reach 7.3 TB/s.)
+constexpr int kTileWarps = 14;                                   // compute warps
+constexpr int kTileProducers = 2;                                // producer warps (warps 14, 15)
+constexpr int kTileThreads = 32 * (kTileWarps + kTileProducers);
 constexpr int kTileQuadsPerWarp = kTileQuads / kTileWarps;       // 2
-constexpr int kTileRowsPerWarp = kTileSpots / kTileWarps;        // 8 rows of every tile are fetched by each warp
+constexpr int kTileRowsPerProducer = kTileSpots / kTileProducers;   // 56 rows of every tile are fetched by each producer warp
+static_assert(kTileQuads == kTileWarps * kTileQuadsPerWarp, "a tile is 2 quads per compute warp");
 constexpr int kTileBytes = kTileSpots * kGeneTile * 4;           // 64 KB
 constexpr int kTileMaxStages = 3;                                // 3 stages: two tiles in flight while one is consumed
 constexpr int kTileOffBytes = 256;                               // 36 ints of the record-offset table per tile
@@ -339,7 +342,7 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(kTileThreads) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(32 * kTileProducers) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(kTileWarps) : "memory");
         }
         mbar_fence_init();
@@ -352,26 +355,43 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
     const char* __restrict__ base = reinterpret_cast<const char*>(X + col);
     const int col_bytes = col_ok ? 16 : 0;
 
-    // this thread's share of tile c (local index) -> stage s
-    auto issue_tile = [&](int c, int s) {
-        const uint32_t st = smem0 + s * stage_bytes;
-        const int t = t_begin + c;
-        const int row0 = t * kTileSpots + warp * kTileRowsPerWarp;
-        const uint32_t dst = st + (uint32_t)(warp * kTileRowsPerWarp) * (kGeneTile * 4) + lane * 16;
-#pragma unroll
-        for (int r = 0; r < kTileRowsPerWarp; ++r) {
-            const int row = row0 + r;
-            const bool ok = row < n;
-            cp_async_16_zfill(dst + r * (kGeneTile * 4), base + (uint64_t)(uint32_t)(ok ? row : 0) * row_bytes, ok ? col_bytes : 0);
+    if (warp >= kTileWarps) {
+        // ===== producer warps: stream the tiles and their plan slices, two tiles ahead of the compute warps =====
+        const int pw = warp - kTileWarps;
+        const char* src = base + (uint64_t)(uint32_t)(t_begin * kTileSpots + pw * kTileRowsPerProducer) * row_bytes;
+        const uint64_t tile_stride = (uint64_t)kTileSpots * row_bytes;
+        const uint32_t dst_lane = (uint32_t)(pw * kTileRowsPerProducer) * (kGeneTile * 4) + lane * 16;
+        int avail = n - (t_begin * kTileSpots + pw * kTileRowsPerProducer);      // valid rows from this warp's first row on
+        int u_start = __ldg(plan_off + t_begin * kTileQuads);
+        int sidx = 0;
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int c = 0; c < my_tiles; ++c) {
+            const int q1 = (t_begin + c + 1) * kTileQuads;
+            const int u_end = __ldg(plan_off + (q1 < nquads ? q1 : nquads));
+            if (c >= nstages) mbar_wait_u32(empty_bar + 8 * sidx, phase ^ 1u);     // tile c - nstages released by every compute warp
+            const uint32_t st = smem0 + sidx * stage_bytes;
+            if (avail >= kTileRowsPerProducer) {
+#pragma unroll 8
+                for (int r = 0; r < kTileRowsPerProducer; ++r)
+                    cp_async_16_zfill(st + dst_lane + r * (kGeneTile * 4), src + (uint64_t)r * row_bytes, col_bytes);
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < kTileRowsPerProducer; ++r)
+                    cp_async_16_zfill(st + dst_lane + r * (kGeneTile * 4), r < avail ? src + (uint64_t)r * row_bytes : base, r < avail ? col_bytes : 0);
+            }
+            const int q0 = (t_begin + c) * kTileQuads;
+            const int pt = pw * 32 + lane;                                        // 0 .. 63 over both producer warps
+            if (pt < 9) cp_async_16_zfill(st + kTileBytes + pt * 16, plan_off + q0 + pt * 4, 16);
+            for (int u = pt; u < u_end - u_start; u += 32 * kTileProducers)
+                cp_async_16_zfill(st + kTileBytes + kTileOffBytes + u * 16, plan_rec + u_start + u, 16);
+            cp_async_mbar_arrive(full_bar + 8 * sidx);
+            u_start = u_end;
+            src += tile_stride;
+            avail -= kTileSpots;
+            if (++sidx == nstages) { sidx = 0; phase ^= 1u; }
         }
-        const int q0 = t * kTileQuads;
-        const int nq = nquads - q0 < kTileQuads ? nquads - q0 : kTileQuads;
-        const int u0 = __ldg(plan_off + q0), u1 = __ldg(plan_off + q0 + nq);
-        if (threadIdx.x < 9) cp_async_16_zfill(st + kTileBytes + threadIdx.x * 16, plan_off + q0 + threadIdx.x * 4, 16);
-        for (int u = threadIdx.x; u < u1 - u0; u += kTileThreads)
-            cp_async_16_zfill(st + kTileBytes + kTileOffBytes + u * 16, plan_rec + u0 + u, 16);
-        cp_async_mbar_arrive(full_bar + 8 * s);
-    };
+    }
 
     Row4 p;
     p.a = p.b = f2_pack(0.f, 0.f);
@@ -388,14 +408,12 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
 #pragma unroll
     for (int t = 0; t < 4; ++t) va[t].a = va[t].b = vg[t].a = vg[t].b = z2;
 
-    for (int c = 0; c < nstages - 1 && c < my_tiles; ++c) issue_tile(c, c);
-
-    // stage / phase of the tile being consumed (c) and of the tile that was consumed last (c - 1), kept
-    // incrementally: no division in the loop
-    int sidx = 0, prev_sidx = nstages - 1;
-    uint32_t phase = 0, prev_phase = 0;
+    // stage / phase of the tile being consumed, kept incrementally: no division in the loop
+    int sidx = 0;
+    uint32_t phase = 0;
+    const int my_compute_tiles = warp < kTileWarps ? my_tiles : 0;
 #pragma unroll 1
-    for (int c = 0; c < my_tiles; ++c) {
+    for (int c = 0; c < my_compute_tiles; ++c) {
         mbar_wait_u32(full_bar + 8 * sidx, phase);
         const uint32_t st = smem0 + sidx * stage_bytes;
         const uint32_t tile_lane = st + lane * 16;
@@ -497,13 +515,6 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
         // this warp is done with the stage
         __syncwarp();
         if (lane == 0) mbar_arrive_u32(empty_bar + 8 * sidx);
-        // tile c + nstages - 1 goes into the stage tile c - 1 occupied: by now every warp has usually released it
-        if (c + nstages - 1 < my_tiles) {
-            if (c > 0) mbar_wait_u32(empty_bar + 8 * prev_sidx, prev_phase);
-            issue_tile(c + nstages - 1, prev_sidx);
-        }
-        prev_sidx = sidx;
-        prev_phase = phase;
         if (++sidx == nstages) { sidx = 0; phase ^= 1; }
         // level-1 (16 spots: two tiles of this warp) -> level-2
         if (c & 1) {
@@ -522,13 +533,15 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
     double* red = reinterpret_cast<double*>(smem_dyn + (smem0 - smem_u32(smem_dyn)));   // [kTileWarps][kGeneTile]
 #pragma unroll
     for (int stt = 0; stt < NST; ++stt) {
-        float f0, f1, f2, f3;
-        f2_unpack(l2[stt].a, f0, f1);
-        f2_unpack(l2[stt].b, f2, f3);
-        red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
-        red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
-        red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
-        red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
+        if (warp < kTileWarps) {
+            float f0, f1, f2, f3;
+            f2_unpack(l2[stt].a, f0, f1);
+            f2_unpack(l2[stt].b, f2, f3);
+            red[warp * kGeneTile + lane * 4 + 0] = (double)f0;
+            red[warp * kGeneTile + lane * 4 + 1] = (double)f1;
+            red[warp * kGeneTile + lane * 4 + 2] = (double)f2;
+            red[warp * kGeneTile + lane * 4 + 3] = (double)f3;
+        }
         __syncthreads();
         if (threadIdx.x < kGeneTile) {
             double t = 0.0;

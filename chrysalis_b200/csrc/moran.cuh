@@ -6,7 +6,7 @@ namespace chr {
 
 constexpr int kGeneTile = 128;    // genes per CTA = 32 lanes x float4 (one 512-byte row slab)
 constexpr int kNStat = 5;         // S1, S2, SW, SC, S5 (Geary)
-constexpr int kTileSpots = 128;   // spots per staged tile = 32 quads (aligned: tile t = spots [128 t, 128 t + 128))
+constexpr int kTileSpots = 112;   // spots per staged tile = 28 quads = 2 per compute warp (tile t = spots [112 t, 112 t + 112))
 constexpr int kTileQuads = kTileSpots / 4;
 
 // ---- quad plan of W (see moran_plan.cu) -------------------------------------------------------

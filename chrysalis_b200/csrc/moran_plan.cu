@@ -13,7 +13,7 @@
 //     list.  Pairs only one endpoint lists stay with it; mutual pairs start with a hash-chosen
 //     owner and are moved by a few Jacobi sweeps so that the 4 lists of a quad get nearly equal
 //     length R: the kernel walks a quad in R rounds of 4 rows.
-//   * list entries are split into rows inside the quad's 128-spot tile (served from the tile the
+//   * list entries are split into rows inside the quad's 112-spot tile (served from the tile the
 //     kernel stages in shared memory) and rows outside it (global loads): R = R_loc + R_glob.
 // On a square lattice with k = 8 a spot reads ~2.9 list rows instead of 8.  Any list is legal
 // (duplicates, self loops, asymmetric kNN): coefficients are multiplicities.  k <= 64 (one
