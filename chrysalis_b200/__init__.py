@@ -3,8 +3,8 @@
 Re-exports mirror ``/root/reference/chrysalis/__init__.py:10-12`` for the path this package
 replaces; everything else of the reference (plots, utils) is out of scope.
 """
-from .core import aa, detect_svgs, pca
+from .core import aa, detect_svgs, morans_i_permutation, pca
 from .anndata_lite import AnnDataLite
 
-__all__ = ["detect_svgs", "pca", "aa", "AnnDataLite"]
+__all__ = ["detect_svgs", "pca", "aa", "morans_i_permutation", "AnnDataLite"]
 __version__ = "0.1.0"

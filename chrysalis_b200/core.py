@@ -39,7 +39,7 @@ def _make_unique(names) -> pd.Index:
 
 
 def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False,
-              shard: bool = True):
+              shard: bool = True, permutations: int = 0, seed: int | None = None):
     """Device part of ``detect_svgs``: filter -> normalise/log1p -> kNN W -> Moran's I.
 
     Returns host arrays ``(keep_mask (G,), I (G',), C (G',) or None)``; also usable directly
@@ -50,6 +50,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     ``normalize_total`` are all-reduced, W is built on every rank, Moran's I needs no exchange,
     and the per-gene results are all-gathered so every rank returns the full arrays.
     ``shard=False`` keeps the call local to this rank (every rank works on its own matrix).
+    ``permutations=P > 0`` (esda's ``Moran(..., permutations=P)``) appends a dict of the simulated
+    quantities (p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim; host arrays over the scored genes).
     """
     n, g_all = X.shape
     rank, size = dd.world() if shard else (0, 1)
@@ -85,12 +87,18 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p)
         # core.py:71-76  the gene loop
         I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
+        sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None
     else:
         I = torch.empty(0, dtype=torch.float64, device=keep.device)
         C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None
+        sim = {k: torch.empty(0, dtype=torch.float64, device=keep.device)
+               for k in ("p_sim", "EI_sim", "VI_sim", "seI_sim", "z_sim", "p_z_sim")} if permutations else None
     I = gather(I)
     C = gather(C) if geary else None
-    return keep_all.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None)
+    out = (keep_all.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None))
+    if permutations:
+        out += ({k: gather(v).cpu().numpy() for k, v in sim.items() if k != "I"},)
+    return out
 
 
 def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
@@ -132,6 +140,24 @@ def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans:
     else:
         chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
     adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]
+
+
+def morans_i_permutation(adata, min_spots: float = 0.05, neighbors: int = 6, permutations: int = 999, seed: int | None = None):
+    """
+    Moran's I with permutation inference for every gene: what ``esda.moran.Moran(y, w, permutations=P)``
+    reports per gene (the reference's ``detect_svgs`` hard-codes ``permutations=0`` at core.py:72; the
+    authors call esda directly for this, ``article/A2_human_lymph_node/morans_i.ipynb:186``).
+
+    Same gene filter, normalisation and W as ``detect_svgs``.  Updates ``.var`` with ``"Moran's I"``,
+    ``"Moran's I p_sim"``, ``"Moran's I z_sim"``, ``"Moran's I EI_sim"``, ``"Moran's I VI_sim"`` (NaN for filtered genes).
+    """
+    assert 0 < min_spots < 1
+    keep, I, _, sim = svg_stage(adata.X, adata.obsm['spatial'], min_spots, neighbors, False,
+                                already_log1p="log1p" in adata.uns_keys(), permutations=int(permutations), seed=seed)
+    names = _make_unique(pd.Index(adata.var_names)[keep])
+    adata.var["Moran's I"] = pd.Series(I, index=names)
+    for key in ("p_sim", "z_sim", "EI_sim", "VI_sim"):
+        adata.var[f"Moran's I {key}"] = pd.Series(sim[key], index=names)
 
 
 def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):

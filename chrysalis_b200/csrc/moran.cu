@@ -321,10 +321,11 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <bool GEARY, bool SHIFT>
+// MAPPED: spot i reads row row_map[i] of X (permutation inference: z is permuted, W stays)
+template <bool GEARY, bool SHIFT, bool MAPPED>
 __global__ void __launch_bounds__(kTileThreads, 1)
-moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int ncol, const int32_t* __restrict__ plan_off,
-                  const int4* __restrict__ plan_rec, int buf_units, int nstages, int tiles_per_cta,
+moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int ncol, const int32_t* __restrict__ row_map,
+                  const int32_t* __restrict__ plan_off, const int4* __restrict__ plan_rec, int buf_units, int nstages, int tiles_per_cta,
                   const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
     constexpr int NST = GEARY ? 5 : 4;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -358,7 +359,8 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
     if (warp >= kTileWarps) {
         // ===== producer warps: stream the tiles and their plan slices, two tiles ahead of the compute warps =====
         const int pw = warp - kTileWarps;
-        const char* src = base + (uint64_t)(uint32_t)(t_begin * kTileSpots + pw * kTileRowsPerProducer) * row_bytes;
+        int row0 = t_begin * kTileSpots + pw * kTileRowsPerProducer;            // first spot this warp fetches of the tile
+        const char* src = base + (uint64_t)(uint32_t)row0 * row_bytes;
         const uint64_t tile_stride = (uint64_t)kTileSpots * row_bytes;
         const uint32_t dst_lane = (uint32_t)(pw * kTileRowsPerProducer) * (kGeneTile * 4) + lane * 16;
         int avail = n - (t_begin * kTileSpots + pw * kTileRowsPerProducer);      // valid rows from this warp's first row on
@@ -371,7 +373,16 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             const int u_end = __ldg(plan_off + (q1 < nquads ? q1 : nquads));
             if (c >= nstages) mbar_wait_u32(empty_bar + 8 * sidx, phase ^ 1u);     // tile c - nstages released by every compute warp
             const uint32_t st = smem0 + sidx * stage_bytes;
-            if (avail >= kTileRowsPerProducer) {
+            if (MAPPED) {
+                // source rows through the map: two coalesced loads cover the warp's 56 rows, then warp shuffles
+                const int m0 = row0 + lane < n ? __ldg(row_map + row0 + lane) : 0;
+                const int m1 = row0 + 32 + lane < n ? __ldg(row_map + row0 + 32 + lane) : 0;
+#pragma unroll 8
+                for (int r = 0; r < kTileRowsPerProducer; ++r) {
+                    const int mr = __shfl_sync(0xffffffffu, r < 32 ? m0 : m1, r & 31);
+                    cp_async_16_zfill(st + dst_lane + r * (kGeneTile * 4), base + (uint64_t)(uint32_t)mr * row_bytes, r < avail ? col_bytes : 0);
+                }
+            } else if (avail >= kTileRowsPerProducer) {
 #pragma unroll 8
                 for (int r = 0; r < kTileRowsPerProducer; ++r)
                     cp_async_16_zfill(st + dst_lane + r * (kGeneTile * 4), src + (uint64_t)r * row_bytes, col_bytes);
@@ -388,6 +399,7 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             cp_async_mbar_arrive(full_bar + 8 * sidx);
             u_start = u_end;
             src += tile_stride;
+            row0 += kTileSpots;
             avail -= kTileSpots;
             if (++sidx == nstages) { sidx = 0; phase ^= 1u; }
         }
@@ -441,7 +453,11 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             if (RG > 0) {
                 const int4 rows = lds_i4(grec);
                 const float4 cf = lds_f4(grec + 16);
-                const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                if (MAPPED) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) rr[t] = __ldg(row_map + rr[t]);
+                }
                 cg[0] = cf.x; cg[1] = cf.y; cg[2] = cf.z; cg[3] = cf.w;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cg[t]);
@@ -464,7 +480,11 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                 for (int r = 1; r < RG; ++r) {
                     const int4 rows = lds_i4(grec + 32 * r);
                     const float4 cf = lds_f4(grec + 32 * r + 16);
-                    const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                    int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                    if (MAPPED) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) rr[t] = __ldg(row_map + rr[t]);
+                    }
                     const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cc[t]);
@@ -635,8 +655,8 @@ size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsign
 }
 
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld, const int32_t* nbr, int k,
-                        const void* plan, int plan_chunk_units, unsigned flags, double* out_I, double* out_C,
-                        double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
+                        const void* plan, int plan_chunk_units, const int32_t* row_map, unsigned flags, double* out_I,
+                        double* out_C, double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
     using namespace chr;
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(n_spots > 1 && n_genes > 0, "chr_moran_dense_f32: need n_spots > 1 and n_genes > 0 (got %lld, %lld)",
@@ -663,6 +683,7 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     if (tile && tile_smem(nstages) > 227 * 1024) nstages = 2;
     if (tile && tile_smem(nstages) > 227 * 1024 && nbr) tile = false;
     CHR_REQUIRE(tile || nbr, "chr_moran_dense_f32: the stream kernel needs the neighbour lists");
+    CHR_REQUIRE(tile || !row_map, "chr_moran_dense_f32: row_map (permutation inference) needs the plan-based tile kernel");
     MoranWs p = moran_ws(n_spots, ncol, tile);
     CHR_REQUIRE(workspace_bytes >= p.total, "chr_moran_dense_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -687,16 +708,21 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
         timer_begin(CHR_FAMILY_MORAN, timing, st);
 #define CHR_TILE(GG, SH)                                                                                            \
     do {                                                                                                            \
-        auto kern = moran_tile_kernel<GG, SH>;                                                                     \
+        if (row_map) CHR_TILE_M(GG, SH, true); else CHR_TILE_M(GG, SH, false);                                     \
+    } while (0)
+#define CHR_TILE_M(GG, SH, MP)                                                                                      \
+    do {                                                                                                            \
+        auto kern = moran_tile_kernel<GG, SH, MP>;                                                                 \
         CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_spots, rb, (int)ncol, plan_off, plan_rec, plan_chunk_units, nstages, tpc, pilot, part, \
-                                               p.gpad);                                                            \
+        kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_spots, rb, (int)ncol, row_map, plan_off, plan_rec, plan_chunk_units, nstages, \
+                                               tpc, pilot, part, p.gpad);                                          \
     } while (0)
         if (geary && preshifted) CHR_TILE(true, false);
         else if (geary) CHR_TILE(true, true);
         else if (preshifted) CHR_TILE(false, false);
         else CHR_TILE(false, true);
 #undef CHR_TILE
+#undef CHR_TILE_M
     } else {
         const int vec16 = (k % 4 == 0) && (((uintptr_t)nbr & 15) == 0);
         size_t smem = (size_t)2 * kV2Chunk * k * sizeof(int32_t);

@@ -191,14 +191,16 @@ def moran_plan(nbr: torch.Tensor) -> MoranPlan | None:
 
 def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, geary: bool = False,
                 timing: bool = False, want_stats: bool = False, variant: int | None = None, preshifted: bool = False,
-                plan: MoranPlan | None = None):
+                plan: MoranPlan | None = None, row_map: torch.Tensor | None = None):
     """Moran's I (and Geary's C) of every column of the dense [n, ld] float32 matrix ``X``.
 
     Returns ``(I, C, stats)`` float64 device tensors (``C``/``stats`` None unless requested).
     ``plan``: the quad plan of ``nbr`` (built here when not given; reuse it across calls with the same W).
     ``preshifted``: the columns of ``X`` already have (near-)zero mean, skip the in-kernel shift.
+    ``row_map``: int32 [n]: spot i takes row ``row_map[i]`` of ``X`` (one permutation draw, see ``moran_permutation_test``).
     """
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1
+    assert row_map is None or (row_map.dtype == torch.int32 and row_map.is_contiguous() and row_map.numel() == X.shape[0])
     assert nbr.dtype == torch.int32 and nbr.is_contiguous()
     n, k = nbr.shape
     assert X.shape[0] == n
@@ -216,9 +218,47 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     out_C = torch.empty(g, dtype=torch.float64, device=X.device) if geary else None
     stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
     _lib.call("chr_moran_dense_f32", _ptr(X), n, g, ld, _ptr(nbr), k, _ptr(plan.buf) if plan is not None else 0,
-              plan.chunk_units if plan is not None else 0, flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
+              plan.chunk_units if plan is not None else 0, _ptr(row_map), flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
               _ptr(ws), ws_bytes, _stream())
     return out_I, out_C, stats
+
+
+def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, permutations: int = 999,
+                           seed: int | None = None, plan: MoranPlan | None = None):
+    """Permutation inference of ``esda.moran.Moran(y, w, permutations=P)`` for every column of ``X``.
+
+    Each draw permutes the spots (rows) against a fixed W and is ONE pass of the Moran kernel over the
+    whole matrix (``row_map``), so a draw is shared by all genes; esda draws per gene from NumPy's global
+    RNG, so parity of the simulated quantities is statistical, parity of ``I`` exact.
+    Returns a dict of float64 device tensors [g]: I, p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim.
+    """
+    n = X.shape[0]
+    g = X.shape[1] if n_genes is None else n_genes
+    if plan is None:
+        plan = moran_plan(nbr)
+    if plan is None:
+        raise _lib.ChrysalisNativeError("permutation inference needs the plan-based kernel (k <= 64)")
+    I, _, _ = moran_dense(X, nbr, g, plan=plan)
+    gen = torch.Generator(device=X.device)
+    gen.manual_seed(int(torch.seed() if seed is None else seed))
+    larger = torch.zeros(g, dtype=torch.int64, device=X.device)
+    s1 = torch.zeros(g, dtype=torch.float64, device=X.device)
+    s2 = torch.zeros(g, dtype=torch.float64, device=X.device)
+    for _ in range(int(permutations)):
+        perm = torch.randperm(n, device=X.device, generator=gen).to(torch.int32)
+        Ip, _, _ = moran_dense(X, nbr, g, plan=plan, row_map=perm)
+        larger += (Ip >= I)
+        s1 += Ip
+        s2 += Ip * Ip
+    P = float(permutations)
+    larger = torch.minimum(larger, int(permutations) - larger)                 # esda: two-sided fold
+    ei = s1 / P
+    vi = (s2 / P - ei * ei).clamp_min(0.0)
+    se = vi.sqrt()
+    z = (I - ei) / se
+    p_z = 0.5 * torch.erfc(z.abs() / 2.0 ** 0.5)                               # 1 - Phi(|z|)
+    return {"I": I, "p_sim": (larger.to(torch.float64) + 1.0) / (P + 1.0), "EI_sim": ei, "VI_sim": vi, "seI_sim": se,
+            "z_sim": z, "p_z_sim": p_z}
 
 
 def last_kernel_ms(family: int = _lib.FAMILY_MORAN) -> float:

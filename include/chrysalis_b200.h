@@ -103,14 +103,18 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
  *    list), plan + plan_chunk_units: chr_moran_plan_build's output for the same nbr.
  *    With a plan the TMA tile kernel runs (nbr may be NULL); without one (plan NULL, any k) the
  *    per-spot stream kernel runs from nbr.
+ * row_map: NULL, or int32 [n_spots]: spot i takes row row_map[i] of X while W stays in place.  One
+ *    call with a random permutation is one draw of esda's permutation inference
+ *    (esda.moran.Moran(..., permutations=P): I of np.random.permutation(z)) for every gene at once.
  * out_I / out_C: [n_genes] float64 (out_C may be NULL without CHR_FLAG_GEARY).
  * out_stats: optional [4][n_genes] float64 = {mean, z'z, z'Wz, geary numerator}.
  * One pass over X; per-gene accumulators fp32 over <= 8/16 spots, fp32 per CTA, then fp64. */
 size_t chr_moran_workspace_bytes(int64_t n_spots, int64_t n_genes, int k, unsigned flags);
 int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_t ld,
                         const int32_t* nbr, int k, const void* plan, int plan_chunk_units,
-                        unsigned flags, double* out_I, double* out_C, double* out_stats,
-                        void* workspace, size_t workspace_bytes, chr_stream_t stream);
+                        const int32_t* row_map, unsigned flags, double* out_I, double* out_C,
+                        double* out_stats, void* workspace, size_t workspace_bytes,
+                        chr_stream_t stream);
 
 /* ---- K6-K8: PCA of the SVG matrix ------------------------------------------------------
  * replaces  PCA(n_components=n_pcs, svd_solver='arpack', random_state=42).fit_transform(pcs)

@@ -49,7 +49,7 @@ def test_workspace_queries_need_no_gpu(lib):
 
 def test_argument_validation_precedes_any_cuda_call(lib):
     # null / inconsistent arguments are rejected with a message before touching the device
-    rc = lib.chr_moran_dense_f32(None, 100, 10, 10, None, 6, None, 0, 0, None, None, None, None, 0, None)
+    rc = lib.chr_moran_dense_f32(None, 100, 10, 10, None, 6, None, 0, None, 0, None, None, None, None, 0, None)
     assert rc != 0 and b"chr_moran_dense_f32" in lib.chr_last_error()
     rc = lib.chr_knn_build(None, 10, 3, None, None, None, 0, None)
     assert rc != 0 and b"chr_knn_build" in lib.chr_last_error()
