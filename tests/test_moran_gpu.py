@@ -319,7 +319,8 @@ def test_permutation_inference_matches_esda_semantics():
     ei = np.array([a["EI"] for a in an]); vi = np.array([a["VI_rand"] for a in an])
     se_mean = np.sqrt(vi / P)
     assert (np.abs(res["EI_sim"] - ei) < 5 * se_mean).all()
-    assert (np.abs(res["VI_sim"] / vi - 1.0) < 0.35).all()              # chi-square spread of a 499-draw variance, 5 sigma
+    ratio = res["VI_sim"] / vi                                          # a 499-draw variance: ~6 % sd, more for sparse (kurtotic) genes
+    assert abs(np.median(ratio) - 1.0) < 0.05 and (np.abs(ratio - 1.0) < 0.6).all()
     # same decisions as the reference-style simulation: strong genes get the minimum p, z-scores agree
     ref_p = np.array([r["p_sim"] for r in ref]); ref_z = np.array([r["z_sim"] for r in ref])
     strong = ref_z > 6
