@@ -53,35 +53,38 @@ __device__ bool chol_solve_subset(const double* __restrict__ full, int ld, const
 }
 
 // Lawson-Hanson NNLS on normal equations  min 1/2 a'Ga - c'a, a >= 0  (G: na x na, ld = na).
-// x: out (na).  Scratch arrays sized by the caller.  Ties in the arg-max go to the lowest index.
+// x: in/out (na).  warm: x holds a feasible starting point (the previous iteration's coefficients); its
+// support seeds the passive set, which usually is already the optimal one - the minimiser is unique (G is
+// positive definite), so the result does not depend on the starting point.  Ties in the arg-max go to the
+// lowest index.
 template <int MAXA>
-__device__ void nnls_normal(const double* __restrict__ G, const double* c, int na, double* x) {
+__device__ void nnls_normal(const double* __restrict__ G, const double* c, int na, double* x, bool warm) {
     int pidx[MAXA];
     double s[MAXA], w[MAXA], L[MAXA * (MAXA + 1) / 2];
     bool inP[MAXA];
     int np = 0;
     double cmax = 0.0;
-    for (int j = 0; j < na; ++j) { x[j] = 0.0; inP[j] = false; w[j] = c[j]; cmax = fmax(cmax, fabs(c[j])); }
+    for (int j = 0; j < na; ++j) {
+        inP[j] = warm && x[j] > 0.0;
+        if (inP[j]) pidx[np++] = j; else x[j] = 0.0;
+        cmax = fmax(cmax, fabs(c[j]));
+    }
     const double tol = 1e-12 * fmax(cmax, 1e-300);
-    for (int outer = 0; outer < 3 * na; ++outer) {
-        int jbest = -1;
-        double wbest = tol;
-        for (int j = 0; j < na; ++j)
-            if (!inP[j] && w[j] > wbest) { wbest = w[j]; jbest = j; }
-        if (jbest < 0) break;
-        inP[jbest] = true;
-        pidx[np++] = jbest;
-        for (int inner = 0; inner < 3 * na; ++inner) {
-            if (!chol_solve_subset(G, na, pidx, np, c, L, s)) {   // numerically dependent column: drop it again
+    // least squares on the passive set, stepping back to the feasible region while a coefficient turns non-positive
+    auto settle = [&](bool added) {
+        for (int inner = 0; inner < 3 * na && np > 0; ++inner) {
+            if (!chol_solve_subset(G, na, pidx, np, c, L, s)) {   // numerically dependent column: drop the newest
                 inP[pidx[np - 1]] = false;
+                x[pidx[np - 1]] = 0.0;
                 --np;
-                break;
+                if (added) return;
+                continue;
             }
             double smin = 1e300;
             for (int i = 0; i < np; ++i) smin = fmin(smin, s[i]);
             if (smin > 0.0) {
                 for (int i = 0; i < np; ++i) x[pidx[i]] = s[i];
-                break;
+                return;
             }
             double alpha = 1e300;
             for (int i = 0; i < np; ++i)
@@ -93,13 +96,23 @@ __device__ void nnls_normal(const double* __restrict__ G, const double* c, int n
                 else pidx[q++] = pidx[i];
             }
             np = q;
-            if (np == 0) break;
         }
+    };
+    if (np > 0) settle(false);
+    for (int outer = 0; outer < 3 * na; ++outer) {
         for (int j = 0; j < na; ++j) {
             double v = c[j];
             for (int i = 0; i < np; ++i) v -= G[j * na + pidx[i]] * x[pidx[i]];
             w[j] = v;
         }
+        int jbest = -1;
+        double wbest = tol;
+        for (int j = 0; j < na; ++j)
+            if (!inP[j] && w[j] > wbest) { wbest = w[j]; jbest = j; }
+        if (jbest < 0) break;
+        inP[jbest] = true;
+        pidx[np++] = jbest;
+        settle(true);
     }
 }
 
@@ -107,7 +120,7 @@ __device__ void nnls_normal(const double* __restrict__ G, const double* c, int n
 // also accumulates the CTA's partial  A^T A (na x na)  and  A^T X (na x d)  for the pinv step
 template <int MAXA>
 __global__ void __launch_bounds__(128)
-aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Z, int na, double M,
+aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Z, int na, double M, int warm,
                 double* __restrict__ alphas, double* __restrict__ part /*[grid][na*na + na*d]*/) {
     extern __shared__ double sh[];
     double* G = sh;                       // na x na
@@ -135,7 +148,9 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
             for (int t = 0; t < d; ++t) v += Zs[a * d + t] * x[t];
             c[a] = v;
         }
-        nnls_normal<MAXA>(G, c, na, a_out);
+        if (warm)
+            for (int a = 0; a < na; ++a) a_out[a] = alphas[i * na + a];
+        nnls_normal<MAXA>(G, c, na, a_out, warm != 0);
         double sum = 0.0;
         for (int a = 0; a < na; ++a) { a_out[a] = fmax(a_out[a], 0.0); sum += a_out[a]; }
         const double inv = 1.0 / sum;
@@ -299,6 +314,67 @@ aa_beta_grad_kernel(const double* __restrict__ X, int64_t n, int d, double M, co
     (void)pidx;
 }
 
+// least squares of [zhat_a, M] on the passive points P of archetype a (serial, lane 0 of its warp): steps back
+// to the feasible region while a coefficient turns non-positive, then writes the residual
+//   R[a] = [zhat_a, M] - sum_p b_p [x_p, M]
+__device__ void beta_refit(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int a, BetaState* st,
+                           int* P, double* b, double* __restrict__ R, double* scratch_a) {
+    const int dp = d + 1;
+    int np = st->np[a];
+    double* H = scratch_a;
+    double* rhs = H + kAaMaxP * kAaMaxP;
+    double* s = rhs + kAaMaxP;
+    double* L = s + kAaMaxP;
+    int ident[kAaMaxP];
+    for (int inner = 0; inner < 3 * kAaMaxP && np > 0; ++inner) {
+        for (int p = 0; p < np; ++p) {
+            const double* xp = X + (int64_t)P[p] * d;
+            for (int q = 0; q <= p; ++q) {
+                const double* xq = X + (int64_t)P[q] * d;
+                double v = M * M;
+                for (int t = 0; t < d; ++t) v += xp[t] * xq[t];
+                H[p * np + q] = v;
+                H[q * np + p] = v;
+            }
+            double v = M * M;
+            for (int t = 0; t < d; ++t) v += xp[t] * Zhat[a * d + t];
+            rhs[p] = v;
+            ident[p] = p;
+        }
+        if (!chol_solve_subset(H, np, ident, np, rhs, L, s)) { --np; st->done[a] = 1; continue; }
+        double smin = 1e300;
+        for (int p = 0; p < np; ++p) smin = fmin(smin, s[p]);
+        if (smin > 0.0) { for (int p = 0; p < np; ++p) b[p] = s[p]; break; }
+        double alpha = 1e300;
+        for (int p = 0; p < np; ++p)
+            if (s[p] <= 0.0) alpha = fmin(alpha, b[p] / (b[p] - s[p]));
+        for (int p = 0; p < np; ++p) b[p] += alpha * (s[p] - b[p]);
+        int q = 0;
+        for (int p = 0; p < np; ++p) {
+            if (b[p] <= 1e-15 && s[p] <= 0.0) continue;
+            P[q] = P[p]; b[q] = b[p]; ++q;
+        }
+        np = q;
+    }
+    st->np[a] = np;
+    for (int t = 0; t < dp; ++t) {
+        double v = t < d ? Zhat[a * d + t] : M;
+        for (int p = 0; p < np; ++p) v -= b[p] * (t < d ? X[(int64_t)P[p] * d + t] : M);
+        R[a * dp + t] = v;
+    }
+}
+
+constexpr int kAaScratchPerA = kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2;
+
+// warm start of the beta step: every archetype keeps the passive points of the previous iteration
+__global__ void aa_beta_refit_kernel(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int na,
+                                     BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef,
+                                     double* __restrict__ R, double* __restrict__ scratch) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= na) return;
+    beta_refit(X, d, M, Zhat, a, st, pidx + a * kAaMaxP, bcoef + a * kAaMaxP, R, scratch + (size_t)a * kAaScratchPerA);
+}
+
 // one warp per archetype: final arg-max, add to the passive set, Lawson-Hanson inner loop, new residual
 __global__ void __launch_bounds__(32 * 8)
 aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ Zhat, int na,
@@ -323,10 +399,9 @@ aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, 
             if (ow > bw || (ow == bw && oi >= 0 && (bi < 0 || oi < bi))) { bw = ow; bi = oi; }
         }
         if (lane == 0) {
-            const int dp = d + 1;
             int* P = pidx + a * kAaMaxP;
             double* b = bcoef + a * kAaMaxP;
-            int np = st->np[a];
+            const int np = st->np[a];
             // scale for the stopping test: |[zhat, M]| * max |[x, M]| ~ M^2
             double znorm = M * M;
             for (int t = 0; t < d; ++t) znorm += Zhat[a * d + t] * Zhat[a * d + t];
@@ -338,51 +413,8 @@ aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, 
             } else {
                 P[np] = (int)bi;
                 b[np] = 0.0;
-                ++np;
-                // scratch per archetype: H (np x np), rhs, s, L
-                double* H = scratch + (size_t)a * (kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2);
-                double* rhs = H + kAaMaxP * kAaMaxP;
-                double* s = rhs + kAaMaxP;
-                double* L = s + kAaMaxP;
-                int ident[kAaMaxP];
-                for (int inner = 0; inner < 3 * kAaMaxP; ++inner) {
-                    for (int p = 0; p < np; ++p) {
-                        const double* xp = X + (int64_t)P[p] * d;
-                        for (int q = 0; q <= p; ++q) {
-                            const double* xq = X + (int64_t)P[q] * d;
-                            double v = M * M;
-                            for (int t = 0; t < d; ++t) v += xp[t] * xq[t];
-                            H[p * np + q] = v;
-                            H[q * np + p] = v;
-                        }
-                        double v = M * M;
-                        for (int t = 0; t < d; ++t) v += xp[t] * Zhat[a * d + t];
-                        rhs[p] = v;
-                        ident[p] = p;
-                    }
-                    if (!chol_solve_subset(H, np, ident, np, rhs, L, s)) { --np; st->done[a] = 1; break; }
-                    double smin = 1e300;
-                    for (int p = 0; p < np; ++p) smin = fmin(smin, s[p]);
-                    if (smin > 0.0) { for (int p = 0; p < np; ++p) b[p] = s[p]; break; }
-                    double alpha = 1e300;
-                    for (int p = 0; p < np; ++p)
-                        if (s[p] <= 0.0) alpha = fmin(alpha, b[p] / (b[p] - s[p]));
-                    for (int p = 0; p < np; ++p) b[p] += alpha * (s[p] - b[p]);
-                    int q = 0;
-                    for (int p = 0; p < np; ++p) {
-                        if (b[p] <= 1e-15 && s[p] <= 0.0) continue;
-                        P[q] = P[p]; b[q] = b[p]; ++q;
-                    }
-                    np = q;
-                    if (np == 0) break;
-                }
-                st->np[a] = np;
-                // residual  R[a] = [zhat_a, M] - sum_p b_p [x_p, M]
-                for (int t = 0; t < dp; ++t) {
-                    double v = t < d ? Zhat[a * d + t] : M;
-                    for (int p = 0; p < np; ++p) v -= b[p] * (t < d ? X[(int64_t)P[p] * d + t] : M);
-                    R[a * dp + t] = v;
-                }
+                st->np[a] = np + 1;
+                beta_refit(X, d, M, Zhat, a, st, P, b, R, scratch + (size_t)a * kAaScratchPerA);
             }
         }
     }
@@ -398,10 +430,11 @@ __global__ void aa_beta_check_kernel(BetaState* st, int na) {
     }
 }
 
-__global__ void aa_beta_init_kernel(BetaState* st, const double* __restrict__ Zhat, int na, int d, double M, double* __restrict__ R) {
+__global__ void aa_beta_init_kernel(BetaState* st, const double* __restrict__ Zhat, int na, int d, double M, int warm,
+                                    double* __restrict__ R) {
     const int t = threadIdx.x;
     if (t == 0) { st->all_done = 0; st->iters = 0; }
-    if (t < na) { st->np[t] = 0; st->done[t] = 0; }
+    if (t < na) { if (!warm) st->np[t] = 0; st->done[t] = 0; }
     for (int e = t; e < na * (d + 1); e += blockDim.x) {
         const int a = e / (d + 1), q = e % (d + 1);
         R[e] = q < d ? Zhat[a * d + q] : M;
@@ -553,7 +586,7 @@ static AaPlan aa_plan(int64_t n, int d, int na) {
     p.off_bcoef = take((size_t)na * kAaMaxP * 8);
     p.off_candw = take((size_t)p.grad_blocks * na * 8);
     p.off_candi = take((size_t)p.grad_blocks * na * 8);
-    p.off_scr = take((size_t)na * (kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2) * 8);
+    p.off_scr = take((size_t)na * kAaScratchPerA * 8);
     p.off_rsspart = take((size_t)p.rss_blocks * 8);
     p.total = o;
     return p;
@@ -631,7 +664,7 @@ int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int
 }
 
 // one full iteration:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);  Z <- betas X;  rss
-int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, double* Z, double* alphas,
+int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, int warm, double* Z, double* alphas,
                    double* rss_out, int* beta_passes_out, void* workspace, size_t workspace_bytes, chr_stream_t stream) {
     using namespace chr;
     cudaStream_t st = (cudaStream_t)stream;
@@ -657,13 +690,13 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     timer_begin(CHR_FAMILY_AA, true, st);
     // ---- alphas
     const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc + 128 * na) * 8;
-    if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+    if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
     else if (na <= 32) {
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
-        aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+        aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
     } else {
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
-        aa_alpha_kernel<64><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, alphas, part);
+        aa_alpha_kernel<64><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
     }
     CHR_LAUNCH_CHECK();
     // ---- Zhat = pinv(alphas) X
@@ -674,13 +707,14 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part2, nred, na, d, n, Zhat);
     CHR_LAUNCH_CHECK();
     // ---- betas: active-set passes, every archetype advances one step per pass
-    aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, R);
+    aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, warm, R);
+    if (warm) aa_beta_refit_kernel<<<1, 64, 0, st>>>(X, d, penalty_M, Zhat, na, bst, pidx, bcoef, R, scr);
     const size_t sm_grad = (size_t)na * (d + 1) * 8 + 32 * 8 + 32 * 8;
     const int max_pass = 3 * (d + 2) + 8;
     int passes = 0;
     int host_done = 0;
     while (passes < max_pass && !host_done) {
-        const int batch = passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4;   // first look after a handful of passes
+        const int batch = warm ? 2 : (passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4);   // cold: first look after a handful of passes
         for (int b = 0; b < batch && passes < max_pass; ++b, ++passes) {
             aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
             aa_beta_update_kernel<<<(unsigned)ceil_div(na * 32, 256), 256, 0, st>>>(X, n, d, penalty_M, Zhat, na, p.grad_blocks, candw,

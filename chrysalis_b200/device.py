@@ -359,12 +359,14 @@ class AAState:
         self.ws_bytes = _lib.query("chr_aa_workspace_bytes", n, d, self.na)
         self.ws = _workspace(self.ws_bytes, X.device)
         self.beta_passes = 0
+        self.n_done = 0          # iterations since the last (re-)initialisation: > 0 warm-starts the active sets
 
     def init_from_rows(self, rows):
         """Z = X[rows]: one-hot betas0 (archetypes 0.4.x initialises archetypes on data points)."""
         n, d = self.X.shape
         r = torch.as_tensor(np.asarray(rows, dtype=np.int64)).to(self.X.device)
         _lib.call("chr_aa_init_archetypes", _ptr(self.X), n, d, _ptr(r), self.na, _ptr(self.Z), _stream())
+        self.n_done = 0
 
     def iterate(self) -> float:
         """One alternating-NNLS iteration in place; returns the residual sum of squares."""
@@ -372,7 +374,8 @@ class AAState:
 
         n, d = self.X.shape
         passes = ctypes.c_int(0)
-        _lib.call("chr_aa_iterate", _ptr(self.X), n, d, self.na, AA_PENALTY_M, _ptr(self.Z), _ptr(self.alphas),
-                  _ptr(self.rss), ctypes.addressof(passes), _ptr(self.ws), self.ws_bytes, _stream())
+        _lib.call("chr_aa_iterate", _ptr(self.X), n, d, self.na, AA_PENALTY_M, int(self.n_done > 0), _ptr(self.Z),
+                  _ptr(self.alphas), _ptr(self.rss), ctypes.addressof(passes), _ptr(self.ws), self.ws_bytes, _stream())
         self.beta_passes = passes.value
+        self.n_done += 1
         return float(self.rss.item())

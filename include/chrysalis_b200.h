@@ -169,9 +169,11 @@ int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int
 /* one iteration, in place:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);
  * Z <- betas X;  *rss_out (device) = ||X - alphas Z||_F^2.  beta_passes_out: HOST int (may be
  * NULL), number of active-set passes of the beta step.  Synchronises the stream (the beta
- * step's termination flag is read back). */
-int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, double* Z,
-                   double* alphas, double* rss_out, int* beta_passes_out, void* workspace,
+ * step's termination flag is read back).  warm != 0: `alphas` and the workspace still hold the
+ * previous iteration of the same restart; their supports seed the active sets (the NNLS
+ * minimisers are unique, so the result is the same - it is only reached in fewer steps). */
+int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double penalty_M, int warm,
+                   double* Z, double* alphas, double* rss_out, int* beta_passes_out, void* workspace,
                    size_t workspace_bytes, chr_stream_t stream);
 
 #ifdef __cplusplus
