@@ -331,11 +331,12 @@ def test_permutation_inference_matches_esda_semantics():
     assert weak.sum() > 3 and (res["p_sim"][weak] > 0.05).all()
     assert (np.abs(res["z_sim"] - ref_z) < 0.2 * np.abs(ref_z) + 0.5).all()
     assert (res["p_sim"] >= 1.0 / (P + 1)).all() and (res["p_sim"] <= 0.5 + 1e-12).all()
-    # a draw is a relabelling of the spots: permuting rows by hand gives the same bits
+    # a draw is a relabelling of the spots: permuting the rows by hand gives the same statistic (the pilot shift
+    # samples different rows, so the float32 rounding differs)
     perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)).to(torch.int32)
     I_map, _, _ = dv.moran_dense(Xd, nb, g, row_map=perm)
     I_hand, _, _ = dv.moran_dense(Xd[perm.long()].contiguous(), nb, g)
-    assert_close(I_map.cpu().numpy(), I_hand.cpu().numpy(), rtol=1e-6, atol=1e-9)
+    assert_close(I_map.cpu().numpy(), I_hand.cpu().numpy())
 
 
 def test_morans_i_permutation_fields(golden_hex):
