@@ -329,9 +329,13 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                   const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
     constexpr int NST = GEARY ? 5 : 4;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
-    const uint32_t smem0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // everything below is addressed in the shared window
+    uint32_t smem0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;            // everything below is addressed in the shared window
+    asm volatile("" : "+r"(smem0));                                    // keep it in a register (do not recompute the window base in the loop)
     const uint32_t stage_bytes = (uint32_t)tile_stage_bytes(buf_units);
     const uint32_t full_bar = smem0 + nstages * stage_bytes, empty_bar = full_bar + 8 * kTileMaxStages;
+    // level-2 accumulators live in shared memory (one float4 per statistic per compute thread): 16 registers less
+    const uint32_t l2_lane = empty_bar + 8 * kTileMaxStages + threadIdx.x * 16;
+    constexpr uint32_t kL2Stride = kTileWarps * 32 * 16;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_col = blockIdx.x * kGeneTile;
@@ -413,9 +417,12 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
         p.b = f2_pack(pf.z, pf.w);
     }
     const f2_t z2 = f2_pack(0.f, 0.f);
-    Row4 l1[NST], l2[NST];
+    Row4 l1[NST];
 #pragma unroll
-    for (int s = 0; s < NST; ++s) { l1[s].a = l1[s].b = z2; l2[s].a = l2[s].b = z2; }
+    for (int s = 0; s < NST; ++s) {
+        l1[s].a = l1[s].b = z2;
+        if (warp < kTileWarps) asm volatile("st.shared.v2.b64 [%0], {%1, %1};" ::"r"(l2_lane + s * kL2Stride), "l"(z2) : "memory");
+    }
     Row4 va[4], vg[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) va[t].a = va[t].b = vg[t].a = vg[t].b = z2;
@@ -462,14 +469,18 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
 #pragma unroll
                 for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cg[t]);
             }
-#pragma unroll 2
+            // in-tile rounds; the plan words of round r + 1 are fetched while round r is multiplied (the record is
+            // followed by at least one more 32-byte unit inside the staged slice or its padding)
+            int4 offs = lds_i4(rec + 16 * kPlanHdrUnits);
+            float4 cf = lds_f4(rec + 16 * (kPlanHdrUnits + 1));
+#pragma unroll 1
             for (int r = 0; r < RL; ++r) {
-                const int4 offs = lds_i4(rec + 16 * (kPlanHdrUnits + 2 * r));
-                const float4 cf = lds_f4(rec + 16 * (kPlanHdrUnits + 2 * r + 1));
                 const int oo[4] = {offs.x, offs.y, offs.z, offs.w};
                 const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) lds_row4_if(va[t], tile_lane + (uint32_t)oo[t], cc[t]);
+                offs = lds_i4(rec + 16 * (kPlanHdrUnits + 2 * r + 2));
+                cf = lds_f4(rec + 16 * (kPlanHdrUnits + 2 * r + 3));
 #pragma unroll
                 for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], va[t]);
             }
@@ -540,13 +551,19 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
         if (c & 1) {
 #pragma unroll
             for (int stt = 0; stt < NST; ++stt) {
-                r4_add(l2[stt], l1[stt]);
+                Row4 acc = lds_row4(l2_lane + stt * kL2Stride);
+                r4_add(acc, l1[stt]);
+                asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(l2_lane + stt * kL2Stride), "l"(acc.a), "l"(acc.b) : "memory");
                 l1[stt].a = l1[stt].b = z2;
             }
         }
     }
+    Row4 l2[NST];
 #pragma unroll
-    for (int stt = 0; stt < NST; ++stt) r4_add(l2[stt], l1[stt]);
+    for (int stt = 0; stt < NST; ++stt) {
+        l2[stt] = l1[stt];
+        if (warp < kTileWarps) r4_add(l2[stt], lds_row4(l2_lane + stt * kL2Stride));
+    }
 
     // per-thread fp32 sums -> fp64, cross-warp reduction in fixed order, one statistic at a time
     __syncthreads();                                                  // every tile consumed: the stages are free
@@ -679,7 +696,9 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
     // shared memory of the tile kernel: 3 (or 2) stages of {64 KB tile, record offsets, plan slice}; very long
     // neighbour lists do not fit and take the stream kernel
     int nstages = kTileMaxStages;
-    auto tile_smem = [&](int ns) { return (size_t)1024 + (size_t)ns * tile_stage_bytes(plan_chunk_units) + 16 * kTileMaxStages; };
+    auto tile_smem = [&](int ns) {
+        return (size_t)1024 + (size_t)ns * tile_stage_bytes(plan_chunk_units) + 16 * kTileMaxStages + (size_t)(geary ? 5 : 4) * kTileWarps * 32 * 16;
+    };
     if (tile && tile_smem(nstages) > 227 * 1024) nstages = 2;
     if (tile && tile_smem(nstages) > 227 * 1024 && nbr) tile = false;
     CHR_REQUIRE(tile || nbr, "chr_moran_dense_f32: the stream kernel needs the neighbour lists");
