@@ -38,6 +38,33 @@ def _make_unique(names) -> pd.Index:
     return pd.Index(out)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream():
+    """A second CUDA stream (one per device, kept: its allocator pool is reused across calls) for work that
+    overlaps the upload of the counts.  None without a device: the device calls then raise ChrysalisNativeError."""
+    if not torch.cuda.is_available():
+        return None
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[dev]
+
+
+class _stream_ctx:
+    def __init__(self, stream):
+        self.ctx = torch.cuda.stream(stream) if stream is not None else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False,
               shard: bool = True, permutations: int = 0, seed: int | None = None):
     """Device part of ``detect_svgs``: filter -> normalise/log1p -> kNN W -> Moran's I.
@@ -56,7 +83,33 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     n, g_all = X.shape
     rank, size = dd.world() if shard else (0, 1)
     lo, hi = dd.shard_range(g_all, rank, size)
-    csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])
+    # While the counts are in flight: W (core.py:61-65, needs the coordinates only) and the zero fill of the dense
+    # matrix run on a side stream.  The dense buffer comes from the main stream's pool; the side stream waits for
+    # everything enqueued so far (whatever used that memory before), not for the upload enqueued next.
+    main = torch.cuda.current_stream() if torch.cuda.is_available() else None
+    side = _side_stream()
+    dense_buf = None
+    if side is not None:
+        dense_buf = torch.empty((n, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
+        side.wait_stream(main)
+    csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])      # asynchronous host -> device copy on the current stream
+    with _stream_ctx(side):
+        # core.py:61-65  kNN weights on (x, -y), row-standardised
+        pts = np.array(spatial, dtype=np.float64, copy=True)
+        pts[:, 1] = pts[:, 1] * -1
+        xy = dv.to_device(pts, torch.float64)
+        bbox = dv.spatial_bbox(xy)
+        order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
+        rank_of = torch.empty_like(order)
+        rank_of[order] = torch.arange(n, device=order.device)
+        nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
+        plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
+        if dense_buf is not None:
+            dense_buf.zero_()
+    if side is not None:
+        main.wait_stream(side)
+        for t in (rank_of, nbr) + ((plan.buf,) if plan is not None else ()):
+            t.record_stream(main)
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
     gene_nnz = dv.csr_gene_nnz(csr)
     keep = gene_nnz >= int(n * min_spots)
@@ -72,19 +125,9 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     scale = None
     if not already_log1p:
         scale = dv.median_scale(reduce_(dv.csr_spot_totals(csr, gene_col)))
-    # core.py:61-65  kNN weights on (x, -y), row-standardised
-    pts = np.array(spatial, dtype=np.float64, copy=True)
-    pts[:, 1] = pts[:, 1] * -1
-    xy = dv.to_device(pts, torch.float64)
-    bbox = dv.spatial_bbox(xy)
-    order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
-    rank_of = torch.empty_like(order)
-    rank_of[order] = torch.arange(n, device=order.device)
-    nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
-    plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
     if n_keep > 0:
         # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
-        dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p)
+        dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p, out=dense_buf)
         # core.py:71-76  the gene loop
         I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
         sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None

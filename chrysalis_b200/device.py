@@ -103,12 +103,18 @@ def dense_ld(n_cols: int) -> int:
 
 
 def csr_densify(csr: DeviceCSR, gene_col: torch.Tensor, n_cols: int, scale: torch.Tensor | None,
-                row_of_spot: torch.Tensor | None, apply_log1p: bool) -> torch.Tensor:
+                row_of_spot: torch.Tensor | None, apply_log1p: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``out``: optional pre-ZEROED [n, ld >= n_cols] float32 buffer (e.g. filled on a side stream while the
+    counts were still in flight from the host); the kernel then only scatters."""
     n, _ = csr.shape
-    ld = dense_ld(n_cols)
-    dense = torch.empty((n, ld), dtype=torch.float32, device=csr.data.device)
+    if out is None:
+        ld = dense_ld(n_cols)
+        dense = torch.empty((n, ld), dtype=torch.float32, device=csr.data.device)
+    else:
+        dense, ld = out, out.stride(0)
+        assert out.dtype == torch.float32 and out.shape[0] == n and ld >= n_cols and out.stride(1) == 1
     _lib.call("chr_csr_densify_log1p", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), n, _ptr(gene_col),
-              _ptr(scale), _ptr(row_of_spot), _ptr(dense), ld, int(apply_log1p), _stream())
+              _ptr(scale), _ptr(row_of_spot), _ptr(dense), ld, int(apply_log1p) | (2 if out is not None else 0), _stream())
     return dense
 
 

@@ -75,7 +75,9 @@ int chr_csr_spot_totals(const int64_t* indptr, const int32_t* indices, const flo
 /* dense[row_of_spot[i]][gene_col[g]] = f(data * scale[i]),  f = log1p if apply_log1p else identity,
  * product formed in float64 and rounded once to float32 (scanpy normalize_total semantics);
  * scale == NULL: no scaling.  dense is [n][ld] float32 and is zero-filled by the callee;
- * row_of_spot may be NULL (identity); genes with gene_col[g] < 0 are dropped. */
+ * row_of_spot may be NULL (identity); genes with gene_col[g] < 0 are dropped.
+ * apply_log1p: bit 0 = apply log1p, bit 1 = `dense` was already zero-filled by the caller (lets the
+ * 4 n ld byte fill overlap the host-to-device copy of the counts on another stream). */
 int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
                           const int32_t* gene_col, const double* scale, const int64_t* row_of_spot,
                           float* dense, int64_t ld, int apply_log1p, chr_stream_t stream);

@@ -108,7 +108,10 @@ class _FakeDevice:
     def moran_plan(self, nbr):
         return None
 
-    def csr_densify(self, csr, gene_col, n_keep, scale, rank_of, apply_log1p):
+    def dense_ld(self, n_cols):
+        return n_cols
+
+    def csr_densify(self, csr, gene_col, n_keep, scale, rank_of, apply_log1p, out=None):
         keep = (gene_col >= 0).numpy()
         d = np.asarray(csr[:, keep].todense(), dtype=np.float64)
         if scale is not None:
@@ -147,7 +150,7 @@ def _check_sharded_pca(rank, size, out_dir):
     pcs = z["pcs"]
     n, s = pcs.shape
     fake = _FakeDevice()
-    fake.csr_densify = lambda csr, gene_col, n_keep, scale, rank_of, apply_log1p: torch.from_numpy(
+    fake.csr_densify = lambda csr, gene_col, n_keep, scale, rank_of, apply_log1p, out=None: torch.from_numpy(
         np.asarray(csr[:, (gene_col >= 0).numpy()].todense(), dtype=np.float32))
     core.dv = fake
     ad = ch.AnnDataLite(sp.csr_matrix(pcs), obsm={"spatial": np.zeros((n, 2))})
