@@ -5,6 +5,7 @@ replaces; everything else of the reference (plots, utils) is out of scope (SURVE
 """
 from .core import aa, detect_svgs, morans_i_permutation, pca
 from .anndata_lite import AnnDataLite
+from .utils import estimate_compartments, integrate_adatas
 
-__all__ = ["detect_svgs", "pca", "aa", "morans_i_permutation", "AnnDataLite"]
+__all__ = ["detect_svgs", "pca", "aa", "morans_i_permutation", "integrate_adatas", "estimate_compartments", "AnnDataLite"]
 __version__ = "0.1.0"

@@ -88,3 +88,60 @@ def test_furthest_sum_matches_oracle_draws():
         r1, r2 = np.random.RandomState(42), np.random.RandomState(42)
         assert np.array_equal(core._furthest_sum(X, a, r1), oaa.furthest_sum(X, a, r2))
         assert r1.randint(1 << 30) == r2.randint(1 << 30)           # same number of draws consumed
+
+
+def test_integrate_adatas_union_and_varm(golden_hex, golden_random, monkeypatch):
+    """utils.py:161-250 with the device stage replaced by the oracle's numbers: per-sample columns, union, inner join."""
+    from oracle import svg as osvg
+    samples, refs = [], []
+    for z, drop in ((golden_hex, 0), (golden_random, 3)):
+        X = golden_csr(z)
+        g = min(X.shape[1], 300) - drop                              # different gene sets -> inner join
+        names = [f"gene{j}" for j in range(g)]
+        ad = ch.AnnDataLite(X[:, :g], obsm={"spatial": z["xy"]}, var_names=names)
+        ref = osvg.detect_svgs(X[:, :g], z["xy"], neighbors=int(z["k"]), top_svg=30)
+        refs.append(ref)
+        samples.append(ad)
+
+    it = iter(refs)
+
+    def stage(X, spatial, min_spots, neighbors, geary, already_log1p, timing=False):
+        r = next(it)
+        m = r["gene_mask"]
+        return m, r["morans"][m], None
+    monkeypatch.setattr(core, "svg_stage", stage)
+    # each sample keeps its own neighbour count through kwargs of the per-sample call (here the same for both)
+    out = ch.integrate_adatas(samples, sample_names=["a", "b"], calculate_svgs=True, top_svg=30, neighbors=6)
+    g_common = 297
+    assert out.shape == (len(samples[0]) + len(samples[1]), g_common)
+    assert list(out.obs["sample"].astype(str).unique()) == ["a", "b"]
+    assert out.obs_names[0].endswith("-a") and out.obs_names[-1].endswith("-b")
+    sv = out.varm["spatially_variable"]
+    assert list(sv.columns[:2]) == ["spatially_variable_a", "spatially_variable_b"]
+    union = sv["spatially_variable_a"].to_numpy(bool) | sv["spatially_variable_b"].to_numpy(bool)
+    assert np.array_equal(out.var["spatially_variable"].to_numpy(), union)
+    assert np.array_equal(sv["spatially_variable_a"].to_numpy(bool), refs[0]["spatially_variable"][:g_common])
+    mi = out.varm["Moran's I"]
+    m0 = refs[0]["gene_mask"][:g_common]
+    assert np.array_equal(mi["Moran's I_a"].to_numpy()[m0], refs[0]["morans"][:g_common][m0])
+    assert "spatially_variable_a" not in out.var.columns and "Moran's I_a" not in out.var.columns
+    assert out.obsm["spatial"].shape == (out.shape[0], 2)
+    with pytest.raises(Exception, match="sample_id_col is already present"):
+        ch.integrate_adatas(samples, sample_names=["a", "b"])
+
+
+def test_estimate_compartments_fields(monkeypatch):
+    n = 60
+    ad = ch.AnnDataLite(np.zeros((n, 5), np.float32), obsm={"spatial": np.zeros((n, 2)), "chr_X_pca": np.random.default_rng(0).normal(size=(n, 8))})
+
+    def fake_stage(X, a, max_iter=200, **kw):
+        al = np.full((X.shape[0], a), 1.0 / a)
+        return {"alphas": al, "archetypes": np.zeros((a, X.shape[1])), "rss": float(100 - a), "n_iter": max_iter}
+    monkeypatch.setattr(core, "aa_stage", fake_stage)
+    ch.estimate_compartments(ad, n_pcs=6, range_archetypes=(3, 7), max_iter=4)
+    assert ad.obsm["entropy"].shape == (n, 4)
+    assert np.allclose(ad.obsm["entropy"][:, 0], np.log(3))
+    assert ad.uns["chr_aa"]["RSSs"] == {3: 97.0, 4: 96.0, 5: 95.0, 6: 94.0}
+    ad2 = ch.AnnDataLite(np.zeros((4, 3), np.float32), obsm={"spatial": np.zeros((4, 2))})
+    with pytest.raises(ValueError, match="chr_X_pca"):
+        ch.estimate_compartments(ad2)
