@@ -208,7 +208,8 @@ def pipeline_stages(args, csr, I, g_scored, svg_e2e_ms, torch, dv, _lib, core):
     executed = 3 * 2.0 * n_pad * (nb * (nb + 1) // 2) * 128 * 128
     pca_s = t4 - t0
     aa_s = t6 - t5
-    return {"workload": f"top {S} SVGs of the resident matrix -> {r} PCs -> {A} archetypes, max_iter={args.aa_max_iter}, n_init=3",
+    cpu = pipeline_cpu_baseline(P, S, emb, r, A, n, int(fit["n_iter"]), args, torch)
+    return {"cpu_baseline": cpu, "workload": f"top {S} SVGs of the resident matrix -> {r} PCs -> {A} archetypes, max_iter={args.aa_max_iter}, n_init=3",
             "svg_e2e_s": None if svg_e2e_ms is None else round(svg_e2e_ms * 1e-3, 4), "pca_s": round(pca_s, 4), "aa_s": round(aa_s, 3),
             "end_to_end_s": None if svg_e2e_ms is None else round(svg_e2e_ms * 1e-3 + pca_s + aa_s, 3),
             "pca_breakdown_s": {"densify_colsum": round(t1 - t0, 4), "gram": round(t2 - t1, 4), "eigh": round(t3 - t2, 4),
@@ -221,6 +222,39 @@ def pipeline_stages(args, csr, I, g_scored, svg_e2e_ms, torch, dv, _lib, core):
                               "peak_source": "measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s",
                               "note": "split-bf16: 3 MMAs per product over the upper-triangular tiles are the executed flops"},
             "eigh_residual": float(worst), "aa_iterations_best_restart": int(fit["n_iter"]), "aa_rss": float(fit["rss"])}
+
+
+def pipeline_cpu_baseline(P, S, emb, r, A, n, aa_iters, args, torch):
+    """The reference's own CPU calls for PCA (sklearn arpack, core.py:127) and AA (archetypes 0.4.x restated,
+    oracle/aa.py) on BOUNDED row samples of the same data, extrapolated linearly in the number of spots
+    (both are O(N) per Lanczos step / per iteration); every extrapolated figure is labelled as such."""
+    from oracle import aa as oaa
+    from oracle import pca as opca
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    n_pca = min(n, 40_000)
+    rows = np.sort(rng.choice(n, n_pca, replace=False))
+    sample = P[torch.from_numpy(rows).cuda(), :S].cpu().numpy()
+    t0 = time.perf_counter()
+    opca.pca_arpack(sample, r)
+    pca_sample_s = time.perf_counter() - t0
+    n_aa = min(n, 4_000)
+    rows = np.sort(rng.choice(n, n_aa, replace=False))
+    X = emb[rows].astype(np.float64)
+    init_rows = rng.choice(n_aa, A, replace=False)
+    B0 = np.zeros((A, n_aa)); B0[np.arange(A), init_rows] = 1.0
+    t0 = time.perf_counter()
+    it = 3
+    oaa.fit_single(X, np.zeros((n_aa, A)), B0, max_iter=it, tol=0.0)
+    aa_iter_s = (time.perf_counter() - t0) / it
+    n_init = 3
+    return {"kind": "port", "cores": cores,
+            "pca": {"sample": f"sklearn PCA(arpack, {r} comps) on {n_pca} of {n} spots x {S} SVGs", "sample_s": round(pca_sample_s, 3),
+                    "extrapolated_full_s": round(pca_sample_s * n / n_pca, 1), "blas_threads": cores},
+            "aa": {"sample": f"{it} iterations of the restated archetypes loop (scipy.optimize.nnls per row) on {n_aa} of {n} spots",
+                   "s_per_iteration_sample": round(aa_iter_s, 3), "extrapolated_s_per_iteration_full": round(aa_iter_s * n / n_aa, 1),
+                   "extrapolated_full_s": round(aa_iter_s * n / n_aa * aa_iters * n_init, 0),
+                   "note": f"{n_init} restarts x {aa_iters} iterations as in the GPU run; single-threaded Python loop"}}
 
 
 # ---------------------------------------------------------------------------------------------
