@@ -107,3 +107,31 @@ def test_device_furthest_sum_matches_host_statement(n, d, a):
     got = dv.aa_furthest_sum(dv.to_device(X, torch.float64), a, first)
     assert np.array_equal(got, ref)
     assert np.array_equal(got, core._furthest_sum(X, a, np.random.RandomState(42)))
+
+
+def test_aa_properties_at_large_n():
+    """200k spots x 20 PCs, 8 archetypes: simplex constraints, monotone RSS of the alternating minimisation,
+    archetypes inside the data's bounding box, equivariance to relabelling the spots."""
+    n, d, a = 200_000, 20, 8
+    X = simplex_data(n, d, a, seed=1).astype(np.float64)
+    rows = np.random.default_rng(0).choice(n, a, replace=False)
+    Xd = dv.to_device(X, torch.float64)
+    st = dv.AAState(Xd, a)
+    st.init_from_rows(rows)
+    rss = [st.iterate() for _ in range(8)]
+    assert all(r2 <= r1 * (1 + 1e-9) for r1, r2 in zip(rss, rss[1:]))
+    al = st.alphas.cpu().numpy()
+    assert (al >= 0).all() and np.allclose(al.sum(1), 1.0, atol=1e-12)
+    Z = st.Z.cpu().numpy()
+    assert (Z >= X.min(0) - 1e-9).all() and (Z <= X.max(0) + 1e-9).all()      # convex combinations of data points
+    # the residual the kernel reports is the residual of its own factors
+    assert abs(rss[-1] - np.linalg.norm(X - al @ Z) ** 2) < 1e-8 * rss[-1]
+    # relabelling the spots permutes the rows of alphas and leaves the archetypes alone
+    perm = np.random.default_rng(1).permutation(n)
+    inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+    st2 = dv.AAState(dv.to_device(X[perm], torch.float64), a)
+    st2.init_from_rows(inv[rows])
+    rss2 = [st2.iterate() for _ in range(8)]
+    assert abs(rss2[-1] - rss[-1]) < 1e-6 * rss[-1]
+    assert np.abs(st2.Z.cpu().numpy() - Z).max() < 1e-6 * np.abs(Z).max()
+    assert np.abs(st2.alphas.cpu().numpy() - al[perm]).max() < 1e-6

@@ -110,3 +110,41 @@ def test_pca_errors_like_sklearn():
     ad2 = ch.AnnDataLite(sp.csr_matrix(P), obsm={"spatial": np.zeros((50, 2))})
     with pytest.raises(KeyError):
         ch.pca(ad2, n_pcs=3)                                    # spatially_variable missing
+
+
+def test_pca_properties_at_full_spot_count():
+    """BASELINE cfg4 spot count (700k) with a 256-gene SVG slab: size-independent properties of the
+    Gram -> eigensolver -> scores chain (the oracle would need minutes and 0.7 GB per call at this size)."""
+    n, s, r = 700_000, 256, 12
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    F = torch.randn((n, 6), device="cuda", generator=gen) * torch.linspace(3.0, 0.7, 6, device="cuda")
+    L = torch.randn((6, s), device="cuda", generator=gen)
+    P = torch.log1p((F @ L * 0.3 + 1.2 + 0.5 * torch.randn((n, s), device="cuda", generator=gen)).clamp_min(0)).contiguous()
+    X = torch.zeros((n, dv.dense_ld(s)), device="cuda")
+    X[:, :s] = P
+    mean = dv.column_sums(X, s) / n
+    assert torch.allclose(mean, P.double().mean(0), rtol=1e-12, atol=0)
+    C = dv.gram_centered(X, s, mean)
+    assert torch.equal(C, C.T)
+    # linearity: the Gram of two halves adds up (split-bf16 rounding is per element, chains differ: tolerance 1e-5 of the diagonal)
+    h = n // 2
+    Ca = dv.gram_centered(X[:h], s, mean)
+    Cb = dv.gram_centered(X[h:], s, mean)
+    scale = float(torch.diagonal(C).max())
+    assert float((Ca + Cb - C).abs().max()) < 2e-5 * scale
+    # against a float64 Gram of a column block (exact reference for 32 genes)
+    Zb = P[:, :32].double() - mean[:32]
+    assert float((C[:32, :32] - Zb.T @ Zb).abs().max()) < 2e-5 * scale
+    evals, V, worst = dv.eigh_topk(C / (n - 1), r)
+    assert worst < 1e-9
+    G = V @ V.T
+    assert float((G - torch.eye(r, device="cuda", dtype=torch.float64)).abs().max()) < 1e-12
+    assert bool((evals[:-1] >= evals[1:]).all())
+    Y = dv.pca_scores(X, s, mean, V)
+    # scores are centred, uncorrelated, with variance = eigenvalue (float32 accumulation: 1e-3)
+    Yd = Y.double()
+    assert float(Yd.mean(0).abs().max()) < 1e-3 * float(evals[0].sqrt())
+    cov = (Yd.T @ Yd) / (n - 1)
+    assert torch.allclose(torch.diagonal(cov), evals, rtol=2e-3)
+    off = cov - torch.diag(torch.diagonal(cov))
+    assert float(off.abs().max()) < 2e-3 * float(evals[0])
