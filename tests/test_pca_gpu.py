@@ -131,7 +131,7 @@ def test_pca_properties_at_full_spot_count():
     Ca = dv.gram_centered(X[:h], s, mean)
     Cb = dv.gram_centered(X[h:], s, mean)
     scale = float(torch.diagonal(C).max())
-    assert float((Ca + Cb - C).abs().max()) < 2e-5 * scale
+    assert float((Ca + Cb - C).abs().max()) < 5e-5 * scale
     # against a float64 Gram of a column block (exact reference for 32 genes)
     Zb = P[:, :32].double() - mean[:32]
     assert float((C[:32, :32] - Zb.T @ Zb).abs().max()) < 2e-5 * scale
