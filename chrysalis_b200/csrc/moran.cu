@@ -447,7 +447,8 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             const uint32_t rec = s_rec + (uint32_t)(lds_i32(s_off + 4 * ql) - off0) * 16;
             const int4 h0 = lds_i4(rec);
             const float4 h1 = lds_f4(rec + 16);                       // c12 c13 c23 -
-            const int RL = h0.x & 0xff, RG = (h0.x >> 8) & 0xff, nvalid = h0.x >> 16;
+            const int RL = h0.x & 0xff, RG = (h0.x >> 8) & 0xff, nvalid = (h0.x >> 16) & 0xff;
+            const bool irregular = (h0.x >> 30) & 1;                  // some indeg != k in this quad
             Row4 x[4], s[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -504,7 +505,7 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                 }
             }
             const float4 cs = lds_f4(rec + 32);                       // csum
-            const float4 dg = lds_f4(rec + 48);                       // indeg
+            const float4 dg = lds_f4(rec + 48);                       // indeg - k
             if (SHIFT) {
                 const float ncs[4] = {-cs.x, -cs.y, -cs.z, -cs.w};
 #pragma unroll
@@ -525,13 +526,17 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                 r4_add(l1[0], x[t]);
                 r4_fma(l1[1], x[t], x[t]);
                 r4_fma(l1[2], x[t], s[t]);
-                r4_fmac(l1[3], dgs[t], x[t]);
-                if (GEARY) {                                          // same I with or without Geary's C
-                    Row4 dx;
-                    const f2_t dd = f2_dup(dgs[t]);
-                    dx.a = f2_fma(dd, x[t].a, z2);
-                    dx.b = f2_fma(dd, x[t].b, z2);
-                    r4_fma(l1[4], dx, x[t]);
+                if (irregular) {
+                    // SC = sum_j indeg_j x_j = k S1 + sum_j (indeg_j - k) x_j: only the second part is accumulated, and
+                    // only in quads that have a spot with indeg != k (lattice boundaries; everywhere for random kNN)
+                    r4_fmac(l1[3], dgs[t], x[t]);
+                    if (GEARY) {                                      // same I with or without Geary's C
+                        Row4 dx;
+                        const f2_t dd = f2_dup(dgs[t]);
+                        dx.a = f2_fma(dd, x[t].a, z2);
+                        dx.b = f2_fma(dd, x[t].b, z2);
+                        r4_fma(l1[4], dx, x[t]);
+                    }
                 }
             };
             if (nvalid == 4) {                                        // every quad but the last one of a ragged n
@@ -613,6 +618,10 @@ moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad,
         S[st] = a;
     }
     const double dn = (double)n, dk = (double)k;
+    if (sym) {                                                    // the tile kernel accumulates the (indeg - k) parts only
+        S[3] += dk * S[0];
+        S[4] += dk * S[1];
+    }
     const double m = S[0] / dn;                                   // mean of shifted values
     const double zz = S[1] - dn * m * m;                          // sum (x - mean)^2
     const double zwz = (S[2] - m * (dk * S[0] + S[3]) + m * m * dn * dk) / dk;  // z' W z, W = Adj / k

@@ -34,7 +34,8 @@ __device__ __forceinline__ uint32_t pair_hash(uint32_t i, uint32_t j) {
 }
 
 // own[i] bit a: spot i owns the pair {i, nbr[i][a]}.  Only first occurrences of a neighbour carry a
-// bit; quad-internal and self pairs carry none.  cnt[i] = number of list entries of spot i.
+// bit; quad-internal and self pairs carry none.  cnt[i] = list entries of spot i: in-tile | out-of-tile << 16
+// (the kernel walks a quad in max(in-tile) + max(out-of-tile) rounds, so the two kinds are balanced separately).
 __global__ void plan_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, uint64_t* __restrict__ own,
                                  int32_t* __restrict__ cnt, int32_t* __restrict__ indeg) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,7 +49,7 @@ __global__ void plan_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int
         bool first = true;
         for (int b = 0; b < a; ++b) first &= (A[b] != j);
         if (!first) continue;
-        if (j == (int32_t)i) { ++c; continue; }                        // self loop: one list entry, no bit
+        if (j == (int32_t)i) { ++c; continue; }                        // self loop: one in-tile list entry, no bit
         if ((j >> 2) == (int32_t)(i >> 2)) continue;                   // quad-internal
         const int32_t* B = nbr + (int64_t)j * k;
         bool back = false;
@@ -58,7 +59,7 @@ __global__ void plan_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int
             const uint32_t lo = (uint32_t)(i < j ? i : j), hi = (uint32_t)(i < j ? j : i);
             mine = ((pair_hash((uint32_t)i, (uint32_t)j) & 1u) ? lo : hi) == (uint32_t)i;
         }
-        if (mine) { ++c; bits |= 1ull << a; }
+        if (mine) { c += (j / kTileSpots) == (int32_t)(i / kTileSpots) ? 1 : (1 << 16); bits |= 1ull << a; }
     }
     own[i] = bits;
     cnt[i] = c;
@@ -86,12 +87,14 @@ __global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, in
         for (int b = 0; b < k; ++b) back |= (B[b] == (int32_t)i);
         if (!back) continue;                                           // one-sided pair: fixed owner
         const bool i_owns = (mine_old >> a) & 1ull;
-        const int cj = cnt_in[j];
-        const int c_owner = i_owns ? ci : cj, c_other = i_owns ? cj : ci;
+        const bool in_tile = (j / kTileSpots) == (int32_t)(i / kTileSpots);     // the same kind for both endpoints
+        const int sh = in_tile ? 0 : 16, one = 1 << sh;
+        const int cii = (ci >> sh) & 0xffff, cj = (cnt_in[j] >> sh) & 0xffff;
+        const int c_owner = i_owns ? cii : cj, c_other = i_owns ? cj : cii;
         const bool flip = (c_owner > c_other + 1) && ((pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
         if (flip) {
-            if (i_owns) { bits &= ~(1ull << a); --c; }
-            else { bits |= 1ull << a; ++c; }
+            if (i_owns) { bits &= ~(1ull << a); c -= one; }
+            else { bits |= 1ull << a; c += one; }
         }
     }
     own_out[i] = bits;
@@ -199,7 +202,7 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int
     const int RL = qrounds[q] & 0xff, RG = qrounds[q] >> 8;
     const int nvalid = (int)(n - 4 * q < 4 ? n - 4 * q : 4);
     for (int w = 1; w < kPlanHdrUnits * 4; ++w) recf[w] = 0.f;
-    rec[0] = RL | (RG << 8) | (nvalid << 16);
+    int irregular = 0;
     const int tile_row0 = (int)((4 * q) % kTileSpots);                 // row of the quad's first spot inside its tile
     int32_t* loc = rec + kPlanHdrUnits * 4;
     int32_t* glob = loc + RL * kPlanRoundUnits * 4;
@@ -228,8 +231,9 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int
             csum += c;
         });
         recf[8 + t] = csum;
-        recf[12 + t] = (float)indeg[i];
-        // pairs inside the quad: written by the lower spot when it lists the pair, else by the upper one
+        recf[12 + t] = (float)(indeg[i] - k);                               // column sum of the adjacency minus its row sum
+        if (indeg[i] != k) irregular = 1;
+        // pairs inside the quad
         const int32_t* A = nbr + i * k;
         for (int a = 0; a < k; ++a) {
             const int32_t j = A[a];
@@ -244,6 +248,8 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int
             recf[1 + idx] = (float)(mult + back);                            // words 1..3 (unit 0), 4..6 (unit 1)
         }
     }
+    // bit 30: some spot of the quad has indeg != k (the kernel then adds the (indeg - k) x terms)
+    rec[0] = RL | (RG << 8) | (nvalid << 16) | (irregular << 30);
 }
 
 struct PlanScratch {
