@@ -527,6 +527,20 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 while the bench runs
+    # (NCCL prints its version banner there from C) is sent to stderr, the descriptor is restored for the result
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+
+    def print(*args, **kw):  # noqa: A001 - the result line goes to the real stdout
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        _real_print(*args, **kw)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     if a.impl == "reference":
         run_reference(a)
     else:
