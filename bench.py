@@ -372,7 +372,7 @@ def run_native(args):
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (fp64 per-gene accumulators)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes per GPU, square lattice, kNN k={k}, "
                                f"dense float32 log1p(normalize_total(counts)) resident in HBM",
                    "n_spots": n, "genes_per_gpu": g, "genes_scored_per_gpu": g_scored, "genes_total": world * g_scored,
@@ -514,7 +514,7 @@ def run_reference(args):
     value = n_sample / (ms * 1e-3)
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 lag)", "data": "synthetic",
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes, square lattice, kNN k={k}", "n_spots": n,
                       "genes_per_gpu": g, "neighbors": k},
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
