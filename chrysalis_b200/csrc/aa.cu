@@ -116,6 +116,72 @@ __device__ void nnls_normal(const double* __restrict__ G, const double* c, int n
     }
 }
 
+// Fast path of the warm-started alpha step: when the previous coefficients of a spot have at most kFastP
+// non-zeros, the least-squares solve on that support runs entirely in registers (unrolled Cholesky, indices by
+// __fns); if the solution is positive and every other archetype has a non-positive gradient it IS the NNLS
+// minimiser (KKT; unique because G is positive definite) and the general active-set code is skipped.
+// Returns false when the spot has to take the general path.
+constexpr int kFastP = 6;
+__device__ __forceinline__ bool nnls_warm_small(const double* __restrict__ G, const double* __restrict__ c, int na, unsigned mask,
+                                                double tol, int* idx, double* sol) {
+    const int np = __popc(mask);
+    if (np == 0 || np > kFastP) return false;
+    double L[kFastP][kFastP], rhs[kFastP];
+#pragma unroll
+    for (int p = 0; p < kFastP; ++p) {
+        idx[p] = p < np ? (int)__fns(mask, 0, p + 1) : 0;
+        rhs[p] = c[idx[p]];
+    }
+    // Cholesky of G[idx, idx] (rows/cols >= np are skipped by the guards)
+#pragma unroll
+    for (int i = 0; i < kFastP; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            if (i < np) {
+                double v = G[idx[i] * na + idx[j]];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+                if (i == j) {
+                    if (!(v > 0.0)) return false;
+                    L[i][i] = sqrt(v);
+                } else {
+                    L[i][j] = v / L[j][j];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kFastP; ++i) {
+        if (i < np) {
+            double v = rhs[i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) v -= L[i][k] * sol[k];
+            sol[i] = v / L[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = kFastP - 1; i >= 0; --i) {
+        if (i < np) {
+            double v = sol[i];
+#pragma unroll
+            for (int k = i + 1; k < kFastP; ++k)
+                if (k < np) v -= L[k][i] * sol[k];
+            sol[i] = v / L[i][i];
+            if (!(sol[i] > 0.0)) return false;
+        }
+    }
+    // KKT: no archetype outside the support may have a positive gradient
+    for (int j = 0; j < na; ++j) {
+        if ((mask >> j) & 1u) continue;
+        double w = c[j];
+#pragma unroll
+        for (int p = 0; p < kFastP; ++p)
+            if (p < np) w -= G[j * na + idx[p]] * sol[p];
+        if (w > tol) return false;
+    }
+    return true;
+}
+
 // ---- alpha step: one thread per spot ---------------------------------------------------------------
 // also accumulates the CTA's partial  A^T A (na x na)  and  A^T X (na x d)  for the pinv step
 template <int MAXA>
@@ -148,9 +214,25 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
             for (int t = 0; t < d; ++t) v += Zs[a * d + t] * x[t];
             c[a] = v;
         }
+        unsigned mask = 0;
+        double cmax = 0.0;
         if (warm)
-            for (int a = 0; a < na; ++a) a_out[a] = alphas[i * na + a];
-        nnls_normal<MAXA>(G, c, na, a_out, warm != 0);
+            for (int a = 0; a < na; ++a) {
+                a_out[a] = alphas[i * na + a];
+                if (a < 32 && a_out[a] > 0.0) mask |= 1u << a;
+                cmax = fmax(cmax, fabs(c[a]));
+            }
+        int idx[kFastP];
+        double sol[kFastP];
+        if (warm && na <= 32 && nnls_warm_small(G, c, na, mask, 1e-12 * fmax(cmax, 1e-300), idx, sol)) {
+            for (int a = 0; a < na; ++a) a_out[a] = 0.0;
+            const int np = __popc(mask);
+#pragma unroll
+            for (int p = 0; p < kFastP; ++p)
+                if (p < np) a_out[idx[p]] = sol[p];
+        } else {
+            nnls_normal<MAXA>(G, c, na, a_out, warm != 0);
+        }
         double sum = 0.0;
         for (int a = 0; a < na; ++a) { a_out[a] = fmax(a_out[a], 0.0); sum += a_out[a]; }
         const double inv = 1.0 / sum;
