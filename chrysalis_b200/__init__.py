@@ -3,9 +3,9 @@
 Re-exports mirror ``/root/reference/chrysalis/__init__.py:10-12`` for the path this package
 replaces; everything else of the reference (plots, utils) is out of scope.
 """
-from .core import aa, detect_svgs, morans_i_permutation, pca
+from .core import aa, detect_svgs, local_morans_i, morans_i_permutation, pca
 from .anndata_lite import AnnDataLite
 from .utils import estimate_compartments, integrate_adatas
 
-__all__ = ["detect_svgs", "pca", "aa", "morans_i_permutation", "integrate_adatas", "estimate_compartments", "AnnDataLite"]
+__all__ = ["detect_svgs", "pca", "aa", "morans_i_permutation", "local_morans_i", "integrate_adatas", "estimate_compartments", "AnnDataLite"]
 __version__ = "0.1.0"

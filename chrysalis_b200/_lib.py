@@ -52,6 +52,7 @@ _SIGNATURES = {
     "chr_aa_furthest_sum_workspace_bytes": (c_size_t, [c_int64]),
     "chr_aa_furthest_sum": (c_int, [_P, c_int64, c_int, c_int, c_int64, _P, _P, c_size_t, _P]),
     "chr_aa_iterate": (c_int, [_P, c_int64, c_int, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "chr_local_moran_f32": (c_int, [_P, c_int64, _P, c_int, c_double, c_int, ctypes.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "chr_moran_plan_bytes": (c_size_t, [c_int64, c_int]),
     "chr_moran_plan_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "chr_moran_plan_build": (c_int, [_P, c_int64, c_int, _P, c_size_t, _P, _P, c_size_t, _P]),

@@ -203,6 +203,46 @@ def morans_i_permutation(adata, min_spots: float = 0.05, neighbors: int = 6, per
         adata.var[f"Moran's I {key}"] = pd.Series(sim[key], index=names)
 
 
+def local_morans_i(adata, keys, neighbors: int = 6, permutations: int = 999, seed: int | None = None, obsm_key: str | None = None):
+    """
+    Local Moran's I (LISA) per spot for a few variables: ``esda.moran.Moran_Local(y, w, permutations=P)`` with the
+    W of ``detect_svgs`` (core.py:61-65), as the authors run it next to the global statistic
+    (``article/A2_human_lymph_node/morans_i.ipynb:150``; ``chrysalis/core.py`` has no such call).
+
+    ``keys``: gene names (columns of ``adata.X`` as stored - normalise first, like for esda), or with ``obsm_key``
+    column indices of ``adata.obsm[obsm_key]`` (e.g. the compartment scores ``'chr_aa'``).
+    Writes ``.obsm['local_morans_i']``, ``['local_morans_q']`` (1 HH, 2 LH, 3 LL, 4 HL) and, with permutations,
+    ``['local_morans_p_sim']`` (all [n, len(keys)]) and ``.uns['local_morans']``.
+    """
+    keys = list(keys)
+    n = len(adata)
+    if obsm_key is None:
+        from scipy.sparse import issparse
+        cols = pd.Index(adata.var_names).get_indexer(keys)
+        assert (cols >= 0).all(), "local_morans_i: unknown gene name"
+        sub = adata.X[:, cols]
+        vals = np.asarray(sub.todense() if issparse(sub) else sub, dtype=np.float32)
+    else:
+        vals = np.asarray(adata.obsm[obsm_key], dtype=np.float32)[:, [int(c) for c in keys]]
+    pts = np.array(adata.obsm['spatial'], dtype=np.float64, copy=True)
+    pts[:, 1] = pts[:, 1] * -1
+    xy = dv.to_device(pts, torch.float64)
+    nbr = dv.knn_build(xy, neighbors, dv.spatial_bbox(xy))
+    seed = int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
+    Is, q, ps = (np.empty((n, len(keys)), dtype=dt) for dt in (np.float32, np.int32, np.float32))
+    yd = dv.to_device(np.ascontiguousarray(vals.T), torch.float32)
+    for j in range(len(keys)):
+        res = dv.local_moran(yd[j], nbr, permutations=int(permutations), seed=seed + j)
+        Is[:, j], q[:, j] = res["Is"].cpu().numpy(), res["q"].cpu().numpy()
+        if permutations:
+            ps[:, j] = res["p_sim"].cpu().numpy()
+    adata.obsm['local_morans_i'] = Is
+    adata.obsm['local_morans_q'] = q
+    if permutations:
+        adata.obsm['local_morans_p_sim'] = ps
+    adata.uns['local_morans'] = {'keys': keys, 'neighbors': neighbors, 'permutations': int(permutations), 'obsm_key': obsm_key}
+
+
 def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     """Device part of ``pca``: densify the SVG columns -> column means -> tcgen05 Gram ->
     eigensolver -> scores.  Returns host arrays (scores (n, r) float32, components (r, S) float32,

@@ -267,6 +267,25 @@ def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | No
             "z_sim": z, "p_z_sim": p_z}
 
 
+def local_moran(y: torch.Tensor, nbr: torch.Tensor, permutations: int = 999, seed: int = 0):
+    """``esda.moran.Moran_Local(y, w, permutations=P)`` for one variable ``y`` [n] (float32, device, spot order of ``nbr``).
+    Returns a dict of device tensors [n]: Is, lag, q, and with permutations p_sim, EI_sim, VI_sim."""
+    assert y.dim() == 1 and nbr.dtype == torch.int32 and nbr.is_contiguous() and nbr.shape[0] == y.numel()
+    n, k = nbr.shape
+    yd = y.to(torch.float64)
+    z = ((yd - yd.mean()) / yd.std(unbiased=False)).to(torch.float32).contiguous()
+    z2ss = float((z.to(torch.float64) ** 2).sum().item())
+    f = lambda dt: torch.empty(n, dtype=dt, device=y.device)
+    lag, Is, q = f(torch.float32), f(torch.float32), f(torch.int32)
+    p_sim, ei, vi = (f(torch.float32), f(torch.float32), f(torch.float32)) if permutations else (None, None, None)
+    _lib.call("chr_local_moran_f32", _ptr(z), n, _ptr(nbr), k, z2ss, int(permutations), int(seed) & (2 ** 64 - 1), _ptr(lag), _ptr(Is),
+              _ptr(q), _ptr(p_sim), _ptr(ei), _ptr(vi), _stream())
+    out = {"Is": Is, "lag": lag, "q": q, "z": z}
+    if permutations:
+        out.update({"p_sim": p_sim, "EI_sim": ei, "VI_sim": vi})
+    return out
+
+
 def last_kernel_ms(family: int = _lib.FAMILY_MORAN) -> float:
     return float(_lib.query("chr_last_kernel_ms", family))
 

@@ -118,6 +118,17 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
                         double* out_stats, void* workspace, size_t workspace_bytes,
                         chr_stream_t stream);
 
+/* ---- Local Moran's I (LISA) ---------------------------------------------------------------
+ * replaces  esda.moran.Moran_Local(y, w, transformation='r', permutations=P)
+ *           (/root/reference/article/A2_human_lymph_node/morans_i.ipynb:150; not called by core.py)
+ * z: [n] float32, the variable STANDARDISED by the caller (z = (y - mean) / population std), z2ss = sum z^2.
+ * Outputs [n]: lag (W z), Is, quadrant q (1 HH, 2 LH, 3 LL, 4 HL) and, with permutations > 0, the
+ * conditional-permutation p_sim, EI_sim, VI_sim per spot (k <= 64). */
+int chr_local_moran_f32(const float* z, int64_t n, const int32_t* nbr, int k, double z2ss,
+                        int permutations, uint64_t seed, float* lag_out, float* Is_out,
+                        int32_t* q_out, float* p_sim_out, float* ei_sim_out, float* vi_sim_out,
+                        chr_stream_t stream);
+
 /* ---- K6-K8: PCA of the SVG matrix ------------------------------------------------------
  * replaces  PCA(n_components=n_pcs, svd_solver='arpack', random_state=42).fit_transform(pcs)
  *           (/root/reference/chrysalis/core.py:126-128; sklearn -> scipy ARPACK svds)

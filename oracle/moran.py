@@ -113,6 +113,41 @@ def moran_permutation(y: np.ndarray, w: sp.csr_matrix, permutations: int = 999,
             "VI_sim": seI_sim ** 2, "z_sim": (I - EI_sim) / seI_sim}
 
 
+def local_moran(y: np.ndarray, w: sp.csr_matrix, permutations: int = 0, rng: np.random.Generator | None = None) -> dict:
+    """``esda.moran.Moran_Local(y, w, transformation='r', permutations=P)`` (esda 2.4 semantics; the authors'
+    call is /root/reference/article/A2_human_lymph_node/morans_i.ipynb:150).  esda is not installed here:
+    this restates its published definition - parity unpinned.
+
+    z = (y - mean) / std,  Is = (n - 1) z * (W z) / sum z^2,  q: 1 HH, 2 LH, 3 LL, 4 HL; conditional
+    permutations: the neighbours of spot i are replaced by a random draw (without replacement) of the other spots.
+    """
+    rng = np.random.default_rng(0) if rng is None else rng
+    y = np.asarray(y, dtype=np.float64).flatten()
+    n = len(y)
+    z = y - y.mean()
+    z = z / z.std()
+    den = (z * z).sum()
+    lag = w * z
+    Is = (n - 1) * z * lag / den
+    zp, lp = z > 0, lag > 0
+    q = np.where(zp & lp, 1, np.where(~zp & lp, 2, np.where(~zp & ~lp, 3, 4)))
+    out = {"z": z, "lag": lag, "Is": Is, "q": q}
+    if permutations:
+        sims = np.empty((n, permutations))
+        ids = np.arange(n)
+        for i in range(n):
+            wi = w.data[w.indptr[i]:w.indptr[i + 1]]
+            others = ids[ids != i]
+            for p in range(permutations):
+                pick = rng.permutation(others)[:len(wi)]
+                sims[i, p] = (n - 1) * z[i] * (wi * z[pick]).sum() / den
+        larger = (sims >= Is[:, None]).sum(1)
+        low = (permutations - larger) < larger
+        larger[low] = permutations - larger[low]
+        out.update({"sim": sims, "p_sim": (larger + 1.0) / (permutations + 1.0), "EI_sim": sims.mean(1), "VI_sim": sims.var(1)})
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # drivers over a spots x genes matrix
 # ----------------------------------------------------------------------------------------

@@ -349,3 +349,49 @@ def test_morans_i_permutation_fields(golden_hex):
     assert np.array_equal(np.isnan(p), ~m) and (p[m] >= 0.01 - 1e-12).all() and (p[m] <= 0.5 + 1e-12).all()
     zs = ad.var["Moran's I z_sim"].to_numpy()
     assert (zs[m][z["morans"][m] > 0.2] > 4).all()                     # clearly spatial genes are far out in the null
+
+
+def test_local_moran_matches_esda_semantics():
+    """esda.moran.Moran_Local: Is / lag / quadrants exact, conditional-permutation p_sim within Monte-Carlo error;
+    the local statistics sum to (n - 1) times the global Moran's I."""
+    n, k, P = 600, 6, 499
+    rs = np.random.RandomState(5)
+    xy = rs.rand(n, 2)
+    nbr = ow.knn_neighbors(xy, k)
+    w = ow.row_standardised_csr(nbr)
+    y = (np.sin(6 * xy[:, 0]) + 0.5 * rs.randn(n)).astype(np.float32)     # spatially structured + noise
+    ref = om.local_moran(y, w, P, np.random.default_rng(1))
+    res = {key: v.cpu().numpy() for key, v in
+           dv.local_moran(torch.from_numpy(y).cuda(), torch.from_numpy(nbr.astype(np.int32)).cuda(), permutations=P, seed=9).items()}
+    np.testing.assert_allclose(res["Is"], ref["Is"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(res["lag"], ref["lag"], rtol=2e-5, atol=2e-6)
+    clear = (np.abs(ref["z"]) > 1e-4) & (np.abs(ref["lag"]) > 1e-4)
+    assert np.array_equal(res["q"][clear], ref["q"][clear])
+    assert abs(res["Is"].astype(np.float64).sum() / (n - 1) - om.morans_I_f64(y, w)) < 1e-5
+    # conditional randomisation: E[sim_i] = -Is-scale * z_i / (n - 1) ... compare with the oracle's draws statistically
+    assert np.abs(res["EI_sim"] - ref["EI_sim"]).max() < 6 * np.sqrt(ref["VI_sim"].max() / P) + 1e-6
+    np.testing.assert_allclose(res["VI_sim"], ref["VI_sim"], rtol=0.35, atol=1e-6)
+    # p_sim: binomial noise of two independent P-draw estimates
+    assert np.abs(res["p_sim"] - ref["p_sim"]).max() < 6 * np.sqrt(2 * 0.25 / P)
+    assert np.corrcoef(res["p_sim"], ref["p_sim"])[0, 1] > 0.97
+    assert res["p_sim"].min() >= 1.0 / (P + 1) and res["p_sim"].max() <= 0.5 + 1.0 / (P + 1)
+    # same seed -> same draws; different launch has no effect
+    again = dv.local_moran(torch.from_numpy(y).cuda(), torch.from_numpy(nbr.astype(np.int32)).cuda(), permutations=P, seed=9)
+    assert np.array_equal(again["p_sim"].cpu().numpy(), res["p_sim"])
+
+
+def test_local_morans_i_fields(golden_hex):
+    X, spatial = golden_csr(golden_hex), golden_hex["xy"]
+    busy = np.argsort(-np.asarray((X > 0).sum(0)).ravel())[:3]
+    ad = ch.AnnDataLite(osvg.normalize_total_log1p(X)[:, busy].tocsr(), obsm={"spatial": spatial})
+    names = list(ad.var_names[:3])
+    ch.local_morans_i(ad, names, neighbors=6, permutations=99, seed=3)
+    n = X.shape[0]
+    assert ad.obsm["local_morans_i"].shape == (n, 3) and ad.obsm["local_morans_p_sim"].shape == (n, 3)
+    assert set(np.unique(ad.obsm["local_morans_q"])) <= {1, 2, 3, 4}
+    nbr = ow.knn_neighbors(ow.reference_points(spatial), 6)
+    w = ow.row_standardised_csr(nbr)
+    dense = np.asarray(ad.X[:, :3].todense(), dtype=np.float32)
+    for j in range(3):
+        if dense[:, j].std() > 0:
+            np.testing.assert_allclose(ad.obsm["local_morans_i"][:, j], om.local_moran(dense[:, j], w)["Is"], rtol=1e-4, atol=1e-5)

@@ -137,3 +137,20 @@ def test_aa_oracle_matches_golden(golden_pca_aa):
     assert fit["rss"] == pytest.approx(float(z["rss"]), rel=1e-6)
     assert np.abs(fit["alphas"] - z["alphas"]).max() < 1e-6
     assert np.allclose(fit["alphas"].sum(1), 1.0) and (fit["alphas"] >= 0).all()
+
+
+def test_local_moran_sums_to_global_and_conditional_null():
+    """Moran_Local restatement: sum_i Is_i = (n - 1) I, quadrants partition the spots, p_sim in (0, 0.5]."""
+    rs = np.random.RandomState(5)
+    n = 200
+    xy = rs.rand(n, 2)
+    w = ow.row_standardised_csr(ow.knn_neighbors(xy, 6))
+    y = np.sin(6 * xy[:, 0]) + 0.5 * rs.randn(n)
+    r = om.local_moran(y, w, 39)
+    assert abs(r["Is"].sum() / (n - 1) - om.morans_I_f64(y, w)) < 1e-12
+    assert set(np.unique(r["q"])) <= {1, 2, 3, 4}
+    assert r["p_sim"].min() >= 1 / 40 and r["p_sim"].max() <= 0.5 + 1 / 40
+    # conditional null mean of spot i: -(n - 1) z_i^2 ... / den averaged over the other spots = -z_i * (sum z - z_i)/(n-1) * (n-1)/den
+    z = r["z"]
+    expect = (n - 1) * z * ((z.sum() - z) / (n - 1)) / (z * z).sum()
+    assert np.abs(r["EI_sim"] - expect).max() < 6 * np.sqrt(r["VI_sim"].max() / 39)
