@@ -539,7 +539,14 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                     }
                 }
             };
-            if (nvalid == 4) {                                        // every quad but the last one of a ragged n
+            if ((h0.x >> 16) == 4) {                                  // 4 valid spots, every indeg == k: the common quad
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    r4_add(l1[0], x[t]);
+                    r4_fma(l1[1], x[t], x[t]);
+                    r4_fma(l1[2], x[t], s[t]);
+                }
+            } else if (nvalid == 4) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) accumulate(t);
             } else {

@@ -18,11 +18,13 @@
 // On a square lattice with k = 8 a spot reads ~2.9 list rows instead of 8.  Any list is legal
 // (duplicates, self loops, asymmetric kNN): coefficients are multiplicities.  k <= 64 (one
 // 64-bit owner mask per spot).
+#include <cstdlib>
 #include "moran.cuh"
 
 namespace chr {
 
-constexpr int kRelaxIters = 8;
+constexpr int kRelaxIters = 8;        // sweeps that balance the per-spot list lengths
+constexpr int kRelaxMaxIters = 40;    // further sweeps that lower the per-quad maxima (what the kernel's round count is)
 
 __device__ __forceinline__ uint32_t pair_hash(uint32_t i, uint32_t j) {
     const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
@@ -65,8 +67,23 @@ __global__ void plan_init_kernel(const int32_t* __restrict__ nbr, int64_t n, int
     cnt[i] = c;
 }
 
+// longest list (in-tile | out-of-tile << 16, each taken separately) among the spots of the quad of spot i
+__device__ __forceinline__ int quad_max_counts(const int32_t* __restrict__ cnt, int64_t n, int64_t i) {
+    int ml = 0, mg = 0;
+    const int64_t q = i & ~(int64_t)3;
+    for (int t = 0; t < 4; ++t)
+        if (q + t < n) {
+            const int c = cnt[q + t];
+            ml = max(ml, c & 0xffff);
+            mg = max(mg, (c >> 16) & 0xffff);
+        }
+    return ml | (mg << 16);
+}
+
 // one Jacobi sweep of owner balancing: a mutual pair moves to the other endpoint when that lowers
 // the larger of the two list lengths; both endpoints evaluate the same rule on the same data.
+// Sweeps >= kRelaxIters also move an entry one step downhill when its owner is the longest list of its
+// quad and the receiver stays within its own quad's longest: the kernel pays max-over-the-quad rounds.
 __global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, const uint64_t* __restrict__ own_in,
                                   const int32_t* __restrict__ cnt_in, uint64_t* __restrict__ own_out, int32_t* __restrict__ cnt_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,6 +93,8 @@ __global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, in
     uint64_t bits = mine_old;
     int c = cnt_in[i];
     const int ci = c;
+    const bool max_aware = iter >= kRelaxIters;
+    const int qmi = max_aware ? quad_max_counts(cnt_in, n, i) : 0;
     for (int a = 0; a < k; ++a) {
         const int32_t j = A[a];
         if (j == (int32_t)i || (j >> 2) == (int32_t)(i >> 2)) continue;
@@ -91,7 +110,17 @@ __global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, in
         const int sh = in_tile ? 0 : 16, one = 1 << sh;
         const int cii = (ci >> sh) & 0xffff, cj = (cnt_in[j] >> sh) & 0xffff;
         const int c_owner = i_owns ? cii : cj, c_other = i_owns ? cj : cii;
-        const bool flip = (c_owner > c_other + 1) && ((pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
+        bool flip;
+        if (!max_aware) {
+            flip = (c_owner > c_other + 1) && ((pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
+        } else {
+            const int qmj = quad_max_counts(cnt_in, n, j);
+            const int m_i = (qmi >> sh) & 0xffff, m_j = (qmj >> sh) & 0xffff;
+            const int m_owner = i_owns ? m_i : m_j, m_other = i_owns ? m_j : m_i;
+            uint32_t h = pair_hash((uint32_t)i, (uint32_t)j) ^ ((uint32_t)iter * 0x9E3779B9u);
+            h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15;
+            flip = ((c_owner > c_other + 1) || (c_owner == m_owner && c_owner > c_other && c_other + 1 <= m_other)) && ((h & 3u) == 0u);
+        }
         if (flip) {
             if (i_owns) { bits &= ~(1ull << a); c -= one; }
             else { bits |= 1ull << a; c += one; }
@@ -125,20 +154,23 @@ __device__ __forceinline__ void plan_for_each_entry(const int32_t* __restrict__ 
     }
 }
 
-// record size of every quad in 16-byte units (R_loc / R_glob = longest in-tile / out-of-tile list of its spots)
+// record size of every quad in 16-byte units.  R_glob = longest out-of-tile list of its spots; an in-tile entry
+// may also sit in a free out-of-tile slot of its spot (addressed by its absolute row like the others), so
+// R_loc + R_glob only has to cover the longest combined list.
 __global__ void plan_size_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int64_t nquads, const uint64_t* __restrict__ own,
                                  int32_t* __restrict__ qsize, int32_t* __restrict__ qrounds) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nquads) return;
-    int rl = 0, rg = 0;
+    int rt = 0, rg = 0;
     for (int t = 0; t < 4; ++t) {
         const int64_t i = 4 * q + t;
         if (i >= n) break;
         int cl = 0, cg = 0;
         plan_for_each_entry(nbr, k, i, own[i], [&](int32_t, float, bool in_tile) { if (in_tile) ++cl; else ++cg; });
-        rl = cl > rl ? cl : rl;
+        rt = cl + cg > rt ? cl + cg : rt;
         rg = cg > rg ? cg : rg;
     }
+    const int rl = rt - rg;                                             // >= 0: rt >= every cg
     qrounds[q] = rl | (rg << 8);
     qsize[q] = kPlanHdrUnits + kPlanRoundUnits * (rl + rg);
 }
@@ -230,6 +262,13 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int
             }
             csum += c;
         });
+        if (sl > RL) {                                                  // in-tile entries beyond R_loc: free out-of-tile slots
+            int seen = 0;
+            plan_for_each_entry(nbr, k, i, own[i], [&](int32_t j, float c, bool in_tile) {
+                if (!in_tile) return;
+                if (seen++ >= RL && sg < RG) { glob[sg * 8 + t] = j; reinterpret_cast<float*>(glob)[sg * 8 + 4 + t] = c; ++sg; }
+            });
+        }
         recf[8 + t] = csum;
         recf[12 + t] = (float)(indeg[i] - k);                               // column sum of the adjacency minus its row sum
         if (indeg[i] != k) irregular = 1;
@@ -314,7 +353,9 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
     CHR_CUDA(cudaMemsetAsync(indeg, 0, (size_t)n_spots * 4, st));
     plan_init_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, own[0], cnt[0], indeg);
     int cur = 0;
-    for (int it = 0; it < kRelaxIters; ++it, cur ^= 1)
+    const char* env_sweeps = getenv("CHR_PLAN_SWEEPS");   /* experiment hook */
+    const int n_sweeps = env_sweeps ? atoi(env_sweeps) : kRelaxIters + kRelaxMaxIters;
+    for (int it = 0; it < n_sweeps; ++it, cur ^= 1)
         plan_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
     plan_size_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, nquads, own[cur], qsize, qrounds);
     plan_scan_kernel<<<1, 1024, 0, st>>>(qsize, nquads, off, 1 + kPlanOffPad);
