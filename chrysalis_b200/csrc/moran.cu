@@ -451,10 +451,7 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             const bool irregular = (h0.x >> 30) & 1;                  // some indeg != k in this quad
             Row4 x[4], s[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                x[t] = lds_row4(tile_lane + (uint32_t)(4 * ql + t) * (kGeneTile * 4));
-                s[t].a = s[t].b = z2;
-            }
+            for (int t = 0; t < 4; ++t) s[t].a = s[t].b = z2;
             // the first out-of-tile round is issued before the in-tile rounds so its latency hides behind them
             const uint32_t grec = rec + 16 * (kPlanHdrUnits + kPlanRoundUnits * RL);
             float cg[4] = {0.f, 0.f, 0.f, 0.f};
@@ -469,6 +466,22 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                 cg[0] = cf.x; cg[1] = cf.y; cg[2] = cf.z; cg[3] = cf.w;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) ldg_row4_if(vg[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cg[t]);
+            }
+            // a second out-of-tile round goes out now as well, into the registers the quad's own rows take later
+            if (RG > 1) {
+                const int4 rows = lds_i4(grec + 32);
+                const float4 cf = lds_f4(grec + 48);
+                int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+                if (MAPPED) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) rr[t] = __ldg(row_map + rr[t]);
+                }
+                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    x[t].a = x[t].b = z2;
+                    ldg_row4_if(x[t], base + (uint64_t)(uint32_t)rr[t] * row_bytes, cc[t]);
+                }
             }
             // in-tile rounds; the plan words of round r + 1 are fetched while round r is multiplied (the record is
             // followed by at least one more 32-byte unit inside the staged slice or its padding)
@@ -488,8 +501,14 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             if (RG > 0) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) r4_fmac(s[t], cg[t], vg[t]);
+                if (RG > 1) {
+                    const float4 cf = lds_f4(grec + 48);
+                    const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], x[t]);
+                }
 #pragma unroll 1
-                for (int r = 1; r < RG; ++r) {
+                for (int r = 2; r < RG; ++r) {
                     const int4 rows = lds_i4(grec + 32 * r);
                     const float4 cf = lds_f4(grec + 32 * r + 16);
                     int rr[4] = {rows.x, rows.y, rows.z, rows.w};
@@ -504,6 +523,8 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                     for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], vg[t]);
                 }
             }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) x[t] = lds_row4(tile_lane + (uint32_t)(4 * ql + t) * (kGeneTile * 4));
             const float4 cs = lds_f4(rec + 32);                       // csum
             const float4 dg = lds_f4(rec + 48);                       // indeg - k
             if (SHIFT) {
