@@ -292,6 +292,18 @@ __device__ __forceinline__ void ldg_row4_if(Row4& v, const char* p, float c) {
         : "+l"(v.a), "+l"(v.b)
         : "l"(p), "f"(c));
 }
+// in-tile list slot: byte offset of the row inside the stage, negative for a padded slot (load skipped)
+__device__ __forceinline__ void lds_row4_ifpos(Row4& v, uint32_t base, int off) {
+    asm volatile("{\n"
+        ".reg .pred q;\n"
+        ".reg .b32 a;\n"
+        "setp.ge.s32 q, %3, 0;\n"
+        "add.u32 a, %2, %3;\n"
+        "@q ld.shared.v2.b64 {%0, %1}, [a];\n"
+        "}\n"
+        : "+l"(v.a), "+l"(v.b)
+        : "r"(base), "r"(off));
+}
 // 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -440,11 +452,13 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
         const int q0 = (t_begin + c) * kTileQuads;
         const int nq = nquads - q0 < kTileQuads ? nquads - q0 : kTileQuads;
         const int off0 = lds_i32(s_off);
+        static_assert(kTileQuadsPerWarp == 2, "both record offsets of the warp are fetched up front");
+        const int offq0 = lds_i32(s_off + 8 * warp), offq1 = lds_i32(s_off + 8 * warp + 4);
 #pragma unroll 1
         for (int qi = 0; qi < kTileQuadsPerWarp; ++qi) {
             const int ql = warp * kTileQuadsPerWarp + qi;
             if (ql >= nq) break;
-            const uint32_t rec = s_rec + (uint32_t)(lds_i32(s_off + 4 * ql) - off0) * 16;
+            const uint32_t rec = s_rec + (uint32_t)((qi == 0 ? offq0 : offq1) - off0) * 16;
             const int4 h0 = lds_i4(rec);
             const float4 h1 = lds_f4(rec + 16);                       // c12 c13 c23 -
             const int RL = h0.x & 0xff, RG = (h0.x >> 8) & 0xff, nvalid = (h0.x >> 16) & 0xff;
@@ -453,7 +467,8 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
 #pragma unroll
             for (int t = 0; t < 4; ++t) s[t].a = s[t].b = z2;
             // the first out-of-tile round is issued before the in-tile rounds so its latency hides behind them
-            const uint32_t grec = rec + 16 * (kPlanHdrUnits + kPlanRoundUnits * RL);
+            const uint32_t grec = rec + 16 * kPlanHdrUnits;            // out-of-tile rounds first, then the in-tile rounds
+            const uint32_t lrec = grec + 16 * kPlanRoundUnits * RG;
             float cg[4] = {0.f, 0.f, 0.f, 0.f};
             if (RG > 0) {
                 const int4 rows = lds_i4(grec);
@@ -485,16 +500,15 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
             }
             // in-tile rounds; the plan words of round r + 1 are fetched while round r is multiplied (the record is
             // followed by at least one more 32-byte unit inside the staged slice or its padding)
-            int4 offs = lds_i4(rec + 16 * kPlanHdrUnits);
-            float4 cf = lds_f4(rec + 16 * (kPlanHdrUnits + 1));
+            int4 offs = lds_i4(lrec);
 #pragma unroll 1
             for (int r = 0; r < RL; ++r) {
                 const int oo[4] = {offs.x, offs.y, offs.z, offs.w};
-                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+                const float4 cf = lds_f4(lrec + 32 * r + 16);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) lds_row4_if(va[t], tile_lane + (uint32_t)oo[t], cc[t]);
-                offs = lds_i4(rec + 16 * (kPlanHdrUnits + 2 * r + 2));
-                cf = lds_f4(rec + 16 * (kPlanHdrUnits + 2 * r + 3));
+                for (int t = 0; t < 4; ++t) lds_row4_ifpos(va[t], tile_lane, oo[t]);
+                offs = lds_i4(lrec + 32 * r + 32);
+                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], va[t]);
             }

@@ -79,12 +79,20 @@ __device__ __forceinline__ int quad_max_counts(const int32_t* __restrict__ cnt, 
         }
     return ml | (mg << 16);
 }
+// longest combined list among the spots of the quad of spot i
+__device__ __forceinline__ int quad_max_total(const int32_t* __restrict__ cnt, int64_t n, int64_t i) {
+    int m = 0;
+    const int64_t q = i & ~(int64_t)3;
+    for (int t = 0; t < 4; ++t)
+        if (q + t < n) m = max(m, (cnt[q + t] & 0xffff) + ((cnt[q + t] >> 16) & 0xffff));
+    return m;
+}
 
 // one Jacobi sweep of owner balancing: a mutual pair moves to the other endpoint when that lowers
 // the larger of the two list lengths; both endpoints evaluate the same rule on the same data.
 // Sweeps >= kRelaxIters also move an entry one step downhill when its owner is the longest list of its
 // quad and the receiver stays within its own quad's longest: the kernel pays max-over-the-quad rounds.
-__global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, const uint64_t* __restrict__ own_in,
+__global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, int k, int iter, int combined, const uint64_t* __restrict__ own_in,
                                   const int32_t* __restrict__ cnt_in, uint64_t* __restrict__ own_out, int32_t* __restrict__ cnt_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -111,7 +119,20 @@ __global__ void plan_relax_kernel(const int32_t* __restrict__ nbr, int64_t n, in
         const int cii = (ci >> sh) & 0xffff, cj = (cnt_in[j] >> sh) & 0xffff;
         const int c_owner = i_owns ? cii : cj, c_other = i_owns ? cj : cii;
         bool flip;
-        if (!max_aware) {
+        if (combined && max_aware) {
+            // combined lists (an in-tile entry can sit in an out-of-tile slot): balance the totals, keep every
+            // out-of-tile list within `combined` entries
+            const int cnt_j = cnt_in[j];
+            const int ti = (ci & 0xffff) + ((ci >> 16) & 0xffff), tj = (cnt_j & 0xffff) + ((cnt_j >> 16) & 0xffff);
+            const int t_owner = i_owns ? ti : tj, t_other = i_owns ? tj : ti;
+            const int mi = quad_max_total(cnt_in, n, i), mj = quad_max_total(cnt_in, n, j);
+            const int m_owner = i_owns ? mi : mj, m_other = i_owns ? mj : mi;
+            const int g_other = ((i_owns ? cnt_j : ci) >> 16) & 0xffff;
+            uint32_t h = pair_hash((uint32_t)i, (uint32_t)j) ^ ((uint32_t)iter * 0x9E3779B9u);
+            h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15;
+            flip = ((t_owner > t_other + 1) || (t_owner == m_owner && t_owner > t_other && t_other + 1 <= m_other)) &&
+                   (in_tile || g_other + 1 <= combined) && ((h & 3u) == 0u);
+        } else if (!max_aware) {
             flip = (c_owner > c_other + 1) && ((pair_hash((uint32_t)i, (uint32_t)j) >> (iter + 1)) & 1u);
         } else {
             const int qmj = quad_max_counts(cnt_in, n, j);
@@ -236,11 +257,11 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ nbr, int64_t n, int
     for (int w = 1; w < kPlanHdrUnits * 4; ++w) recf[w] = 0.f;
     int irregular = 0;
     const int tile_row0 = (int)((4 * q) % kTileSpots);                 // row of the quad's first spot inside its tile
-    int32_t* loc = rec + kPlanHdrUnits * 4;
-    int32_t* glob = loc + RL * kPlanRoundUnits * 4;
+    int32_t* glob = rec + kPlanHdrUnits * 4;                           // out-of-tile rounds first (fixed position), then in-tile
+    int32_t* loc = glob + RG * kPlanRoundUnits * 4;
     for (int r = 0; r < RL; ++r)
         for (int t = 0; t < 4; ++t) {
-            loc[r * 8 + t] = (tile_row0 + (t < nvalid ? t : 0)) * (kGeneTile * 4);   // padding: own row, coefficient 0
+            loc[r * 8 + t] = (int32_t)0x80000000;                      // padding: negative offset (load skipped), coefficient 0
             loc[r * 8 + 4 + t] = 0;
         }
     for (int r = 0; r < RG; ++r)
@@ -355,8 +376,10 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
     int cur = 0;
     const char* env_sweeps = getenv("CHR_PLAN_SWEEPS");   /* experiment hook */
     const int n_sweeps = env_sweeps ? atoi(env_sweeps) : kRelaxIters + kRelaxMaxIters;
+    const char* env_mode = getenv("CHR_PLAN_COMBINED");     /* experiment hook */
+    const int combined = env_mode ? atoi(env_mode) : 0;
     for (int it = 0; it < n_sweeps; ++it, cur ^= 1)
-        plan_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
+        plan_relax_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, it, combined, own[cur], cnt[cur], own[cur ^ 1], cnt[cur ^ 1]);
     plan_size_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, nquads, own[cur], qsize, qrounds);
     plan_scan_kernel<<<1, 1024, 0, st>>>(qsize, nquads, off, 1 + kPlanOffPad);
     plan_header_kernel<<<1, 256, 0, st>>>(off, n_spots, k, nquads, hdr, off_bytes, rec_bytes);

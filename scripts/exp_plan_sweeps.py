@@ -10,6 +10,11 @@ order = dv.hilbert_order(xy, bbox)
 nbr = dv.knn_build(xy[order].contiguous(), k, bbox)
 X = torch.rand((n, dv.dense_ld(g)), device="cuda")
 for sweeps in sys.argv[1:]:
+    if ":" in sweeps:
+        sweeps, comb = sweeps.split(":")
+        os.environ["CHR_PLAN_COMBINED"] = comb
+    else:
+        os.environ.pop("CHR_PLAN_COMBINED", None)
     os.environ["CHR_PLAN_SWEEPS"] = sweeps
     plan = dv.moran_plan(nbr)
     for _ in range(3):
@@ -19,12 +24,5 @@ for sweeps in sys.argv[1:]:
         dv.moran_dense(X, nbr, g, plan=plan, timing=True)
         torch.cuda.synchronize()
         ms.append(dv.last_kernel_ms())
-    print(json.dumps({"sweeps": int(sweeps), "total_units": plan.total_units, "rounds_per_quad": (plan.total_units / ((n + 3) // 4) - 4) / 2,
+    print(json.dumps({"sweeps": int(sweeps), "combined": os.environ.get("CHR_PLAN_COMBINED"), "total_units": plan.total_units, "rounds_per_quad": (plan.total_units / ((n + 3) // 4) - 4) / 2,
                       "kernel_ms_2304": round(float(np.median(ms)), 4)}))
-# plan build time per sweep count
-for sweeps in sys.argv[1:]:
-    os.environ["CHR_PLAN_SWEEPS"] = sweeps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dv.moran_plan(nbr); torch.cuda.synchronize()
-    e0.record(); dv.moran_plan(nbr); e1.record(); torch.cuda.synchronize()
-    print(json.dumps({"sweeps": int(sweeps), "plan_build_ms": round(e0.elapsed_time(e1), 3)}))
