@@ -447,18 +447,21 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
     for (int c = 0; c < my_compute_tiles; ++c) {
         mbar_wait_u32(full_bar + 8 * sidx, phase);
         const uint32_t st = smem0 + sidx * stage_bytes;
-        const uint32_t tile_lane = st + lane * 16;
+        uint32_t tile_lane = st + lane * 16;
         const uint32_t s_off = st + kTileBytes, s_rec = st + kTileBytes + kTileOffBytes;
         const int q0 = (t_begin + c) * kTileQuads;
         const int nq = nquads - q0 < kTileQuads ? nquads - q0 : kTileQuads;
         const int off0 = lds_i32(s_off);
+        // per-tile addresses stay in registers (otherwise they are re-derived from the kernel arguments in every quad)
+        uint32_t s_recbase = s_rec - (uint32_t)off0 * 16;
+        asm volatile("" : "+r"(tile_lane), "+r"(s_recbase));
         static_assert(kTileQuadsPerWarp == 2, "both record offsets of the warp are fetched up front");
         const int offq0 = lds_i32(s_off + 8 * warp), offq1 = lds_i32(s_off + 8 * warp + 4);
 #pragma unroll 1
         for (int qi = 0; qi < kTileQuadsPerWarp; ++qi) {
             const int ql = warp * kTileQuadsPerWarp + qi;
             if (ql >= nq) break;
-            const uint32_t rec = s_rec + (uint32_t)((qi == 0 ? offq0 : offq1) - off0) * 16;
+            const uint32_t rec = s_recbase + (uint32_t)(qi == 0 ? offq0 : offq1) * 16;
             const int4 h0 = lds_i4(rec);
             const float4 h1 = lds_f4(rec + 16);                       // c12 c13 c23 -
             const int RL = h0.x & 0xff, RG = (h0.x >> 8) & 0xff, nvalid = (h0.x >> 16) & 0xff;
@@ -512,6 +515,26 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
 #pragma unroll
                 for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], va[t]);
             }
+            // own rows, pilot shift and the pairs inside the quad
+            auto own_rows = [&]() {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x[t] = lds_row4(tile_lane + (uint32_t)(4 * ql + t) * (kGeneTile * 4));
+                if (SHIFT) {
+                    const float4 cs = lds_f4(rec + 32);               // csum
+                    const float ncs[4] = {-cs.x, -cs.y, -cs.z, -cs.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        r4_sub(x[t], p);
+                        r4_fmac(s[t], ncs[t], p);
+                    }
+                }
+                r4_fmac(s[0], __int_as_float(h0.y), x[1]);
+                r4_fmac(s[0], __int_as_float(h0.z), x[2]);
+                r4_fmac(s[0], __int_as_float(h0.w), x[3]);
+                r4_fmac(s[1], h1.x, x[2]);
+                r4_fmac(s[1], h1.y, x[3]);
+                r4_fmac(s[2], h1.z, x[3]);
+            };
             if (RG > 0) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) r4_fmac(s[t], cg[t], vg[t]);
@@ -537,25 +560,8 @@ moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int nc
                     for (int t = 0; t < 4; ++t) r4_fmac(s[t], cc[t], vg[t]);
                 }
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) x[t] = lds_row4(tile_lane + (uint32_t)(4 * ql + t) * (kGeneTile * 4));
-            const float4 cs = lds_f4(rec + 32);                       // csum
+            own_rows();
             const float4 dg = lds_f4(rec + 48);                       // indeg - k
-            if (SHIFT) {
-                const float ncs[4] = {-cs.x, -cs.y, -cs.z, -cs.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    r4_sub(x[t], p);
-                    r4_fmac(s[t], ncs[t], p);
-                }
-            }
-            // pairs inside the quad
-            r4_fmac(s[0], __int_as_float(h0.y), x[1]);
-            r4_fmac(s[0], __int_as_float(h0.z), x[2]);
-            r4_fmac(s[0], __int_as_float(h0.w), x[3]);
-            r4_fmac(s[1], h1.x, x[2]);
-            r4_fmac(s[1], h1.y, x[3]);
-            r4_fmac(s[2], h1.z, x[3]);
             const float dgs[4] = {dg.x, dg.y, dg.z, dg.w};
             auto accumulate = [&](int t) {
                 r4_add(l1[0], x[t]);
