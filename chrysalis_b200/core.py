@@ -89,15 +89,17 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     main = torch.cuda.current_stream() if torch.cuda.is_available() else None
     side = _side_stream()
     dense_buf = None
+    # core.py:61-62  coordinates (x, -y): uploaded BEFORE the counts, otherwise this small copy queues behind the
+    # multi-GB transfer on the copy engine and the side-stream work below cannot start until the upload has finished
+    pts = np.array(spatial, dtype=np.float64, copy=True)
+    pts[:, 1] = pts[:, 1] * -1
+    xy = dv.to_device(pts, torch.float64)
     if side is not None:
         dense_buf = torch.empty((n, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
         side.wait_stream(main)
     csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])      # asynchronous host -> device copy on the current stream
     with _stream_ctx(side):
-        # core.py:61-65  kNN weights on (x, -y), row-standardised
-        pts = np.array(spatial, dtype=np.float64, copy=True)
-        pts[:, 1] = pts[:, 1] * -1
-        xy = dv.to_device(pts, torch.float64)
+        # core.py:64-65  kNN weights, row-standardised
         bbox = dv.spatial_bbox(xy)
         order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
         rank_of = torch.empty_like(order)

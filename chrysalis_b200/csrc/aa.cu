@@ -22,6 +22,10 @@ constexpr int kAaMaxA = 64;     // archetypes
 constexpr int kAaMaxD = 64;     // embedding dimensions
 constexpr int kAaMaxP = kAaMaxD + 2;   // passive-set bound for the beta problems (rank of [X, M] <= d + 1)
 
+// measurement aid (scripts/aa_breakdown.py): [0] spots solved by warm alpha steps, [1] of those through the general
+// active-set path, [2] warps with at least one such spot, [3] warps
+__device__ unsigned long long g_aa_stats[4];
+
 // ---- small dense helpers (per thread, column-major n x n in `a`, n <= 66) ----------------------
 // Cholesky solve of the SPD system  H s = r  restricted to the index list `idx` (size np) of a
 // full matrix `full` with leading dimension ld.  L is scratch (np*(np+1)/2).  Returns false if not SPD.
@@ -224,7 +228,19 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
             }
         int idx[kFastP];
         double sol[kFastP];
-        if (warm && na <= 32 && nnls_warm_small(G, c, na, mask, 1e-12 * fmax(cmax, 1e-300), idx, sol)) {
+        const bool fast = warm && na <= 32 && nnls_warm_small(G, c, na, mask, 1e-12 * fmax(cmax, 1e-300), idx, sol);
+#ifdef CHR_AA_STATS
+        if (warm) {
+            const unsigned act = __activemask(), slow = __ballot_sync(act, !fast);
+            if ((threadIdx.x & 31) == __ffs(act) - 1) {
+                atomicAdd(&g_aa_stats[0], (unsigned long long)__popc(act));
+                atomicAdd(&g_aa_stats[1], (unsigned long long)__popc(slow));
+                atomicAdd(&g_aa_stats[2], slow ? 1ull : 0ull);
+                atomicAdd(&g_aa_stats[3], 1ull);
+            }
+        }
+#endif
+        if (fast) {
             for (int a = 0; a < na; ++a) a_out[a] = 0.0;
             const int np = __popc(mask);
 #pragma unroll
@@ -261,6 +277,211 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
     for (int e = threadIdx.x; e < nacc; e += blockDim.x) part[(size_t)blockIdx.x * nacc + e] = acc[e];
 }
 
+// ---- alpha step for n_archetypes <= 16: branch-free masked Cholesky, one thread per spot --------------------
+// The active-set iteration of a spot is written so that every lane of a warp executes the same instruction
+// stream whatever its passive set P is: the least-squares problem on P is solved as the FULL NA x NA system
+//     G'_ij = G_ij  (i, j in P),   delta_ij otherwise;      rhs'_i = c_i (i in P), 0 otherwise
+// (NA = n_archetypes padded to a multiple of 4, padding rows are never passive), with a compile-time unrolled
+// Cholesky whose factor lives in shared memory as L[entry][thread] (conflict-free), the row being eliminated in
+// registers.  One loop iteration = one solve, then either "accept + KKT test + add the arg-max archetype" or
+// "step back to the feasible region + drop" (Lawson-Hanson, same tolerances as nnls_normal); lanes that have
+// converged idle.  A warm start (previous coefficients) usually needs 1-3 solves.  The minimiser is unique, so
+// this and nnls_normal agree to rounding.
+template <int NA>
+struct AlphaFixed {
+    static constexpr int kTri = NA * (NA + 1) / 2;
+    static constexpr int kThreads = 128;
+
+    // solve on the passive set `P` (bit mask); returns s (0 outside P); indices whose pivot collapses are dropped from P
+    static __device__ __forceinline__ void solve(const double* __restrict__ G, unsigned& P, const double (&c)[NA], double* __restrict__ Lt,
+                                                 double (&s)[NA]) {
+        double dinv[NA], y[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const bool mi = (P >> i) & 1u;
+            double row[NA];
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                double v = (mi && ((P >> j) & 1u)) ? G[i * NA + j] : 0.0;
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= row[k] * Lt[(j * (j + 1) / 2 + k) * kThreads];
+                row[j] = v * dinv[j];
+            }
+            const double gii = G[i * NA + i];
+            double v = mi ? gii : 1.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) v -= row[k] * row[k];
+            const bool ok = v > 1e-13 * gii || !mi;           // numerically dependent archetype: leave it out
+            if (!ok) P &= ~(1u << i);
+            v = ok ? v : 1.0;
+            dinv[i] = rsqrt(v);
+            double r = (mi && ok) ? c[i] : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                row[j] = ok ? row[j] : 0.0;
+                Lt[(i * (i + 1) / 2 + j) * kThreads] = row[j];
+                r -= row[j] * y[j];
+            }
+            y[i] = r * dinv[i];
+        }
+#pragma unroll
+        for (int i = NA - 1; i >= 0; --i) {
+            double v = y[i];
+#pragma unroll
+            for (int k = i + 1; k < NA; ++k) v -= Lt[(k * (k + 1) / 2 + i) * kThreads] * s[k];
+            s[i] = v * dinv[i];
+        }
+    }
+};
+
+template <int NA>
+__global__ void __launch_bounds__(128)
+aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Z, int na, double M, int warm,
+                      double* __restrict__ alphas, double* __restrict__ part /*[grid][na*na + na*d]*/, int region_doubles) {
+    using AF = AlphaFixed<NA>;
+    constexpr int T = AF::kThreads;
+    extern __shared__ double sh[];
+    double* G = sh;                        // NA x NA, identity on the padding
+    double* Zs = G + NA * NA;              // na x d
+    double* region = Zs + na * d;          // staged X rows -> Cholesky factors -> [alphas | X] rows of the CTA
+    (void)region_doubles;
+    const int tid = threadIdx.x;
+    const int nacc = na * na + na * d;
+    const int dpad = d | 1;                // odd row stride: conflict-free per-thread rows
+    const int64_t i_base = (int64_t)blockIdx.x * T;
+    const int nvalid = (int)((n - i_base) < (int64_t)T ? (n - i_base) : (int64_t)T);
+    for (int e = tid; e < na * d; e += T) Zs[e] = Z[e];
+    {   // the CTA's rows of X: one contiguous block, coalesced
+        const double* __restrict__ src = X + i_base * d;
+        for (int e = tid; e < nvalid * d; e += T) region[(e / d) * dpad + (e % d)] = src[e];
+    }
+    __syncthreads();
+    for (int e = tid; e < NA * NA; e += T) {
+        const int a = e / NA, b = e % NA;
+        double v = a == b ? 1.0 : 0.0;
+        if (a < na && b < na) {
+            v = M * M;
+            for (int t = 0; t < d; ++t) v += Zs[a * d + t] * Zs[b * d + t];
+        }
+        G[e] = v;
+    }
+    const bool valid = tid < nvalid;
+    double c[NA], x[NA], s[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) { c[a] = a < na ? M * M : 0.0; x[a] = 0.0; s[a] = 0.0; }
+    if (valid) {
+        const double* __restrict__ xr = region + tid * dpad;
+        for (int t = 0; t < d; ++t) {
+            const double xv = xr[t];
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                if (a < na) c[a] += Zs[a * d + t] * xv;
+        }
+    }
+    unsigned P = 0;
+    double cmax = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) cmax = fmax(cmax, fabs(c[a]));
+    if (valid && warm) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+            if (a < na) {
+                x[a] = alphas[(i_base + tid) * na + a];
+                if (x[a] > 0.0) P |= 1u << a; else x[a] = 0.0;
+            }
+    }
+    __syncthreads();                       // G complete; every thread is done with its staged row (the factors go there)
+    const double tol = 1e-12 * fmax(cmax, 1e-300), tiny = 1e-15 * fmax(1.0, cmax);
+    double* Lt = region + tid;
+    bool active = valid;
+    for (int it = 0; it < 8 * NA && __any_sync(0xffffffffu, active); ++it) {
+        unsigned Pn = P;
+        AF::solve(G, Pn, c, Lt, s);
+        if (active) {
+            if (Pn != P) {                 // collapsed pivots: those archetypes leave the passive set
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+                    if (((P ^ Pn) >> a) & 1u) x[a] = 0.0;
+                P = Pn;
+            }
+            bool feas = true;
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                if ((P >> a) & 1u) feas = feas && s[a] > 0.0;
+            if (feas) {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) x[a] = ((P >> a) & 1u) ? s[a] : 0.0;
+            } else {
+                double alpha = 1e300;
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+                    if (((P >> a) & 1u) && s[a] <= 0.0) alpha = fmin(alpha, x[a] / (x[a] - s[a]));
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+                    if ((P >> a) & 1u) {
+                        x[a] += alpha * (s[a] - x[a]);
+                        if (x[a] <= tiny && s[a] <= 0.0) { x[a] = 0.0; P &= ~(1u << a); }
+                    }
+            }
+            if (feas) {                    // KKT: the largest gradient outside the passive set joins it, lowest index on ties
+                int jbest = -1;
+                double wbest = tol;
+#pragma unroll
+                for (int j = 0; j < NA; ++j) {
+                    double w = c[j];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) w -= G[j * NA + a] * x[a];
+                    if (j < na && !((P >> j) & 1u) && w > wbest) { wbest = w; jbest = j; }
+                }
+                if (jbest < 0) active = false; else P |= 1u << jbest;
+            }
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) { x[a] = fmax(x[a], 0.0); sum += x[a]; }
+    const double inv = 1.0 / sum;
+    __syncthreads();                       // the factors are dead: the region becomes B = [alphas | X] (row = spot)
+    const int W = na + d;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+        if (a < na) region[tid * W + a] = valid ? x[a] * inv : 0.0;
+    {
+        const double* __restrict__ src = X + i_base * d;
+        for (int e = tid; e < T * d; e += T) region[(e / d) * W + na + (e % d)] = e < nvalid * d ? src[e] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < nvalid * na; e += T) alphas[i_base * na + e] = region[(e / na) * W + (e % na)];
+    // partial  A^T [A | X]  of the CTA (na x W), spots summed in order: every thread owns strips of 4 columns
+    const int nstrip = (W + 3) >> 2;
+    for (int e = tid; e < na * nstrip; e += T) {
+        const int a = e / nstrip, c0 = (e % nstrip) * 4;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        const int w1 = c0 + 1 < W ? c0 + 1 : c0, w2 = c0 + 2 < W ? c0 + 2 : c0, w3 = c0 + 3 < W ? c0 + 3 : c0;
+        for (int t = 0; t < T; ++t) {
+            const double* __restrict__ b = region + t * W;
+            const double av = b[a];
+            v0 += av * b[c0]; v1 += av * b[w1]; v2 += av * b[w2]; v3 += av * b[w3];
+        }
+        const double vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = c0 + q;
+            if (col < W) {
+                // same layout as aa_alpha_kernel: [na x na | na x d]
+                const int dst = col < na ? a * na + col : na * na + a * d + (col - na);
+                part[(size_t)blockIdx.x * nacc + dst] = vv[q];
+            }
+        }
+    }
+}
+
+static size_t aa_alpha_fixed_region_doubles(int NA, int na, int d) {
+    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128, xs = (size_t)128 * (d | 1), b = (size_t)128 * (na + d);
+    size_t r = tri > xs ? tri : xs;
+    return r > b ? r : b;
+}
+
 // fixed-order reduction of the per-CTA partials  A^T A | A^T X  in chunks of 64 CTAs (second level in aa_pinv_kernel)
 constexpr int kAaRedChunk = 64;
 __global__ void aa_partial_reduce_kernel(const double* __restrict__ part, int nparts, int nacc, double* __restrict__ part2) {
@@ -286,8 +507,11 @@ __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int 
     }
     for (int e = threadIdx.x; e < na * na; e += blockDim.x) Vv[e] = (e / na == e % na) ? 1.0 : 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // cyclic Jacobi (na <= 64: a few thousand rotations, serial is fine for a na x na matrix)
+    if (threadIdx.x < 32) {
+        // cyclic Jacobi by one warp: the rotation (p, q) is computed redundantly by every lane, its three element-wise
+        // updates (columns of S, rows of S, columns of V) are spread over the lanes - the same operations in the same
+        // order as a serial sweep
+        const int lane = threadIdx.x;
         for (int sweep = 0; sweep < 60; ++sweep) {
             double off = 0.0, diag = 0.0;
             for (int p = 0; p < na; ++p) { diag += S[p * na + p] * S[p * na + p]; for (int q = p + 1; q < na; ++q) off += S[p * na + q] * S[p * na + q]; }
@@ -295,25 +519,26 @@ __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int 
             for (int p = 0; p < na - 1; ++p)
                 for (int q = p + 1; q < na; ++q) {
                     const double apq = S[p * na + q];
-                    if (fabs(apq) < 1e-300) continue;
+                    if (fabs(apq) < 1e-300) continue;                 // uniform across the warp
                     const double theta = (S[q * na + q] - S[p * na + p]) / (2.0 * apq);
                     const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                     const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                    for (int k = 0; k < na; ++k) {
+                    __syncwarp();
+                    for (int k = lane; k < na; k += 32) {
                         const double skp = S[k * na + p], skq = S[k * na + q];
                         S[k * na + p] = c * skp - s * skq;
                         S[k * na + q] = s * skp + c * skq;
-                    }
-                    for (int k = 0; k < na; ++k) {
-                        const double spk = S[p * na + k], sqk = S[q * na + k];
-                        S[p * na + k] = c * spk - s * sqk;
-                        S[q * na + k] = s * spk + c * sqk;
-                    }
-                    for (int k = 0; k < na; ++k) {
                         const double vkp = Vv[k * na + p], vkq = Vv[k * na + q];
                         Vv[k * na + p] = c * vkp - s * vkq;
                         Vv[k * na + q] = s * vkp + c * vkq;
                     }
+                    __syncwarp();
+                    for (int k = lane; k < na; k += 32) {
+                        const double spk = S[p * na + k], sqk = S[q * na + k];
+                        S[p * na + k] = c * spk - s * sqk;
+                        S[q * na + k] = s * spk + c * sqk;
+                    }
+                    __syncwarp();
                 }
         }
     }
@@ -394,6 +619,80 @@ aa_beta_grad_kernel(const double* __restrict__ X, int64_t n, int d, double M, co
         }
     }
     (void)pidx;
+}
+
+// gradient pass for n_archetypes <= 16: the CTA's rows are staged in shared memory 256 at a time (coalesced) and every
+// thread evaluates all archetypes for its row in one sweep (X is read once per pass instead of once per archetype).
+// Same arithmetic per (row, archetype) and the same tie rule as aa_beta_grad_kernel: identical candidates.
+template <int MAXA>
+__global__ void __launch_bounds__(256)
+aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ R, int na,
+                          const BetaState* __restrict__ st, double* __restrict__ cand_w, int64_t* __restrict__ cand_i) {
+    if (st->all_done) return;
+    extern __shared__ double sh[];
+    const int dpad = d | 1;
+    double* Rs = sh;                                   // na x (d+1)
+    double* Xs = Rs + na * (d + 1);                    // 256 x dpad
+    double* red_w = Xs + 256 * dpad;                   // [8][MAXA]
+    int* red_i = reinterpret_cast<int*>(red_w + 8 * MAXA);   // [8][MAXA] offsets from i0
+    for (int e = threadIdx.x; e < na * (d + 1); e += 256) Rs[e] = R[e];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * 1024;
+    const int ncta = (int)((n - i0) < 1024 ? (n - i0) : 1024);
+    double bw[MAXA];
+    int bi[MAXA];
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) { bw[a] = -1e300; bi[a] = -1; }
+    for (int c0 = 0; c0 < ncta; c0 += 256) {
+        const int nrows = ncta - c0 < 256 ? ncta - c0 : 256;
+        __syncthreads();                               // previous chunk consumed (and Rs written, first time)
+        const double* __restrict__ src = X + (i0 + c0) * d;
+        for (int e = threadIdx.x; e < nrows * d; e += 256) Xs[(e / d) * dpad + (e % d)] = src[e];
+        __syncthreads();
+        if ((int)threadIdx.x < nrows) {
+            const double* __restrict__ x = Xs + threadIdx.x * dpad;
+            double v[MAXA];
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) v[a] = a < na ? M * Rs[a * (d + 1) + d] : 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double xv = x[t];
+#pragma unroll
+                for (int a = 0; a < MAXA; ++a)
+                    if (a < na) v[a] += xv * Rs[a * (d + 1) + t];
+            }
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a)
+                if (a < na && v[a] > bw[a]) { bw[a] = v[a]; bi[a] = c0 + (int)threadIdx.x; }
+        }
+    }
+    // arg-max per archetype over the CTA, lowest index wins ties
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) {
+        if (a < na) {
+            double w = bw[a];
+            int i = bi[a];
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ow = __shfl_xor_sync(0xffffffffu, w, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+                if (ow > w || (ow == w && oi >= 0 && (i < 0 || oi < i))) { w = ow; i = oi; }
+            }
+            if (lane == 0) { red_w[warp * MAXA + a] = w; red_i[warp * MAXA + a] = i; }
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < na) {
+        const int a = threadIdx.x;
+        double w = red_w[a];
+        int i = red_i[a];
+        for (int q = 1; q < 8; ++q) {
+            const double ow = red_w[q * MAXA + a];
+            const int oi = red_i[q * MAXA + a];
+            if (ow > w || (ow == w && oi >= 0 && (i < 0 || oi < i))) { w = ow; i = oi; }
+        }
+        const bool done = st->done[a] != 0;
+        cand_w[(size_t)blockIdx.x * na + a] = done ? -1e300 : w;
+        cand_i[(size_t)blockIdx.x * na + a] = (done || i < 0) ? -1 : i0 + i;
+    }
 }
 
 // least squares of [zhat_a, M] on the passive points P of archetype a (serial, lane 0 of its warp): steps back
@@ -546,10 +845,10 @@ __global__ void aa_beta_finish_kernel(const double* __restrict__ X, int d, int n
     }
 }
 
-// rss partials:  sum_i || x_i - sum_a alpha_ia Z_a ||^2
+// rss partials, rows read straight from global memory (fallback when the staged rows do not fit shared memory)
 __global__ void __launch_bounds__(256)
-aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ alphas, const double* __restrict__ Z,
-              int na, double* __restrict__ part) {
+aa_rss_direct_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ alphas, const double* __restrict__ Z,
+                     int na, double* __restrict__ part) {
     extern __shared__ double sh[];
     double* Zs = sh;
     __shared__ double red[32];
@@ -577,11 +876,64 @@ aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __re
     }
 }
 
-__global__ void aa_sum_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+// rss partials:  sum_i || x_i - sum_a alpha_ia Z_a ||^2.  The CTA's 256 rows of X and of alphas are contiguous blocks:
+// they are staged in shared memory with coalesced loads (odd row strides: conflict-free per-thread rows)
+__global__ void __launch_bounds__(256)
+aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ alphas, const double* __restrict__ Z,
+              int na, double* __restrict__ part) {
+    extern __shared__ double sh[];
+    const int dpad = d | 1, apad = na | 1;
+    double* Zs = sh;                       // na x d
+    double* Xs = Zs + na * d;              // 256 x dpad
+    double* As = Xs + 256 * dpad;          // 256 x apad
+    __shared__ double red[32];
+    const int64_t i_base = (int64_t)blockIdx.x * 256;
+    const int nvalid = (int)((n - i_base) < 256 ? (n - i_base) : 256);
+    for (int e = threadIdx.x; e < na * d; e += 256) Zs[e] = Z[e];
+    {
+        const double* __restrict__ src = X + i_base * d;
+        for (int e = threadIdx.x; e < nvalid * d; e += 256) Xs[(e / d) * dpad + (e % d)] = src[e];
+        const double* __restrict__ sa = alphas + i_base * na;
+        for (int e = threadIdx.x; e < nvalid * na; e += 256) As[(e / na) * apad + (e % na)] = sa[e];
+    }
+    __syncthreads();
+    double r = 0.0;
+    if ((int)threadIdx.x < nvalid) {
+        const double* __restrict__ x = Xs + threadIdx.x * dpad;
+        const double* __restrict__ al = As + threadIdx.x * apad;
+        for (int t = 0; t < d; ++t) {
+            double v = x[t];
+            for (int a = 0; a < na; ++a) v -= al[a] * Zs[a * d + t];
+            r += v * v;
+        }
+    }
+    r = warp_sum(r);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int p = 0; p < np; ++p) t += part[p];
-        *out = t;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) aa_sum_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
+    // fixed order: every thread sums a contiguous chunk, thread 0 adds the 256 chunk sums in order
+    __shared__ double red[256];
+    const int chunk = (np + 255) / 256;
+    const int p0 = threadIdx.x * chunk, p1 = p0 + chunk < np ? p0 + chunk : np;
+    double t = 0.0;
+    for (int p = p0; p < p1; ++p) t += part[p];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double u = 0.0;
+        for (int w = 0; w < 8; ++w) u += red[threadIdx.x * 8 + w];
+        // lanes hold consecutive groups of 8 chunks: a fixed binary tree over the 32 lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+        if (threadIdx.x == 0) *out = u;
     }
 }
 
@@ -772,7 +1124,21 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     timer_begin(CHR_FAMILY_AA, true, st);
     // ---- alphas
     const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc + 128 * na) * 8;
-    if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
+    if (na <= 16 && !getenv("CHR_AA_ALPHA_GENERAL")) {
+        const int NA = (na + 3) & ~3;
+        const size_t region = aa_alpha_fixed_region_doubles(NA, na, d);
+        const size_t smf = ((size_t)NA * NA + (size_t)na * d + region) * 8;
+#define CHR_ALPHA_FIXED(NAV)                                                                                              \
+    do {                                                                                                                  \
+        CHR_CUDA(cudaFuncSetAttribute(aa_alpha_fixed_kernel<NAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf)); \
+        aa_alpha_fixed_kernel<NAV><<<p.alpha_blocks, 128, smf, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part, (int)region); \
+    } while (0)
+        if (NA == 4) CHR_ALPHA_FIXED(4);
+        else if (NA == 8) CHR_ALPHA_FIXED(8);
+        else if (NA == 12) CHR_ALPHA_FIXED(12);
+        else CHR_ALPHA_FIXED(16);
+#undef CHR_ALPHA_FIXED
+    } else if (na <= 16) aa_alpha_kernel<16><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
     else if (na <= 32) {
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_alpha));
         aa_alpha_kernel<32><<<p.alpha_blocks, 128, sm_alpha, st>>>(X, n, d, Z, na, penalty_M, warm, alphas, part);
@@ -792,13 +1158,19 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, warm, R);
     if (warm) aa_beta_refit_kernel<<<1, 64, 0, st>>>(X, d, penalty_M, Zhat, na, bst, pidx, bcoef, R, scr);
     const size_t sm_grad = (size_t)na * (d + 1) * 8 + 32 * 8 + 32 * 8;
+    const size_t sm_gradf = ((size_t)na * (d + 1) + 256 * (size_t)(d | 1) + 8 * 16) * 8 + 8 * 16 * 4;
+    if (na <= 16 && sm_gradf > 48 * 1024)
+        CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
     const int max_pass = 3 * (d + 2) + 8;
     int passes = 0;
     int host_done = 0;
     while (passes < max_pass && !host_done) {
         const int batch = warm ? 2 : (passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4);   // cold: first look after a handful of passes
         for (int b = 0; b < batch && passes < max_pass; ++b, ++passes) {
-            aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
+            if (na <= 16)
+                aa_beta_grad_fixed_kernel<16><<<p.grad_blocks, 256, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+            else
+                aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
             aa_beta_update_kernel<<<(unsigned)ceil_div(na * 32, 256), 256, 0, st>>>(X, n, d, penalty_M, Zhat, na, p.grad_blocks, candw,
                                                                                  candi, bst, pidx, bcoef, R, scr);
             aa_beta_check_kernel<<<1, 32, 0, st>>>(bst, na);
@@ -810,10 +1182,27 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     if (beta_passes_out) *beta_passes_out = passes;
     aa_beta_finish_kernel<<<na, 64, 0, st>>>(X, d, na, bst, pidx, bcoef, Z);
     // ---- rss
-    aa_rss_kernel<<<p.rss_blocks, 256, (size_t)na * d * 8, st>>>(X, n, d, alphas, Z, na, rsspart);
-    aa_sum_kernel<<<1, 32, 0, st>>>(rsspart, p.rss_blocks, rss_out);
+    const size_t sm_rss = ((size_t)na * d + 256 * (size_t)(d | 1) + 256 * (size_t)(na | 1)) * 8;
+    if (sm_rss <= 160 * 1024) {
+        if (sm_rss > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_rss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rss));
+        aa_rss_kernel<<<p.rss_blocks, 256, sm_rss, st>>>(X, n, d, alphas, Z, na, rsspart);
+    } else {
+        aa_rss_direct_kernel<<<p.rss_blocks, 256, (size_t)na * d * 8, st>>>(X, n, d, alphas, Z, na, rsspart);
+    }
+    aa_sum_kernel<<<1, 256, 0, st>>>(rsspart, p.rss_blocks, rss_out);
     timer_end(CHR_FAMILY_AA, true, st);
     CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+// measurement aid, not part of the C ABI in include/
+int chr_debug_aa_stats(unsigned long long* out4, int reset) {
+    using namespace chr;
+    if (out4 && cudaMemcpyFromSymbol(out4, g_aa_stats, sizeof(unsigned long long) * 4) != cudaSuccess) return 2;
+    if (reset) {
+        const unsigned long long z[4] = {0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_aa_stats, z, sizeof(z)) != cudaSuccess) return 2;
+    }
     return 0;
 }
 

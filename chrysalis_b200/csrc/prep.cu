@@ -31,6 +31,38 @@ __global__ void csr_gene_nnz_rows_kernel(const int64_t* __restrict__ indptr, con
     }
 }
 
+// privatised variant: one histogram per CTA in shared memory (n_genes * 4 bytes), flat coalesced sweep over the
+// stored entries (nnz = indptr[n], read on the device), merged with one global atomic per gene and CTA
+__global__ void __launch_bounds__(1024)
+csr_gene_nnz_smem_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+                         int64_t n, int n_genes, int32_t* __restrict__ gene_nnz) {
+    extern __shared__ int32_t hist[];
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) hist[g] = 0;
+    __syncthreads();
+    const int64_t nnz = indptr[n];
+    const int64_t nvec = nnz >> 2;                                  // both arrays are 16-byte aligned (checked by the caller)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int4* __restrict__ idx4 = reinterpret_cast<const int4*>(indices);
+    const float4* __restrict__ dat4 = reinterpret_cast<const float4*>(data);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const int4 c = __ldcs(idx4 + v);
+        const float4 x = __ldcs(dat4 + v);
+        if (x.x > 0.f) atomicAdd(hist + c.x, 1);
+        if (x.y > 0.f) atomicAdd(hist + c.y, 1);
+        if (x.z > 0.f) atomicAdd(hist + c.z, 1);
+        if (x.w > 0.f) atomicAdd(hist + c.w, 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (nnz & 3)) {
+        const int64_t e = (nvec << 2) + threadIdx.x;
+        if (data[e] > 0.f) atomicAdd(hist + indices[e], 1);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
+        const int32_t h = hist[g];
+        if (h) atomicAdd(gene_nnz + g, h);
+    }
+}
+
 __global__ void csr_spot_totals_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                        const float* __restrict__ data, int64_t n, const int32_t* __restrict__ gene_col,
                                        double* __restrict__ totals) {
@@ -78,7 +110,15 @@ int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float*
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(indptr && indices && data && gene_nnz && n > 0 && n_genes > 0, "chr_csr_gene_nnz: bad arguments");
     CHR_CUDA(cudaMemsetAsync(gene_nnz, 0, (size_t)n_genes * sizeof(int32_t), st));
-    csr_gene_nnz_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n, gene_nnz);
+    const size_t hist_bytes = (size_t)n_genes * sizeof(int32_t);
+    const bool aligned = (((uintptr_t)indices | (uintptr_t)data) & 15) == 0;
+    if (aligned && hist_bytes <= 200 * 1024) {
+        if (hist_bytes > 48 * 1024)
+            CHR_CUDA(cudaFuncSetAttribute(csr_gene_nnz_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+        csr_gene_nnz_smem_kernel<<<kNumSMs, 1024, hist_bytes, st>>>(indptr, indices, data, n, (int)n_genes, gene_nnz);
+    } else {
+        csr_gene_nnz_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n, gene_nnz);
+    }
     CHR_LAUNCH_CHECK();
     return 0;
 }

@@ -1,12 +1,13 @@
 #!/bin/bash
-# builds ab_libs/<name>.so = the library with moran.cu compiled with extra flags (experiment macros).  usage: build_variant.sh name "-DEXP_X=1"
+# builds ab_libs/<name>.so = the library with ONE source compiled with extra flags (experiment macros).
+# usage: build_variant.sh name "-DEXP_X=1" [source-stem, default moran]; select it with CHRYSALIS_B200_LIB=ab_libs/<name>.so
 set -e
-NAME=$1; EXTRA=$2
+NAME=$1; EXTRA=$2; SRC=${3:-moran}
 cd "$(dirname "$0")/../chrysalis_b200/csrc"
 mkdir -p ../../ab_libs build
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-$NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr -Xptxas -v $EXTRA -c moran.cu -o build/var_moran_$NAME.o 2> build/moran_$NAME.log
-grep -A1 "moran_tile_kernelILb0ELb1ELb0E" build/moran_$NAME.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo
-OBJS=$(ls build/*.o | grep -v "build/moran.o\|build/var_")
-$NVCC $ARCH -shared -o ../../ab_libs/$NAME.so $OBJS build/var_moran_$NAME.o -lcudart_static -ldl -lrt -lpthread
+$NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr -Xptxas -v $EXTRA -c $SRC.cu -o build/var_${SRC}_$NAME.o 2> build/${SRC}_$NAME.log
+if [ "$SRC" = moran ]; then grep -A1 "moran_tile_kernelILb0ELb1ELb0E" build/moran_$NAME.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo; fi
+OBJS=$(ls build/*.o | grep -v "build/$SRC.o\|build/var_")
+$NVCC $ARCH -shared -o ../../ab_libs/$NAME.so $OBJS build/var_${SRC}_$NAME.o -lcudart_static -ldl -lrt -lpthread

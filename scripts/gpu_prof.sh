@@ -5,9 +5,9 @@ KRE=${2:-moran_sym}
 EXTRA=${3:-}
 OUT=gpurun_out
 mkdir -p $OUT
-NCUCMD="python bench.py --g 2304 --steps 3 --warmup 3 --no-e2e --no-cpu $EXTRA"
+NCUCMD="python bench.py --g 2304 --steps 3 --warmup 3 --no-e2e --no-cpu --no-pipeline $EXTRA"
 $NCUCMD > $OUT/plain_$TAG.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'moran|sym_' -s 48 -c 48 --csv --log-file $OUT/launches_$TAG.csv $NCUCMD > $OUT/ncu_list_$TAG.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'moran|sym_' -c 200 --csv --log-file $OUT/launches_$TAG.csv $NCUCMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?" | tee -a $OUT/summary_$TAG.txt
 $NCUCMD > $OUT/plain2_$TAG.log 2>&1 && \
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 4 -c 1 -f -o $OUT/moran_$TAG $NCUCMD > $OUT/ncu_full_$TAG.log 2>&1
