@@ -277,6 +277,26 @@ aa_alpha_kernel(const double* __restrict__ X, int64_t n, int d, const double* __
     for (int e = threadIdx.x; e < nacc; e += blockDim.x) part[(size_t)blockIdx.x * nacc + e] = acc[e];
 }
 
+// stage `nrows` contiguous rows of `d` doubles into shared-memory rows of stride `ld`: flat coalesced sweep with 8-byte
+// cp.async (everything in flight at once, no registers; (row, column) advance incrementally - no division in the loop).
+// The caller waits with stage_wait() and a CTA barrier.
+__device__ __forceinline__ void stage_rows(double* __restrict__ dst, int ld, const double* __restrict__ src, int d, int nrows) {
+    const int T = blockDim.x, total = nrows * d;
+    const int q = T / d, rm = T - q * d;
+    int row = threadIdx.x / d, col = threadIdx.x - row * d;
+    for (int e = threadIdx.x; e < total; e += T) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + row * ld + col)), "l"(src + e)
+                     : "memory");
+        col += rm;
+        row += q;
+        if (col >= d) { col -= d; ++row; }
+    }
+}
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---- alpha step for n_archetypes <= 16: branch-free masked Cholesky, one thread per spot --------------------
 // The active-set iteration of a spot is written so that every lane of a warp executes the same instruction
 // stream whatever its passive set P is: the least-squares problem on P is solved as the FULL NA x NA system
@@ -351,10 +371,8 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
     const int64_t i_base = (int64_t)blockIdx.x * T;
     const int nvalid = (int)((n - i_base) < (int64_t)T ? (n - i_base) : (int64_t)T);
     for (int e = tid; e < na * d; e += T) Zs[e] = Z[e];
-    {   // the CTA's rows of X: one contiguous block, coalesced
-        const double* __restrict__ src = X + i_base * d;
-        for (int e = tid; e < nvalid * d; e += T) region[(e / d) * dpad + (e % d)] = src[e];
-    }
+    stage_rows(region, dpad, X + i_base * d, d, nvalid);   // the CTA's rows of X: one contiguous block
+    stage_wait();
     __syncthreads();
     for (int e = tid; e < NA * NA; e += T) {
         const int a = e / NA, b = e % NA;
@@ -446,12 +464,16 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
 #pragma unroll
     for (int a = 0; a < NA; ++a)
         if (a < na) region[tid * W + a] = valid ? x[a] * inv : 0.0;
-    {
-        const double* __restrict__ src = X + i_base * d;
-        for (int e = tid; e < T * d; e += T) region[(e / d) * W + na + (e % d)] = e < nvalid * d ? src[e] : 0.0;
-    }
+    stage_rows(region + na, W, X + i_base * d, d, nvalid);
+    for (int r = nvalid + (tid >> 5); r < T; r += T >> 5)          // rows past the end of the matrix contribute zeros
+        for (int t = tid & 31; t < d; t += 32) region[r * W + na + t] = 0.0;
+    stage_wait();
     __syncthreads();
-    for (int e = tid; e < nvalid * na; e += T) alphas[i_base * na + e] = region[(e / na) * W + (e % na)];
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < nvalid; r += T >> 5)
+            for (int a = lane; a < na; a += 32) alphas[(i_base + r) * na + a] = region[r * W + a];
+    }
     // partial  A^T [A | X]  of the CTA (na x W), spots summed in order: every thread owns strips of 4 columns
     const int nstrip = (W + 3) >> 2;
     for (int e = tid; e < na * nstrip; e += T) {
@@ -621,33 +643,35 @@ aa_beta_grad_kernel(const double* __restrict__ X, int64_t n, int d, double M, co
     (void)pidx;
 }
 
-// gradient pass for n_archetypes <= 16: the CTA's rows are staged in shared memory 256 at a time (coalesced) and every
-// thread evaluates all archetypes for its row in one sweep (X is read once per pass instead of once per archetype).
-// Same arithmetic per (row, archetype) and the same tie rule as aa_beta_grad_kernel: identical candidates.
+// gradient pass for n_archetypes <= 16: persistent CTAs walk the spots in chunks of 128 rows, staged in shared memory
+// (coalesced); every thread evaluates all archetypes for its row in one sweep, so X is read once per pass instead of once
+// per archetype.  Same arithmetic per (row, archetype) as aa_beta_grad_kernel and ties go to the lowest index, so the
+// winners are the same whatever the grid is.
+constexpr int kGradChunk = 128;
 template <int MAXA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kGradChunk)
 aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ R, int na,
                           const BetaState* __restrict__ st, double* __restrict__ cand_w, int64_t* __restrict__ cand_i) {
     if (st->all_done) return;
     extern __shared__ double sh[];
     const int dpad = d | 1;
     double* Rs = sh;                                   // na x (d+1)
-    double* Xs = Rs + na * (d + 1);                    // 256 x dpad
-    double* red_w = Xs + 256 * dpad;                   // [8][MAXA]
-    int* red_i = reinterpret_cast<int*>(red_w + 8 * MAXA);   // [8][MAXA] offsets from i0
-    for (int e = threadIdx.x; e < na * (d + 1); e += 256) Rs[e] = R[e];
+    double* Xs = Rs + na * (d + 1);                    // kGradChunk x dpad
+    double* red_w = Xs + kGradChunk * dpad;            // [4][MAXA]
+    int64_t* red_i = reinterpret_cast<int64_t*>(red_w + 4 * MAXA);
+    for (int e = threadIdx.x; e < na * (d + 1); e += kGradChunk) Rs[e] = R[e];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i0 = (int64_t)blockIdx.x * 1024;
-    const int ncta = (int)((n - i0) < 1024 ? (n - i0) : 1024);
+    const int64_t nchunks = (n + kGradChunk - 1) / kGradChunk;
     double bw[MAXA];
-    int bi[MAXA];
+    int64_t bi[MAXA];
 #pragma unroll
     for (int a = 0; a < MAXA; ++a) { bw[a] = -1e300; bi[a] = -1; }
-    for (int c0 = 0; c0 < ncta; c0 += 256) {
-        const int nrows = ncta - c0 < 256 ? ncta - c0 : 256;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int64_t r0 = c * kGradChunk;
+        const int nrows = (int)((n - r0) < kGradChunk ? (n - r0) : kGradChunk);
         __syncthreads();                               // previous chunk consumed (and Rs written, first time)
-        const double* __restrict__ src = X + (i0 + c0) * d;
-        for (int e = threadIdx.x; e < nrows * d; e += 256) Xs[(e / d) * dpad + (e % d)] = src[e];
+        stage_rows(Xs, dpad, X + r0 * d, d, nrows);
+        stage_wait();
         __syncthreads();
         if ((int)threadIdx.x < nrows) {
             const double* __restrict__ x = Xs + threadIdx.x * dpad;
@@ -662,7 +686,7 @@ aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double
             }
 #pragma unroll
             for (int a = 0; a < MAXA; ++a)
-                if (a < na && v[a] > bw[a]) { bw[a] = v[a]; bi[a] = c0 + (int)threadIdx.x; }
+                if (a < na && v[a] > bw[a]) { bw[a] = v[a]; bi[a] = r0 + threadIdx.x; }     // rows ascend: ties keep the lowest
         }
     }
     // arg-max per archetype over the CTA, lowest index wins ties
@@ -670,10 +694,10 @@ aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double
     for (int a = 0; a < MAXA; ++a) {
         if (a < na) {
             double w = bw[a];
-            int i = bi[a];
+            int64_t i = bi[a];
             for (int o = 16; o > 0; o >>= 1) {
                 const double ow = __shfl_xor_sync(0xffffffffu, w, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+                const int64_t oi = __shfl_xor_sync(0xffffffffu, i, o);
                 if (ow > w || (ow == w && oi >= 0 && (i < 0 || oi < i))) { w = ow; i = oi; }
             }
             if (lane == 0) { red_w[warp * MAXA + a] = w; red_i[warp * MAXA + a] = i; }
@@ -683,87 +707,145 @@ aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double
     if ((int)threadIdx.x < na) {
         const int a = threadIdx.x;
         double w = red_w[a];
-        int i = red_i[a];
-        for (int q = 1; q < 8; ++q) {
+        int64_t i = red_i[a];
+        for (int q = 1; q < kGradChunk / 32; ++q) {
             const double ow = red_w[q * MAXA + a];
-            const int oi = red_i[q * MAXA + a];
+            const int64_t oi = red_i[q * MAXA + a];
             if (ow > w || (ow == w && oi >= 0 && (i < 0 || oi < i))) { w = ow; i = oi; }
         }
         const bool done = st->done[a] != 0;
         cand_w[(size_t)blockIdx.x * na + a] = done ? -1e300 : w;
-        cand_i[(size_t)blockIdx.x * na + a] = (done || i < 0) ? -1 : i0 + i;
+        cand_i[(size_t)blockIdx.x * na + a] = done ? -1 : i;
     }
 }
 
-// least squares of [zhat_a, M] on the passive points P of archetype a (serial, lane 0 of its warp): steps back
-// to the feasible region while a coefficient turns non-positive, then writes the residual
+// least squares of [zhat_a, M] on the passive points P of archetype a, by one warp: steps back to the feasible region
+// while a coefficient turns non-positive, then writes the residual
 //   R[a] = [zhat_a, M] - sum_p b_p [x_p, M]
-__device__ void beta_refit(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int a, BetaState* st,
-                           int* P, double* b, double* __restrict__ R, double* scratch_a) {
-    const int dp = d + 1;
+// Shared memory of the warp (doubles): passive rows Xp [npmax][d|1], Gram / Cholesky factor [npmax][npmax|1], rhs, s.
+// The Gram entries and the factor are computed entry by entry with the accumulation order of a serial solve (lanes own
+// rows), the triangular solves sweep column by column.
+__device__ inline int beta_npmax(int d) { return d + 3 < kAaMaxP ? d + 3 : kAaMaxP; }
+static size_t beta_refit_smem_bytes(int d) {
+    const int npmax = d + 3 < kAaMaxP ? d + 3 : kAaMaxP;
+    return ((size_t)npmax * (d | 1) + (size_t)npmax * (npmax | 1) + 2 * (size_t)npmax) * 8;
+}
+
+__device__ void beta_refit_warp(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int a, BetaState* st,
+                                int* P, double* b, double* __restrict__ R, double* sm) {
+    const int lane = threadIdx.x & 31;
+    const int npmax = beta_npmax(d), dp1 = d | 1, ldl = npmax | 1, dp = d + 1;
+    double* Xp = sm;
+    double* Lm = Xp + npmax * dp1;
+    double* rhs = Lm + npmax * ldl;
+    double* sv = rhs + npmax;
     int np = st->np[a];
-    double* H = scratch_a;
-    double* rhs = H + kAaMaxP * kAaMaxP;
-    double* s = rhs + kAaMaxP;
-    double* L = s + kAaMaxP;
-    int ident[kAaMaxP];
+    __syncwarp();
     for (int inner = 0; inner < 3 * kAaMaxP && np > 0; ++inner) {
-        for (int p = 0; p < np; ++p) {
-            const double* xp = X + (int64_t)P[p] * d;
-            for (int q = 0; q <= p; ++q) {
-                const double* xq = X + (int64_t)P[q] * d;
-                double v = M * M;
-                for (int t = 0; t < d; ++t) v += xp[t] * xq[t];
-                H[p * np + q] = v;
-                H[q * np + p] = v;
-            }
-            double v = M * M;
-            for (int t = 0; t < d; ++t) v += xp[t] * Zhat[a * d + t];
-            rhs[p] = v;
-            ident[p] = p;
+        for (int e = lane; e < np * d; e += 32) {
+            const int p = e / d, t = e - p * d;
+            Xp[p * dp1 + t] = X[(int64_t)P[p] * d + t];
         }
-        if (!chol_solve_subset(H, np, ident, np, rhs, L, s)) { --np; st->done[a] = 1; continue; }
-        double smin = 1e300;
-        for (int p = 0; p < np; ++p) smin = fmin(smin, s[p]);
-        if (smin > 0.0) { for (int p = 0; p < np; ++p) b[p] = s[p]; break; }
-        double alpha = 1e300;
+        __syncwarp();
         for (int p = 0; p < np; ++p)
-            if (s[p] <= 0.0) alpha = fmin(alpha, b[p] / (b[p] - s[p]));
-        for (int p = 0; p < np; ++p) b[p] += alpha * (s[p] - b[p]);
-        int q = 0;
-        for (int p = 0; p < np; ++p) {
-            if (b[p] <= 1e-15 && s[p] <= 0.0) continue;
-            P[q] = P[p]; b[q] = b[p]; ++q;
+            for (int q = lane; q <= p; q += 32) {
+                double v = M * M;
+                for (int t = 0; t < d; ++t) v += Xp[p * dp1 + t] * Xp[q * dp1 + t];
+                Lm[p * ldl + q] = v;
+            }
+        for (int p = lane; p < np; p += 32) {
+            double v = M * M;
+            for (int t = 0; t < d; ++t) v += Xp[p * dp1 + t] * Zhat[a * d + t];
+            rhs[p] = v;
         }
-        np = q;
+        __syncwarp();
+        bool ok = true;
+        for (int j = 0; j < np; ++j) {                  // Cholesky in place, column j: diagonal, then the rows below it
+            double v = Lm[j * ldl + j];
+            for (int k = 0; k < j; ++k) v -= Lm[j * ldl + k] * Lm[j * ldl + k];
+            if (!(v > 0.0)) { ok = false; break; }      // the same value in every lane
+            const double ljj = sqrt(v);
+            __syncwarp();
+            if (lane == 0) Lm[j * ldl + j] = ljj;
+            for (int i = j + 1 + lane; i < np; i += 32) {
+                double w = Lm[i * ldl + j];
+                for (int k = 0; k < j; ++k) w -= Lm[i * ldl + k] * Lm[j * ldl + k];
+                Lm[i * ldl + j] = w / ljj;
+            }
+            __syncwarp();
+        }
+        if (!ok) {                                      // numerically dependent point: drop the newest, stop adding
+            --np;
+            if (lane == 0) st->done[a] = 1;
+            __syncwarp();
+            continue;
+        }
+        for (int i = lane; i < np; i += 32) sv[i] = rhs[i];
+        __syncwarp();
+        for (int k = 0; k < np; ++k) {                  // L y = rhs
+            const double sk = sv[k] / Lm[k * ldl + k];
+            __syncwarp();
+            if (lane == 0) sv[k] = sk;
+            for (int i = k + 1 + lane; i < np; i += 32) sv[i] -= Lm[i * ldl + k] * sk;
+            __syncwarp();
+        }
+        for (int k = np - 1; k >= 0; --k) {             // L^T s = y
+            const double sk = sv[k] / Lm[k * ldl + k];
+            __syncwarp();
+            if (lane == 0) sv[k] = sk;
+            for (int i = lane; i < k; i += 32) sv[i] -= Lm[k * ldl + i] * sk;
+            __syncwarp();
+        }
+        double smin = 1e300;
+        for (int p = lane; p < np; p += 32) smin = fmin(smin, sv[p]);
+        for (int o = 16; o > 0; o >>= 1) smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        if (smin > 0.0) {
+            for (int p = lane; p < np; p += 32) b[p] = sv[p];
+            __syncwarp();
+            break;
+        }
+        double alpha = 1e300;
+        for (int p = lane; p < np; p += 32)
+            if (sv[p] <= 0.0) alpha = fmin(alpha, b[p] / (b[p] - sv[p]));
+        for (int o = 16; o > 0; o >>= 1) alpha = fmin(alpha, __shfl_xor_sync(0xffffffffu, alpha, o));
+        for (int p = lane; p < np; p += 32) b[p] += alpha * (sv[p] - b[p]);
+        __syncwarp();
+        int q = 0;
+        if (lane == 0) {
+            for (int p = 0; p < np; ++p) {
+                if (b[p] <= 1e-15 && sv[p] <= 0.0) continue;
+                P[q] = P[p]; b[q] = b[p]; ++q;
+            }
+        }
+        np = __shfl_sync(0xffffffffu, q, 0);
+        __syncwarp();
     }
-    st->np[a] = np;
-    for (int t = 0; t < dp; ++t) {
+    if (lane == 0) st->np[a] = np;
+    for (int t = lane; t < dp; t += 32) {
         double v = t < d ? Zhat[a * d + t] : M;
         for (int p = 0; p < np; ++p) v -= b[p] * (t < d ? X[(int64_t)P[p] * d + t] : M);
         R[a * dp + t] = v;
     }
+    __syncwarp();
 }
 
-constexpr int kAaScratchPerA = kAaMaxP * kAaMaxP + 3 * kAaMaxP + kAaMaxP * (kAaMaxP + 1) / 2;
-
-// warm start of the beta step: every archetype keeps the passive points of the previous iteration
-__global__ void aa_beta_refit_kernel(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int na,
-                                     BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef,
-                                     double* __restrict__ R, double* __restrict__ scratch) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+// warm start of the beta step: every archetype (one warp each) keeps the passive points of the previous iteration
+__global__ void __launch_bounds__(32)
+aa_beta_refit_kernel(const double* __restrict__ X, int d, double M, const double* __restrict__ Zhat, int na,
+                     BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef, double* __restrict__ R) {
+    extern __shared__ double sh[];
+    const int a = blockIdx.x;
     if (a >= na) return;
-    beta_refit(X, d, M, Zhat, a, st, pidx + a * kAaMaxP, bcoef + a * kAaMaxP, R, scratch + (size_t)a * kAaScratchPerA);
+    beta_refit_warp(X, d, M, Zhat, a, st, pidx + a * kAaMaxP, bcoef + a * kAaMaxP, R, sh);
 }
 
-// one warp per archetype: final arg-max, add to the passive set, Lawson-Hanson inner loop, new residual
-__global__ void __launch_bounds__(32 * 8)
+// one warp (= one CTA) per archetype: final arg-max, add to the passive set, Lawson-Hanson inner loop, new residual
+__global__ void __launch_bounds__(32)
 aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ Zhat, int na,
                       int nblocks, const double* __restrict__ cand_w, const int64_t* __restrict__ cand_i,
-                      BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef, double* __restrict__ R,
-                      double* __restrict__ scratch) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int a = warp;
+                      BetaState* __restrict__ st, int* __restrict__ pidx, double* __restrict__ bcoef, double* __restrict__ R) {
+    extern __shared__ double sh[];
+    const int a = blockIdx.x, lane = threadIdx.x & 31;
     if (a >= na || st->all_done) return;
     if (!st->done[a]) {
         // final arg-max over the CTAs of the gradient pass (lane-strided, lowest index wins ties)
@@ -779,9 +861,10 @@ aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, 
             const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ow > bw || (ow == bw && oi >= 0 && (bi < 0 || oi < bi))) { bw = ow; bi = oi; }
         }
+        int* P = pidx + a * kAaMaxP;
+        double* b = bcoef + a * kAaMaxP;
+        int add = 0;
         if (lane == 0) {
-            int* P = pidx + a * kAaMaxP;
-            double* b = bcoef + a * kAaMaxP;
             const int np = st->np[a];
             // scale for the stopping test: |[zhat, M]| * max |[x, M]| ~ M^2
             double znorm = M * M;
@@ -789,15 +872,17 @@ aa_beta_update_kernel(const double* __restrict__ X, int64_t n, int d, double M, 
             const double tol = 1e-11 * znorm;
             bool in_set = false;
             for (int p = 0; p < np; ++p) in_set |= (P[p] == (int)bi);
-            if (bi < 0 || bw <= tol || in_set || np >= kAaMaxP - 1) {
+            if (bi < 0 || bw <= tol || in_set || np >= beta_npmax(d) - 1) {
                 st->done[a] = 1;
             } else {
                 P[np] = (int)bi;
                 b[np] = 0.0;
                 st->np[a] = np + 1;
-                beta_refit(X, d, M, Zhat, a, st, P, b, R, scratch + (size_t)a * kAaScratchPerA);
+                add = 1;
             }
         }
+        add = __shfl_sync(0xffffffffu, add, 0);
+        if (add) beta_refit_warp(X, d, M, Zhat, a, st, P, b, R, sh);
     }
     (void)n;
 }
@@ -890,12 +975,9 @@ aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __re
     const int64_t i_base = (int64_t)blockIdx.x * 256;
     const int nvalid = (int)((n - i_base) < 256 ? (n - i_base) : 256);
     for (int e = threadIdx.x; e < na * d; e += 256) Zs[e] = Z[e];
-    {
-        const double* __restrict__ src = X + i_base * d;
-        for (int e = threadIdx.x; e < nvalid * d; e += 256) Xs[(e / d) * dpad + (e % d)] = src[e];
-        const double* __restrict__ sa = alphas + i_base * na;
-        for (int e = threadIdx.x; e < nvalid * na; e += 256) As[(e / na) * apad + (e % na)] = sa[e];
-    }
+    stage_rows(Xs, dpad, X + i_base * d, d, nvalid);
+    stage_rows(As, apad, alphas + i_base * na, na, nvalid);
+    stage_wait();
     __syncthreads();
     double r = 0.0;
     if ((int)threadIdx.x < nvalid) {
@@ -1018,9 +1100,12 @@ static AaPlan aa_plan(int64_t n, int d, int na) {
     p.off_state = take(sizeof(BetaState));
     p.off_pidx = take((size_t)na * kAaMaxP * 4);
     p.off_bcoef = take((size_t)na * kAaMaxP * 8);
-    p.off_candw = take((size_t)p.grad_blocks * na * 8);
-    p.off_candi = take((size_t)p.grad_blocks * na * 8);
-    p.off_scr = take((size_t)na * kAaScratchPerA * 8);
+    int64_t cand_rows = ceil_div<int64_t>(n, 128);          // staged gradient pass: one row per persistent CTA
+    if (cand_rows > kNumSMs * 4) cand_rows = kNumSMs * 4;
+    if (cand_rows < p.grad_blocks) cand_rows = p.grad_blocks;
+    p.off_candw = take((size_t)cand_rows * na * 8);
+    p.off_candi = take((size_t)cand_rows * na * 8);
+    p.off_scr = take(256);                  // (unused: the beta refits keep their scratch in shared memory)
     p.off_rsspart = take((size_t)p.rss_blocks * 8);
     p.total = o;
     return p;
@@ -1118,7 +1203,6 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     double* bcoef = (double*)(ws + p.off_bcoef);
     double* candw = (double*)(ws + p.off_candw);
     int64_t* candi = (int64_t*)(ws + p.off_candi);
-    double* scr = (double*)(ws + p.off_scr);
     double* rsspart = (double*)(ws + p.off_rsspart);
 
     timer_begin(CHR_FAMILY_AA, true, st);
@@ -1156,11 +1240,21 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     CHR_LAUNCH_CHECK();
     // ---- betas: active-set passes, every archetype advances one step per pass
     aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, warm, R);
-    if (warm) aa_beta_refit_kernel<<<1, 64, 0, st>>>(X, d, penalty_M, Zhat, na, bst, pidx, bcoef, R, scr);
+    const size_t sm_refit = beta_refit_smem_bytes(d);
+    if (sm_refit > 48 * 1024) {
+        CHR_CUDA(cudaFuncSetAttribute(aa_beta_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_refit));
+        CHR_CUDA(cudaFuncSetAttribute(aa_beta_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_refit));
+    }
+    if (warm) aa_beta_refit_kernel<<<na, 32, sm_refit, st>>>(X, d, penalty_M, Zhat, na, bst, pidx, bcoef, R);
     const size_t sm_grad = (size_t)na * (d + 1) * 8 + 32 * 8 + 32 * 8;
-    const size_t sm_gradf = ((size_t)na * (d + 1) + 256 * (size_t)(d | 1) + 8 * 16) * 8 + 8 * 16 * 4;
+    const size_t sm_gradf = ((size_t)na * (d + 1) + kGradChunk * (size_t)(d | 1) + 4 * 16 * 2) * 8;
     if (na <= 16 && sm_gradf > 48 * 1024)
         CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+    // persistent grid of the staged gradient pass (aa_plan sizes the candidate arrays for it)
+    const int64_t grad_chunks = ceil_div<int64_t>(n, kGradChunk);
+    int gradf_grid = kNumSMs * 4;
+    if (gradf_grid > grad_chunks) gradf_grid = (int)grad_chunks;
+    const int cand_blocks = na <= 16 ? gradf_grid : p.grad_blocks;
     const int max_pass = 3 * (d + 2) + 8;
     int passes = 0;
     int host_done = 0;
@@ -1168,11 +1262,10 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
         const int batch = warm ? 2 : (passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4);   // cold: first look after a handful of passes
         for (int b = 0; b < batch && passes < max_pass; ++b, ++passes) {
             if (na <= 16)
-                aa_beta_grad_fixed_kernel<16><<<p.grad_blocks, 256, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+                aa_beta_grad_fixed_kernel<16><<<gradf_grid, kGradChunk, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
             else
                 aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
-            aa_beta_update_kernel<<<(unsigned)ceil_div(na * 32, 256), 256, 0, st>>>(X, n, d, penalty_M, Zhat, na, p.grad_blocks, candw,
-                                                                                 candi, bst, pidx, bcoef, R, scr);
+            aa_beta_update_kernel<<<na, 32, sm_refit, st>>>(X, n, d, penalty_M, Zhat, na, cand_blocks, candw, candi, bst, pidx, bcoef, R);
             aa_beta_check_kernel<<<1, 32, 0, st>>>(bst, na);
         }
         CHR_LAUNCH_CHECK();
