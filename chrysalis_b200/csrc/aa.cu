@@ -360,17 +360,20 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
                       double* __restrict__ alphas, double* __restrict__ part /*[grid][na*na + na*d]*/, int region_doubles) {
     using AF = AlphaFixed<NA>;
     constexpr int T = AF::kThreads;
-    extern __shared__ double sh[];
+    extern __shared__ __align__(16) double sh[];
     double* G = sh;                        // NA x NA, identity on the padding
-    double* Zs = G + NA * NA;              // na x d
-    double* region = Zs + na * d;          // staged X rows -> Cholesky factors -> [alphas | X] rows of the CTA
+    double* Zs = G + NA * NA;              // d x NA, transposed and zero-padded: the archetypes of one coordinate are contiguous
+    double* region = Zs + NA * d;          // staged X rows -> Cholesky factors -> [alphas | X] rows of the CTA
     (void)region_doubles;
     const int tid = threadIdx.x;
     const int nacc = na * na + na * d;
     const int dpad = d | 1;                // odd row stride: conflict-free per-thread rows
     const int64_t i_base = (int64_t)blockIdx.x * T;
     const int nvalid = (int)((n - i_base) < (int64_t)T ? (n - i_base) : (int64_t)T);
-    for (int e = tid; e < na * d; e += T) Zs[e] = Z[e];
+    for (int e = tid; e < NA * d; e += T) {
+        const int t = e / NA, a = e - t * NA;
+        Zs[e] = a < na ? Z[a * d + t] : 0.0;
+    }
     stage_rows(region, dpad, X + i_base * d, d, nvalid);   // the CTA's rows of X: one contiguous block
     stage_wait();
     __syncthreads();
@@ -379,7 +382,7 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
         double v = a == b ? 1.0 : 0.0;
         if (a < na && b < na) {
             v = M * M;
-            for (int t = 0; t < d; ++t) v += Zs[a * d + t] * Zs[b * d + t];
+            for (int t = 0; t < d; ++t) v += Zs[t * NA + a] * Zs[t * NA + b];
         }
         G[e] = v;
     }
@@ -391,9 +394,13 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
         const double* __restrict__ xr = region + tid * dpad;
         for (int t = 0; t < d; ++t) {
             const double xv = xr[t];
+            const double2* __restrict__ z2 = reinterpret_cast<const double2*>(Zs + t * NA);
 #pragma unroll
-            for (int a = 0; a < NA; ++a)
-                if (a < na) c[a] += Zs[a * d + t] * xv;
+            for (int h = 0; h < NA / 2; ++h) {
+                const double2 z = z2[h];                               // padding archetypes: z = 0
+                c[2 * h] += z.x * xv;
+                c[2 * h + 1] += z.y * xv;
+            }
         }
     }
     unsigned P = 0;
@@ -480,10 +487,19 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
         const int a = e / nstrip, c0 = (e % nstrip) * 4;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
         const int w1 = c0 + 1 < W ? c0 + 1 : c0, w2 = c0 + 2 < W ? c0 + 2 : c0, w3 = c0 + 3 < W ? c0 + 3 : c0;
-        for (int t = 0; t < T; ++t) {
-            const double* __restrict__ b = region + t * W;
-            const double av = b[a];
-            v0 += av * b[c0]; v1 += av * b[w1]; v2 += av * b[w2]; v3 += av * b[w3];
+        if (!(W & 1) && c0 + 3 < W) {                                  // aligned full strip: two 16-byte loads per row
+            for (int t = 0; t < T; ++t) {
+                const double* __restrict__ b = region + t * W;
+                const double av = b[a];
+                const double2 b01 = *reinterpret_cast<const double2*>(b + c0), b23 = *reinterpret_cast<const double2*>(b + c0 + 2);
+                v0 += av * b01.x; v1 += av * b01.y; v2 += av * b23.x; v3 += av * b23.y;
+            }
+        } else {
+            for (int t = 0; t < T; ++t) {
+                const double* __restrict__ b = region + t * W;
+                const double av = b[a];
+                v0 += av * b[c0]; v1 += av * b[w1]; v2 += av * b[w2]; v3 += av * b[w3];
+            }
         }
         const double vv[4] = {v0, v1, v2, v3};
 #pragma unroll
@@ -530,38 +546,66 @@ __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int 
     for (int e = threadIdx.x; e < na * na; e += blockDim.x) Vv[e] = (e / na == e % na) ? 1.0 : 0.0;
     __syncthreads();
     if (threadIdx.x < 32) {
-        // cyclic Jacobi by one warp: the rotation (p, q) is computed redundantly by every lane, its three element-wise
-        // updates (columns of S, rows of S, columns of V) are spread over the lanes - the same operations in the same
-        // order as a serial sweep
+        // Jacobi eigen-decomposition by one warp, round-robin ordering: a round holds na/2 rotations on disjoint index
+        // pairs - they commute, so their angles are taken from the same S and their column and row updates run in parallel
         const int lane = threadIdx.x;
+        const int m = (na + 1) & ~1;                       // players of the round-robin schedule (an odd na gets a bye)
+        double* cs = Vv + na * na;                         // [m/2][2] cosine, sine
+        int* pq = reinterpret_cast<int*>(cs + m);          // [m/2] p | q << 8, q >= na: bye
         for (int sweep = 0; sweep < 60; ++sweep) {
             double off = 0.0, diag = 0.0;
-            for (int p = 0; p < na; ++p) { diag += S[p * na + p] * S[p * na + p]; for (int q = p + 1; q < na; ++q) off += S[p * na + q] * S[p * na + q]; }
-            if (off <= 1e-30 * diag) break;
-            for (int p = 0; p < na - 1; ++p)
-                for (int q = p + 1; q < na; ++q) {
-                    const double apq = S[p * na + q];
-                    if (fabs(apq) < 1e-300) continue;                 // uniform across the warp
-                    const double theta = (S[q * na + q] - S[p * na + p]) / (2.0 * apq);
-                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                    __syncwarp();
-                    for (int k = lane; k < na; k += 32) {
-                        const double skp = S[k * na + p], skq = S[k * na + q];
-                        S[k * na + p] = c * skp - s * skq;
-                        S[k * na + q] = s * skp + c * skq;
-                        const double vkp = Vv[k * na + p], vkq = Vv[k * na + q];
-                        Vv[k * na + p] = c * vkp - s * vkq;
-                        Vv[k * na + q] = s * vkp + c * vkq;
+            for (int e = lane; e < na * na; e += 32) {
+                const int p = e / na, q = e - p * na;
+                const double v = S[e];
+                if (p == q) diag += v * v; else if (q > p) off += v * v;
+            }
+            off = warp_sum(off);
+            diag = warp_sum(diag);
+            if (off <= 1e-30 * diag) break;                // butterfly sums: the same value in every lane
+            for (int r = 0; r < m - 1; ++r) {
+                if (lane < m / 2) {
+                    int p = lane == 0 ? m - 1 : (r + lane) % (m - 1);
+                    int q = lane == 0 ? r : (r - lane + (m - 1)) % (m - 1);
+                    if (p > q) { const int t = p; p = q; q = t; }
+                    double c = 1.0, sn = 0.0;
+                    if (q < na) {
+                        const double apq = S[p * na + q];
+                        if (fabs(apq) >= 1e-300) {
+                            const double theta = (S[q * na + q] - S[p * na + p]) / (2.0 * apq);
+                            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                            c = 1.0 / sqrt(t * t + 1.0);
+                            sn = t * c;
+                        }
                     }
-                    __syncwarp();
-                    for (int k = lane; k < na; k += 32) {
-                        const double spk = S[p * na + k], sqk = S[q * na + k];
-                        S[p * na + k] = c * spk - s * sqk;
-                        S[q * na + k] = s * spk + c * sqk;
-                    }
-                    __syncwarp();
+                    cs[2 * lane] = c;
+                    cs[2 * lane + 1] = sn;
+                    pq[lane] = p | (q << 8);
                 }
+                __syncwarp();
+                for (int it = lane; it < na * (m / 2); it += 32) {          // columns p, q of S and V
+                    const int pr = it / na, k = it - pr * na;
+                    const int p = pq[pr] & 0xff, q = pq[pr] >> 8;
+                    if (q >= na) continue;
+                    const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                    const double skp = S[k * na + p], skq = S[k * na + q];
+                    S[k * na + p] = c * skp - sn * skq;
+                    S[k * na + q] = sn * skp + c * skq;
+                    const double vkp = Vv[k * na + p], vkq = Vv[k * na + q];
+                    Vv[k * na + p] = c * vkp - sn * vkq;
+                    Vv[k * na + q] = sn * vkp + c * vkq;
+                }
+                __syncwarp();
+                for (int it = lane; it < na * (m / 2); it += 32) {          // rows p, q of S
+                    const int pr = it / na, k = it - pr * na;
+                    const int p = pq[pr] & 0xff, q = pq[pr] >> 8;
+                    if (q >= na) continue;
+                    const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                    const double spk = S[p * na + k], sqk = S[q * na + k];
+                    S[p * na + k] = c * spk - sn * sqk;
+                    S[q * na + k] = sn * spk + c * sqk;
+                }
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
@@ -643,23 +687,26 @@ aa_beta_grad_kernel(const double* __restrict__ X, int64_t n, int d, double M, co
     (void)pidx;
 }
 
-// gradient pass for n_archetypes <= 16: persistent CTAs walk the spots in chunks of 128 rows, staged in shared memory
+// gradient pass for n_archetypes <= 16: persistent CTAs walk the spots in chunks of 256 rows, staged in shared memory
 // (coalesced); every thread evaluates all archetypes for its row in one sweep, so X is read once per pass instead of once
 // per archetype.  Same arithmetic per (row, archetype) as aa_beta_grad_kernel and ties go to the lowest index, so the
 // winners are the same whatever the grid is.
-constexpr int kGradChunk = 128;
+constexpr int kGradChunk = 256, kGradThreads = 128;      // every thread owns 2 rows of a chunk: the residual rows are loaded once for both
 template <int MAXA>
-__global__ void __launch_bounds__(kGradChunk)
+__global__ void __launch_bounds__(kGradThreads)
 aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double M, const double* __restrict__ R, int na,
                           const BetaState* __restrict__ st, double* __restrict__ cand_w, int64_t* __restrict__ cand_i) {
     if (st->all_done) return;
-    extern __shared__ double sh[];
+    extern __shared__ __align__(16) double sh[];
     const int dpad = d | 1;
-    double* Rs = sh;                                   // na x (d+1)
-    double* Xs = Rs + na * (d + 1);                    // kGradChunk x dpad
+    double* Rt = sh;                                   // (d+1) x MAXA, transposed: the archetypes of one coordinate are contiguous
+    double* Xs = Rt + (d + 1) * MAXA;                  // kGradChunk x dpad
     double* red_w = Xs + kGradChunk * dpad;            // [4][MAXA]
     int64_t* red_i = reinterpret_cast<int64_t*>(red_w + 4 * MAXA);
-    for (int e = threadIdx.x; e < na * (d + 1); e += kGradChunk) Rs[e] = R[e];
+    for (int e = threadIdx.x; e < (d + 1) * MAXA; e += kGradThreads) {
+        const int t = e / MAXA, a = e % MAXA;
+        Rt[e] = a < na ? R[a * (d + 1) + t] : 0.0;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nchunks = (n + kGradChunk - 1) / kGradChunk;
     double bw[MAXA];
@@ -669,24 +716,31 @@ aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double
     for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int64_t r0 = c * kGradChunk;
         const int nrows = (int)((n - r0) < kGradChunk ? (n - r0) : kGradChunk);
-        __syncthreads();                               // previous chunk consumed (and Rs written, first time)
+        __syncthreads();                               // previous chunk consumed (and Rt written, first time)
         stage_rows(Xs, dpad, X + r0 * d, d, nrows);
         stage_wait();
         __syncthreads();
-        if ((int)threadIdx.x < nrows) {
-            const double* __restrict__ x = Xs + threadIdx.x * dpad;
-            double v[MAXA];
+        // rows tid and tid + 128 (a row past the end shadows row 0 and is not offered as a candidate)
+        const int ra = threadIdx.x, rb = threadIdx.x + kGradThreads;
+        const double* __restrict__ xa = Xs + (ra < nrows ? ra : 0) * dpad;
+        const double* __restrict__ xb = Xs + (rb < nrows ? rb : 0) * dpad;
+        double va[MAXA], vb[MAXA];
 #pragma unroll
-            for (int a = 0; a < MAXA; ++a) v[a] = a < na ? M * Rs[a * (d + 1) + d] : 0.0;
-            for (int t = 0; t < d; ++t) {
-                const double xv = x[t];
+        for (int a = 0; a < MAXA; ++a) va[a] = vb[a] = M * Rt[d * MAXA + a];
+        for (int t = 0; t < d; ++t) {
+            const double xva = xa[t], xvb = xb[t];
+            const double2* __restrict__ r2 = reinterpret_cast<const double2*>(Rt + t * MAXA);
 #pragma unroll
-                for (int a = 0; a < MAXA; ++a)
-                    if (a < na) v[a] += xv * Rs[a * (d + 1) + t];
+            for (int h = 0; h < MAXA / 2; ++h) {
+                const double2 r = r2[h];
+                va[2 * h] += xva * r.x; va[2 * h + 1] += xva * r.y;
+                vb[2 * h] += xvb * r.x; vb[2 * h + 1] += xvb * r.y;
             }
+        }
 #pragma unroll
-            for (int a = 0; a < MAXA; ++a)
-                if (a < na && v[a] > bw[a]) { bw[a] = v[a]; bi[a] = r0 + threadIdx.x; }     // rows ascend: ties keep the lowest
+        for (int a = 0; a < MAXA; ++a) {               // rows ascend (ra before rb, chunks in order): ties keep the lowest index
+            if (a < na && ra < nrows && va[a] > bw[a]) { bw[a] = va[a]; bi[a] = r0 + ra; }
+            if (a < na && rb < nrows && vb[a] > bw[a]) { bw[a] = vb[a]; bi[a] = r0 + rb; }
         }
     }
     // arg-max per archetype over the CTA, lowest index wins ties
@@ -708,7 +762,7 @@ aa_beta_grad_fixed_kernel(const double* __restrict__ X, int64_t n, int d, double
         const int a = threadIdx.x;
         double w = red_w[a];
         int64_t i = red_i[a];
-        for (int q = 1; q < kGradChunk / 32; ++q) {
+        for (int q = 1; q < kGradThreads / 32; ++q) {
             const double ow = red_w[q * MAXA + a];
             const int64_t oi = red_i[q * MAXA + a];
             if (ow > w || (ow == w && oi >= 0 && (i < 0 || oi < i))) { w = ow; i = oi; }
@@ -1211,7 +1265,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     if (na <= 16 && !getenv("CHR_AA_ALPHA_GENERAL")) {
         const int NA = (na + 3) & ~3;
         const size_t region = aa_alpha_fixed_region_doubles(NA, na, d);
-        const size_t smf = ((size_t)NA * NA + (size_t)na * d + region) * 8;
+        const size_t smf = ((size_t)NA * NA + (size_t)NA * d + region) * 8;
 #define CHR_ALPHA_FIXED(NAV)                                                                                              \
     do {                                                                                                                  \
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_fixed_kernel<NAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf)); \
@@ -1232,7 +1286,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     }
     CHR_LAUNCH_CHECK();
     // ---- Zhat = pinv(alphas) X
-    const size_t sm_pinv = (size_t)(2 * na * na + na * d) * 8;
+    const size_t sm_pinv = (size_t)(2 * na * na + na * d + 2 * na + 8) * 8;      // + rotation table of a Jacobi round
     if (sm_pinv > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pinv));
     const int nred = ceil_div(p.alpha_blocks, kAaRedChunk);
     aa_partial_reduce_kernel<<<dim3((unsigned)ceil_div(p.nacc, 128), (unsigned)nred), 128, 0, st>>>(part, p.alpha_blocks, p.nacc, part2);
@@ -1247,12 +1301,17 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     }
     if (warm) aa_beta_refit_kernel<<<na, 32, sm_refit, st>>>(X, d, penalty_M, Zhat, na, bst, pidx, bcoef, R);
     const size_t sm_grad = (size_t)na * (d + 1) * 8 + 32 * 8 + 32 * 8;
-    const size_t sm_gradf = ((size_t)na * (d + 1) + kGradChunk * (size_t)(d | 1) + 4 * 16 * 2) * 8;
-    if (na <= 16 && sm_gradf > 48 * 1024)
-        CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+    const size_t sm_gradf = ((size_t)(d + 1) * 16 + kGradChunk * (size_t)(d | 1) + 4 * 16 * 2) * 8;
+    const int NAg = (na + 3) & ~3;
+    if (na <= 16 && sm_gradf > 48 * 1024) {
+        if (NAg == 4) CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+        else if (NAg == 8) CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+        else if (NAg == 12) CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+        else CHR_CUDA(cudaFuncSetAttribute(aa_beta_grad_fixed_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_gradf));
+    }
     // persistent grid of the staged gradient pass (aa_plan sizes the candidate arrays for it)
     const int64_t grad_chunks = ceil_div<int64_t>(n, kGradChunk);
-    int gradf_grid = kNumSMs * 4;
+    int gradf_grid = kNumSMs * 3;
     if (gradf_grid > grad_chunks) gradf_grid = (int)grad_chunks;
     const int cand_blocks = na <= 16 ? gradf_grid : p.grad_blocks;
     const int max_pass = 3 * (d + 2) + 8;
@@ -1261,8 +1320,10 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     while (passes < max_pass && !host_done) {
         const int batch = warm ? 2 : (passes == 0 ? (d + 2 < 8 ? d + 2 : 8) : 4);   // cold: first look after a handful of passes
         for (int b = 0; b < batch && passes < max_pass; ++b, ++passes) {
-            if (na <= 16)
-                aa_beta_grad_fixed_kernel<16><<<gradf_grid, kGradChunk, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+            if (NAg == 4) aa_beta_grad_fixed_kernel<4><<<gradf_grid, kGradThreads, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+            else if (NAg == 8) aa_beta_grad_fixed_kernel<8><<<gradf_grid, kGradThreads, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+            else if (NAg == 12) aa_beta_grad_fixed_kernel<12><<<gradf_grid, kGradThreads, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
+            else if (NAg == 16) aa_beta_grad_fixed_kernel<16><<<gradf_grid, kGradThreads, sm_gradf, st>>>(X, n, d, penalty_M, R, na, bst, candw, candi);
             else
                 aa_beta_grad_kernel<<<p.grad_blocks, 256, sm_grad, st>>>(X, n, d, penalty_M, R, na, bst, pidx, candw, candi);
             aa_beta_update_kernel<<<na, 32, sm_refit, st>>>(X, n, d, penalty_M, Zhat, na, cand_blocks, candw, candi, bst, pidx, bcoef, R);
