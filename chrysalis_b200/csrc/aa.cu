@@ -364,7 +364,7 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
     double* G = sh;                        // NA x NA, identity on the padding
     double* Zs = G + NA * NA;              // d x NA, transposed and zero-padded: the archetypes of one coordinate are contiguous
     double* region = Zs + NA * d;          // staged X rows -> Cholesky factors -> [alphas | X] rows of the CTA
-    (void)region_doubles;
+    double* A0 = region + region_doubles;  // T x (na | 1): the previous coefficients of the CTA's spots (warm start)
     const int tid = threadIdx.x;
     const int nacc = na * na + na * d;
     const int dpad = d | 1;                // odd row stride: conflict-free per-thread rows
@@ -375,6 +375,7 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
         Zs[e] = a < na ? Z[a * d + t] : 0.0;
     }
     stage_rows(region, dpad, X + i_base * d, d, nvalid);   // the CTA's rows of X: one contiguous block
+    if (warm) stage_rows(A0, na | 1, alphas + i_base * na, na, nvalid);
     stage_wait();
     __syncthreads();
     for (int e = tid; e < NA * NA; e += T) {
@@ -411,7 +412,7 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
 #pragma unroll
         for (int a = 0; a < NA; ++a)
             if (a < na) {
-                x[a] = alphas[(i_base + tid) * na + a];
+                x[a] = A0[tid * (na | 1) + a];
                 if (x[a] > 0.0) P |= 1u << a; else x[a] = 0.0;
             }
     }
@@ -466,40 +467,43 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
 #pragma unroll
     for (int a = 0; a < NA; ++a) { x[a] = fmax(x[a], 0.0); sum += x[a]; }
     const double inv = 1.0 / sum;
-    __syncthreads();                       // the factors are dead: the region becomes B = [alphas | X] (row = spot)
-    const int W = na + d;
+    __syncthreads();                       // the factors are dead: the region becomes B = [alphas | X | 0] (row = spot)
+    const int W = na + d, Wp = (W + 3) & ~3;      // rows padded to whole strips of 4 columns (32-byte aligned)
 #pragma unroll
     for (int a = 0; a < NA; ++a)
-        if (a < na) region[tid * W + a] = valid ? x[a] * inv : 0.0;
-    stage_rows(region + na, W, X + i_base * d, d, nvalid);
+        if (a < na) region[tid * Wp + a] = valid ? x[a] * inv : 0.0;
+    for (int c = W; c < Wp; ++c) region[tid * Wp + c] = 0.0;
+    stage_rows(region + na, Wp, X + i_base * d, d, nvalid);
     for (int r = nvalid + (tid >> 5); r < T; r += T >> 5)          // rows past the end of the matrix contribute zeros
-        for (int t = tid & 31; t < d; t += 32) region[r * W + na + t] = 0.0;
+        for (int t = tid & 31; t < d; t += 32) region[r * Wp + na + t] = 0.0;
     stage_wait();
     __syncthreads();
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int r = warp; r < nvalid; r += T >> 5)
-            for (int a = lane; a < na; a += 32) alphas[(i_base + r) * na + a] = region[r * W + a];
+    {   // the CTA's alphas: one contiguous block of the output, written coalesced
+        const int q = T / na, rm = T - q * na;
+        int row = tid / na, col = tid - row * na;
+        for (int e = tid; e < nvalid * na; e += T) {
+            alphas[i_base * na + e] = region[row * Wp + col];
+            col += rm;
+            row += q;
+            if (col >= na) { col -= na; ++row; }
+        }
     }
-    // partial  A^T [A | X]  of the CTA (na x W), spots summed in order: every thread owns strips of 4 columns
-    const int nstrip = (W + 3) >> 2;
-    for (int e = tid; e < na * nstrip; e += T) {
-        const int a = e / nstrip, c0 = (e % nstrip) * 4;
+    // partial  A^T [A | X]  of the CTA (na x W), spots summed in order.  A thread owns one strip of 4 columns of one row a;
+    // strips entirely below the diagonal of A^T A are skipped (their mirror images are written instead), which brings
+    // 12 archetypes x 30 dimensions to 120 strips: one pass of the CTA
+    const int nstrip = Wp >> 2;
+    int total_strips = 0;
+    for (int a = 0; a < na; ++a) total_strips += nstrip - (a >> 2);
+    for (int e = tid; e < total_strips; e += T) {
+        int a = 0, rem = e;
+        while (rem >= nstrip - (a >> 2)) { rem -= nstrip - (a >> 2); ++a; }
+        const int c0 = ((a >> 2) + rem) * 4;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        const int w1 = c0 + 1 < W ? c0 + 1 : c0, w2 = c0 + 2 < W ? c0 + 2 : c0, w3 = c0 + 3 < W ? c0 + 3 : c0;
-        if (!(W & 1) && c0 + 3 < W) {                                  // aligned full strip: two 16-byte loads per row
-            for (int t = 0; t < T; ++t) {
-                const double* __restrict__ b = region + t * W;
-                const double av = b[a];
-                const double2 b01 = *reinterpret_cast<const double2*>(b + c0), b23 = *reinterpret_cast<const double2*>(b + c0 + 2);
-                v0 += av * b01.x; v1 += av * b01.y; v2 += av * b23.x; v3 += av * b23.y;
-            }
-        } else {
-            for (int t = 0; t < T; ++t) {
-                const double* __restrict__ b = region + t * W;
-                const double av = b[a];
-                v0 += av * b[c0]; v1 += av * b[w1]; v2 += av * b[w2]; v3 += av * b[w3];
-            }
+        for (int t = 0; t < T; ++t) {
+            const double* __restrict__ b = region + t * Wp;
+            const double av = b[a];
+            const double2 b01 = *reinterpret_cast<const double2*>(b + c0), b23 = *reinterpret_cast<const double2*>(b + c0 + 2);
+            v0 += av * b01.x; v1 += av * b01.y; v2 += av * b23.x; v3 += av * b23.y;
         }
         const double vv[4] = {v0, v1, v2, v3};
 #pragma unroll
@@ -509,13 +513,14 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
                 // same layout as aa_alpha_kernel: [na x na | na x d]
                 const int dst = col < na ? a * na + col : na * na + a * d + (col - na);
                 part[(size_t)blockIdx.x * nacc + dst] = vv[q];
+                if (col < na && (col >> 2) > (a >> 2)) part[(size_t)blockIdx.x * nacc + col * na + a] = vv[q];   // skipped mirror strip
             }
         }
     }
 }
 
 static size_t aa_alpha_fixed_region_doubles(int NA, int na, int d) {
-    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128, xs = (size_t)128 * (d | 1), b = (size_t)128 * (na + d);
+    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128, xs = (size_t)128 * (d | 1), b = (size_t)128 * ((na + d + 3) & ~3);
     size_t r = tri > xs ? tri : xs;
     return r > b ? r : b;
 }
@@ -1265,7 +1270,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     if (na <= 16 && !getenv("CHR_AA_ALPHA_GENERAL")) {
         const int NA = (na + 3) & ~3;
         const size_t region = aa_alpha_fixed_region_doubles(NA, na, d);
-        const size_t smf = ((size_t)NA * NA + (size_t)NA * d + region) * 8;
+        const size_t smf = ((size_t)NA * NA + (size_t)NA * d + region + (size_t)128 * (na | 1)) * 8;
 #define CHR_ALPHA_FIXED(NAV)                                                                                              \
     do {                                                                                                                  \
         CHR_CUDA(cudaFuncSetAttribute(aa_alpha_fixed_kernel<NAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf)); \
