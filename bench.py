@@ -399,7 +399,8 @@ def run_native(args):
             keep, I_h, _ = core.svg_stage(host, xy_host, MIN_SPOTS, k, False, already_log1p=False, shard=False)
             return I_h
 
-        I_h = e2e_step()
+        for _ in range(3):                                        # warm-up: allocator pools, pinned staging, side stream
+            I_h = e2e_step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -408,6 +409,8 @@ def run_native(args):
             I_h = e2e_step()
         torch.cuda.synchronize()
         e_ms = (time.perf_counter() - t1) * 1e3 / e_steps
+        if core.SVG_TRACE:                                        # CHR_SVG_TRACE=1: host timeline of the last step
+            sys.stderr.write(f"svg_stage trace (ms): {core.SVG_TRACE}\n")
         if world > 1:
             t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -7,6 +7,9 @@ hand-written sm_100a kernels reached through the C ABI (``include/chrysalis_b200
 """
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
 import pandas as pd
 import torch
@@ -39,6 +42,13 @@ def _make_unique(names) -> pd.Index:
 
 
 _SIDE_STREAMS = {}
+SVG_TRACE = []     # CHR_SVG_TRACE=1: (label, host seconds since the call started) of the last svg_stage call
+
+
+def _mark(t0, label):
+    if t0 is not None:
+        SVG_TRACE.append((label, round((time.perf_counter() - t0) * 1e3, 3)))
+
 
 
 def _side_stream():
@@ -81,6 +91,10 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     quantities (p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim; host arrays over the scored genes).
     """
     n, g_all = X.shape
+    t0 = None
+    if os.environ.get("CHR_SVG_TRACE"):
+        SVG_TRACE.clear()
+        t0 = time.perf_counter()
     rank, size = dd.world() if shard else (0, 1)
     lo, hi = dd.shard_range(g_all, rank, size)
     # While the counts are in flight: W (core.py:61-65, needs the coordinates only) and the zero fill of the dense
@@ -97,7 +111,9 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     if side is not None:
         dense_buf = torch.empty((n, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
         side.wait_stream(main)
+    _mark(t0, "coords uploaded, dense buffer allocated")
     csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])      # asynchronous host -> device copy on the current stream
+    _mark(t0, "counts upload enqueued")
     with _stream_ctx(side):
         # core.py:64-65  kNN weights, row-standardised
         bbox = dv.spatial_bbox(xy)
@@ -112,12 +128,14 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         main.wait_stream(side)
         for t in (rank_of, nbr) + ((plan.buf,) if plan is not None else ()):
             t.record_stream(main)
+    _mark(t0, "W build + zero fill enqueued (side stream)")
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
     gene_nnz = dv.csr_gene_nnz(csr)
     keep = gene_nnz >= int(n * min_spots)
     gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
                            torch.full_like(gene_nnz, -1))
     n_keep = int(keep.sum().item())
+    _mark(t0, "gene filter known on the host (upload finished)")
     gather = dd.allgather_ragged if size > 1 else (lambda t, n_total=None: t)
     reduce_ = dd.allreduce_sum_ if size > 1 else (lambda t: t)
     keep_all = gather(keep, g_all)
@@ -138,9 +156,11 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None
         sim = {k: torch.empty(0, dtype=torch.float64, device=keep.device)
                for k in ("p_sim", "EI_sim", "VI_sim", "seI_sim", "z_sim", "p_z_sim")} if permutations else None
+    _mark(t0, "densify + Moran enqueued")
     I = gather(I)
     C = gather(C) if geary else None
     out = (keep_all.cpu().numpy(), I.cpu().numpy(), (C.cpu().numpy() if geary else None))
+    _mark(t0, "results on the host")
     if permutations:
         out += ({k: gather(v).cpu().numpy() for k, v in sim.items() if k != "I"},)
     return out

@@ -35,6 +35,8 @@ def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if t.numel() * t.element_size() < (32 << 20):
+        return t.to(dev)                 # small arrays: a plain (staged) copy is cheaper than pinning a fresh buffer
     return t.pin_memory().to(dev, non_blocking=True)
 
 
