@@ -364,10 +364,15 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
     """Device part of ``aa``: ``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit(X)``
     (core.py:186-191).  ``init_rows``: optional list of n_init index arrays (matched initialisation).
     Returns a dict with alphas (N, A), archetypes (A, d), rss, n_iter and the initial rows used."""
-    X = np.ascontiguousarray(np.asarray(X), dtype=np.float64)   # numpy upcasts the float32 scores inside archetypes
+    X = np.asarray(X)
     n, d = X.shape
     rs = np.random.RandomState(random_state)
-    Xd = dv.to_device(X, torch.float64)
+    # numpy upcasts the float32 scores to float64 inside archetypes; here the (exact) widening happens on the device,
+    # so half the bytes cross PCIe and the host never builds the float64 copy
+    if X.dtype == np.float32:
+        Xd = dv.to_device(np.ascontiguousarray(X), torch.float32).to(torch.float64)
+    else:
+        Xd = dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
     best = None
     used = []
     for r in range(n_init):

@@ -312,8 +312,8 @@ struct AlphaFixed {
     static constexpr int kTri = NA * (NA + 1) / 2;
     static constexpr int kThreads = 128;
 
-    // solve on the passive set `P` (bit mask); returns s (0 outside P); indices whose pivot collapses are dropped from P
-    static __device__ __forceinline__ void solve(const double* __restrict__ G, unsigned& P, const double (&c)[NA], double* __restrict__ Lt,
+    // row-oriented variant (factor rows re-read from shared memory): used when the matrix does not fit the register file (NA = 16)
+        static __device__ __forceinline__ void solve_rows(const double* __restrict__ G, unsigned& P, const double (&c)[NA], double* __restrict__ Lt,
                                                  double (&s)[NA]) {
         double dinv[NA], y[NA];
 #pragma unroll
@@ -352,6 +352,56 @@ struct AlphaFixed {
             s[i] = v * dinv[i];
         }
     }
+
+    // solve on the passive set `P` (bit mask); returns s (0 outside P); indices whose pivot collapses are dropped from P.
+    // Right-looking Cholesky with the (masked) matrix in registers: column j is scaled, written to shared memory once
+    // (the back substitution reads it) and subtracted from the trailing entries; the forward substitution is fused.
+    // Every entry sees the subtractions in the order k = 0, 1, ... of the inner-product form.
+    static __device__ __forceinline__ void solve(const double* __restrict__ G, unsigned& P, const double (&c)[NA], double* __restrict__ Lt,
+                                                 double (&s)[NA]) {
+        if constexpr (NA > 12) {
+            solve_rows(G, P, c, Lt, s);
+            return;
+        }
+        double A[kTri], y[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const bool mi = (P >> i) & 1u;
+#pragma unroll
+            for (int j = 0; j < i; ++j) A[i * (i + 1) / 2 + j] = (mi && ((P >> j) & 1u)) ? G[i * NA + j] : 0.0;
+            A[i * (i + 1) / 2 + i] = mi ? G[i * NA + i] : 1.0;
+            y[i] = mi ? c[i] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const bool mj = (P >> j) & 1u;
+            double v = A[j * (j + 1) / 2 + j];
+            const bool ok = v > 1e-13 * G[j * NA + j] || !mj;         // numerically dependent archetype: leave it out
+            if (!ok) P &= ~(1u << j);
+            v = ok ? v : 1.0;
+            const double dj = rsqrt(v);
+            Lt[(j * (j + 1) / 2 + j) * kThreads] = dj;                  // the diagonal slot keeps 1 / L_jj
+            y[j] = ok ? y[j] * dj : 0.0;
+            double col[NA];
+#pragma unroll
+            for (int i = j + 1; i < NA; ++i) {
+                col[i] = ok ? A[i * (i + 1) / 2 + j] * dj : 0.0;
+                Lt[(i * (i + 1) / 2 + j) * kThreads] = col[i];
+                y[i] -= col[i] * y[j];
+            }
+#pragma unroll
+            for (int i = j + 1; i < NA; ++i)
+#pragma unroll
+                for (int k = j + 1; k <= i; ++k) A[i * (i + 1) / 2 + k] -= col[i] * col[k];
+        }
+#pragma unroll
+        for (int i = NA - 1; i >= 0; --i) {
+            double v = y[i];
+#pragma unroll
+            for (int k = i + 1; k < NA; ++k) v -= Lt[(k * (k + 1) / 2 + i) * kThreads] * s[k];
+            s[i] = v * Lt[(i * (i + 1) / 2 + i) * kThreads];
+        }
+    }
 };
 
 template <int NA>
@@ -364,10 +414,10 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
     double* G = sh;                        // NA x NA, identity on the padding
     double* Zs = G + NA * NA;              // d x NA, transposed and zero-padded: the archetypes of one coordinate are contiguous
     double* region = Zs + NA * d;          // staged X rows -> Cholesky factors -> [alphas | X] rows of the CTA
-    double* A0 = region + region_doubles;  // T x (na | 1): the previous coefficients of the CTA's spots (warm start)
     const int tid = threadIdx.x;
     const int nacc = na * na + na * d;
     const int dpad = d | 1;                // odd row stride: conflict-free per-thread rows
+    double* A0 = region + region_doubles;  // T x (na | 1): the previous coefficients of the CTA's spots (warm start)
     const int64_t i_base = (int64_t)blockIdx.x * T;
     const int nvalid = (int)((n - i_base) < (int64_t)T ? (n - i_base) : (int64_t)T);
     for (int e = tid; e < NA * d; e += T) {
@@ -420,7 +470,14 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
     const double tol = 1e-12 * fmax(cmax, 1e-300), tiny = 1e-15 * fmax(1.0, cmax);
     double* Lt = region + tid;
     bool active = valid;
+#ifdef CHR_AA_STATS
+    int my_solves = 0, warp_solves = 0;
+#endif
     for (int it = 0; it < 8 * NA && __any_sync(0xffffffffu, active); ++it) {
+#ifdef CHR_AA_STATS
+        my_solves += active ? 1 : 0;
+        ++warp_solves;
+#endif
         unsigned Pn = P;
         AF::solve(G, Pn, c, Lt, s);
         if (active) {
@@ -463,64 +520,97 @@ aa_alpha_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const doub
             }
         }
     }
+#ifdef CHR_AA_STATS
+    if (warm) {   // [0] spots, [1] solves the spots needed, [2] solves the warps executed (x 32 lanes), [3] warps
+        atomicAdd(&g_aa_stats[0], valid ? 1ull : 0ull);
+        atomicAdd(&g_aa_stats[1], (unsigned long long)my_solves);
+        if ((tid & 31) == 0) { atomicAdd(&g_aa_stats[2], (unsigned long long)warp_solves); atomicAdd(&g_aa_stats[3], 1ull); }
+    }
+#endif
     double sum = 0.0;
 #pragma unroll
     for (int a = 0; a < NA; ++a) { x[a] = fmax(x[a], 0.0); sum += x[a]; }
     const double inv = 1.0 / sum;
     __syncthreads();                       // the factors are dead: the region becomes B = [alphas | X | 0] (row = spot)
-    const int W = na + d, Wp = (W + 3) & ~3;      // rows padded to whole strips of 4 columns (32-byte aligned)
+    // rows padded to whole strips of 4 columns; the row stride is = 2 (mod 4) doubles: 16-byte aligned rows, and the
+    // per-thread row writes below see 2-way instead of 4-way bank conflicts
+    const int W = na + d, Wp4 = (W + 3) & ~3, S = Wp4 + 2;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
-        if (a < na) region[tid * Wp + a] = valid ? x[a] * inv : 0.0;
-    for (int c = W; c < Wp; ++c) region[tid * Wp + c] = 0.0;
-    stage_rows(region + na, Wp, X + i_base * d, d, nvalid);
+        if (a < na) region[tid * S + a] = valid ? x[a] * inv : 0.0;
+    for (int c = W; c < Wp4; ++c) region[tid * S + c] = 0.0;
+    stage_rows(region + na, S, X + i_base * d, d, nvalid);
     for (int r = nvalid + (tid >> 5); r < T; r += T >> 5)          // rows past the end of the matrix contribute zeros
-        for (int t = tid & 31; t < d; t += 32) region[r * Wp + na + t] = 0.0;
+        for (int t = tid & 31; t < d; t += 32) region[r * S + na + t] = 0.0;
     stage_wait();
     __syncthreads();
     {   // the CTA's alphas: one contiguous block of the output, written coalesced
         const int q = T / na, rm = T - q * na;
         int row = tid / na, col = tid - row * na;
         for (int e = tid; e < nvalid * na; e += T) {
-            alphas[i_base * na + e] = region[row * Wp + col];
+            alphas[i_base * na + e] = region[row * S + col];
             col += rm;
             row += q;
             if (col >= na) { col -= na; ++row; }
         }
     }
-    // partial  A^T [A | X]  of the CTA (na x W), spots summed in order.  A thread owns one strip of 4 columns of one row a;
-    // strips entirely below the diagonal of A^T A are skipped (their mirror images are written instead), which brings
-    // 12 archetypes x 30 dimensions to 120 strips: one pass of the CTA
-    const int nstrip = Wp >> 2;
-    int total_strips = 0;
-    for (int a = 0; a < na; ++a) total_strips += nstrip - (a >> 2);
-    for (int e = tid; e < total_strips; e += T) {
-        int a = 0, rem = e;
-        while (rem >= nstrip - (a >> 2)) { rem -= nstrip - (a >> 2); ++a; }
-        const int c0 = ((a >> 2) + rem) * 4;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        for (int t = 0; t < T; ++t) {
-            const double* __restrict__ b = region + t * Wp;
-            const double av = b[a];
-            const double2 b01 = *reinterpret_cast<const double2*>(b + c0), b23 = *reinterpret_cast<const double2*>(b + c0 + 2);
-            v0 += av * b01.x; v1 += av * b01.y; v2 += av * b23.x; v3 += av * b23.y;
-        }
-        const double vv[4] = {v0, v1, v2, v3};
+    // partial  A^T [A | X]  of the CTA (na x W) as 4 x 4 register blocks: block row ab (archetypes 4ab .. 4ab+3) times
+    // strip st (columns 4st .. 4st+3), 16 products for four 16-byte loads.  Strips entirely below the diagonal of A^T A
+    // are skipped (their mirror images are written instead).  Warp w sums the spots 32w .. 32w+31, its lanes own the
+    // blocks; the four partial sums of a block are added in warp order (fixed summation tree).
+    const int nstrip = Wp4 >> 2;
+    int nE = 0;
+    for (int ab = 0; ab < NA / 4; ++ab) nE += nstrip - ab;
+    double* red = region + T * S;          // [4 warps][nE][16]
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int e = lane; e < nE; e += 32) {
+        int ab = 0, rem = e;
+        while (rem >= nstrip - ab) { rem -= nstrip - ab; ++ab; }
+        const int st = ab + rem;
+        double acc[4][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int col = c0 + q;
-            if (col < W) {
-                // same layout as aa_alpha_kernel: [na x na | na x d]
-                const int dst = col < na ? a * na + col : na * na + a * d + (col - na);
-                part[(size_t)blockIdx.x * nacc + dst] = vv[q];
-                if (col < na && (col >> 2) > (a >> 2)) part[(size_t)blockIdx.x * nacc + col * na + a] = vv[q];   // skipped mirror strip
-            }
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
+        const double* __restrict__ b = region + (warp * 32) * S;
+        for (int t = 0; t < 32; ++t, b += S) {
+            const double2 a01 = *reinterpret_cast<const double2*>(b + 4 * ab), a23 = *reinterpret_cast<const double2*>(b + 4 * ab + 2);
+            const double2 c01 = *reinterpret_cast<const double2*>(b + 4 * st), c23 = *reinterpret_cast<const double2*>(b + 4 * st + 2);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, cv[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] += av[r] * cv[q];
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[((size_t)warp * nE + e) * 16 + r * 4 + q] = acc[r][q];
+    }
+    __syncthreads();
+    for (int o = tid; o < nE * 16; o += T) {
+        const int e = o >> 4, r = (o >> 2) & 3, q = o & 3;
+        int ab = 0, rem = e;
+        while (rem >= nstrip - ab) { rem -= nstrip - ab; ++ab; }
+        const int a = 4 * ab + r, col = 4 * (ab + rem) + q;
+        if (a >= na || col >= W) continue;
+        double v = red[o];
+#pragma unroll
+        for (int w = 1; w < T / 32; ++w) v += red[(size_t)w * nE * 16 + o];
+        // same layout as aa_alpha_kernel: [na x na | na x d]
+        const int dst = col < na ? a * na + col : na * na + a * d + (col - na);
+        part[(size_t)blockIdx.x * nacc + dst] = v;
+        if (col < na && (col >> 2) > (a >> 2)) part[(size_t)blockIdx.x * nacc + col * na + a] = v;   // skipped mirror strip
     }
 }
 
 static size_t aa_alpha_fixed_region_doubles(int NA, int na, int d) {
-    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128, xs = (size_t)128 * (d | 1), b = (size_t)128 * ((na + d + 3) & ~3);
+    const int W = na + d, Wp4 = (W + 3) & ~3, S = Wp4 + 2, nstrip = Wp4 >> 2;
+    int nE = 0;
+    for (int ab = 0; ab < NA / 4; ++ab) nE += nstrip - ab;
+    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128;                            // Cholesky factors
+    const size_t xs = (size_t)128 * (d | 1);                                       // staged rows
+    const size_t b = (size_t)128 * S + (size_t)4 * nE * 16;                        // [alphas | X] rows + the warps' partial blocks
     size_t r = tri > xs ? tri : xs;
     return r > b ? r : b;
 }
@@ -545,7 +635,8 @@ __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int 
     double* Vv = B + na * d;        // na x na  eigenvectors (columns)
     for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
         double a = 0.0;
-        for (int p = 0; p < nparts; ++p) a += part[(size_t)p * nacc + e];
+#pragma unroll 16
+        for (int p = 0; p < nparts; ++p) a += part[(size_t)p * nacc + e];          // loads issue ahead, the sum stays in order
         if (e < na * na) S[e] = a; else B[e - na * na] = a;
     }
     for (int e = threadIdx.x; e < na * na; e += blockDim.x) Vv[e] = (e / na == e % na) ? 1.0 : 0.0;
@@ -1020,6 +1111,57 @@ aa_rss_direct_kernel(const double* __restrict__ X, int64_t n, int d, const doubl
     }
 }
 
+// rss partials for n_archetypes <= 16: the spot's coefficients stay in registers, Z is kept transposed so that the
+// archetypes of one coordinate come with 16-byte loads (same per-spot arithmetic as aa_rss_kernel)
+template <int NA>
+__global__ void __launch_bounds__(256)
+aa_rss_fixed_kernel(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ alphas, const double* __restrict__ Z,
+                    int na, double* __restrict__ part) {
+    extern __shared__ __align__(16) double sh[];
+    const int dpad = d | 1, apad = na | 1;
+    double* Zt = sh;                       // d x NA, zero on the padding
+    double* Xs = Zt + NA * d;              // 256 x dpad
+    double* As = Xs + 256 * dpad;          // 256 x apad
+    __shared__ double red[32];
+    const int64_t i_base = (int64_t)blockIdx.x * 256;
+    const int nvalid = (int)((n - i_base) < 256 ? (n - i_base) : 256);
+    for (int e = threadIdx.x; e < NA * d; e += 256) {
+        const int t = e / NA, a = e - t * NA;
+        Zt[e] = a < na ? Z[a * d + t] : 0.0;
+    }
+    stage_rows(Xs, dpad, X + i_base * d, d, nvalid);
+    stage_rows(As, apad, alphas + i_base * na, na, nvalid);
+    stage_wait();
+    __syncthreads();
+    double r = 0.0;
+    if ((int)threadIdx.x < nvalid) {
+        const double* __restrict__ x = Xs + threadIdx.x * dpad;
+        double al[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) al[a] = a < na ? As[threadIdx.x * apad + a] : 0.0;
+        for (int t = 0; t < d; ++t) {
+            double v = x[t];
+            const double2* __restrict__ z2 = reinterpret_cast<const double2*>(Zt + t * NA);
+#pragma unroll
+            for (int h = 0; h < NA / 2; ++h) {
+                const double2 z = z2[h];
+                v -= al[2 * h] * z.x;
+                v -= al[2 * h + 1] * z.y;
+            }
+            r += v * v;
+        }
+    }
+    r = warp_sum(r);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
 // rss partials:  sum_i || x_i - sum_a alpha_ia Z_a ||^2.  The CTA's 256 rows of X and of alphas are contiguous blocks:
 // they are staged in shared memory with coalesced loads (odd row strides: conflict-free per-thread rows)
 __global__ void __launch_bounds__(256)
@@ -1342,7 +1484,21 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     aa_beta_finish_kernel<<<na, 64, 0, st>>>(X, d, na, bst, pidx, bcoef, Z);
     // ---- rss
     const size_t sm_rss = ((size_t)na * d + 256 * (size_t)(d | 1) + 256 * (size_t)(na | 1)) * 8;
-    if (sm_rss <= 160 * 1024) {
+    const int NAr = (na + 3) & ~3;
+    const size_t sm_rssf = ((size_t)NAr * d + 256 * (size_t)(d | 1) + 256 * (size_t)(na | 1)) * 8;
+    if (na <= 16 && sm_rssf <= 160 * 1024) {
+#define CHR_RSS_FIXED(NAV)                                                                                                  \
+    do {                                                                                                                    \
+        if (sm_rssf > 48 * 1024)                                                                                            \
+            CHR_CUDA(cudaFuncSetAttribute(aa_rss_fixed_kernel<NAV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rssf)); \
+        aa_rss_fixed_kernel<NAV><<<p.rss_blocks, 256, sm_rssf, st>>>(X, n, d, alphas, Z, na, rsspart);                       \
+    } while (0)
+        if (NAr == 4) CHR_RSS_FIXED(4);
+        else if (NAr == 8) CHR_RSS_FIXED(8);
+        else if (NAr == 12) CHR_RSS_FIXED(12);
+        else CHR_RSS_FIXED(16);
+#undef CHR_RSS_FIXED
+    } else if (sm_rss <= 160 * 1024) {
         if (sm_rss > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_rss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rss));
         aa_rss_kernel<<<p.rss_blocks, 256, sm_rss, st>>>(X, n, d, alphas, Z, na, rsspart);
     } else {

@@ -48,29 +48,29 @@ def blob_data(n, d, seed):
     return rng.normal(size=(n, d)) * (3.0 / np.sqrt(1.0 + np.arange(d)))
 
 
-@pytest.mark.parametrize("n,d,a", [(777, 30, 12), (1300, 11, 3), (2049, 16, 16), (1000, 9, 10), (130, 40, 13)])
-def test_fixed_size_alpha_step_matches_general_path_and_oracle(n, d, a, monkeypatch):
-    """The branch-free alpha kernel (n_archetypes <= 16) against the general active-set kernel (CHR_AA_ALPHA_GENERAL=1)
-    and against the oracle: the NNLS minimisers are unique, so all three agree to rounding."""
+@pytest.mark.parametrize("n,d,a", [(777, 30, 12), (1300, 11, 3), (2049, 16, 16), (1000, 9, 10), (130, 40, 13), (3000, 20, 8)])
+def test_alpha_step_variants_agree_with_each_other_and_the_oracle(n, d, a, monkeypatch):
+    """The branch-free masked-Cholesky alpha kernel (n_archetypes <= 16) against the general active-set kernel
+    (CHR_AA_ALPHA_GENERAL=1) and against the oracle: the NNLS minimisers are unique, so all agree to rounding."""
     X = blob_data(n, d, seed=n + a)
     rows = np.random.default_rng(3).choice(n, a, replace=False)
     Xd = dv.to_device(X, torch.float64)
     runs = {}
-    for general in (False, True):
-        if general:
-            monkeypatch.setenv("CHR_AA_ALPHA_GENERAL", "1")
-        else:
-            monkeypatch.delenv("CHR_AA_ALPHA_GENERAL", raising=False)
+    for variant, env in (("default", None), ("general", "CHR_AA_ALPHA_GENERAL")):
+        monkeypatch.delenv("CHR_AA_ALPHA_GENERAL", raising=False)
+        if env:
+            monkeypatch.setenv(env, "1")
         st = dv.AAState(Xd, a)
         st.init_from_rows(rows)
         rss = [st.iterate() for _ in range(4)]
-        runs[general] = (st.alphas.cpu().numpy(), st.Z.cpu().numpy(), rss)
+        runs[variant] = (st.alphas.cpu().numpy(), st.Z.cpu().numpy(), rss)
     monkeypatch.delenv("CHR_AA_ALPHA_GENERAL", raising=False)
-    al, Z, rss = runs[False]
+    al, Z, rss = runs["default"]
     assert (al >= 0).all() and np.allclose(al.sum(1), 1.0, atol=1e-12)
-    assert np.abs(al - runs[True][0]).max() < 1e-8
-    assert np.abs(Z - runs[True][1]).max() < 1e-8 * np.abs(Z).max()
-    assert np.allclose(rss, runs[True][2], rtol=1e-9)
+    for other in ("general",):
+        assert np.abs(al - runs[other][0]).max() < 1e-8, other
+        assert np.abs(Z - runs[other][1]).max() < 1e-8 * np.abs(Z).max(), other
+        assert np.allclose(rss, runs[other][2], rtol=1e-9), other
     ref = oaa.fit_single(X, np.zeros((n, a)), one_hot_betas(rows, n), max_iter=4, tol=0.0)
     assert np.abs(al - ref["alphas"]).max() < 1e-6
     assert abs(rss[-1] - ref["rss"]) < 1e-6 * ref["rss"]
