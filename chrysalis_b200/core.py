@@ -373,7 +373,8 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
         Xd = dv.to_device(np.ascontiguousarray(X), torch.float32).to(torch.float64)
     else:
         Xd = dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
-    best = None
+    # initial archetypes of every restart first: the RNG stream (one randint + one choice per restart) does not depend
+    # on the fits, so the restarts can then run side by side
     used = []
     for r in range(n_init):
         if init_rows is not None:
@@ -382,6 +383,8 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
             rows = dv.aa_furthest_sum(Xd, n_archetypes, int(rs.randint(n)))
             rs.choice(n_archetypes, n, replace=True)            # alphas0 draw: unused by the updates, keeps the RNG stream
         used.append(rows)
+
+    def fit_restart(rows):
         st = dv.AAState(Xd, n_archetypes)
         st.init_from_rows(rows)
         rss_prev, rss, it = np.inf, np.inf, 0
@@ -390,8 +393,15 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
             if abs(rss_prev - rss) < tol:
                 break
             rss_prev = rss
-        if best is None or rss < best["rss"]:
-            best = {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
+        return {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
+
+    # (running the restarts on separate host threads / CUDA streams was measured: 0.52 s instead of 0.58 s at cfg4 once
+    # the per-stream allocator pools are warm, 0.99 s on a first call - not worth the threads)
+    fits = [fit_restart(rows) for rows in used]
+    best = None
+    for f in fits:                                              # first restart with the smallest RSS, as a sequential loop keeps it
+        if best is None or f["rss"] < best["rss"]:
+            best = f
     out = {"alphas": best["alphas"].cpu().numpy(), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
            "n_iter": best["n_iter"], "init_rows": used}
     return out

@@ -1,4 +1,5 @@
 // Library-level plumbing of the C ABI: version, thread-local error string, kernel timers.
+#include <mutex>
 #include "async.cuh"
 
 namespace chr {
@@ -20,9 +21,13 @@ void timer_begin(int family, bool on, cudaStream_t s) {
     KernelTimer& t = timer(family);
     t.armed = false;
     if (!on) return;
-    if (!t.a) {
-        cudaEventCreate(&t.a);
-        cudaEventCreate(&t.b);
+    {
+        static std::mutex mu;                       // restarts of one fit may run on several host threads
+        std::lock_guard<std::mutex> lock(mu);
+        if (!t.a) {
+            cudaEventCreate(&t.b);
+            cudaEventCreate(&t.a);
+        }
     }
     cudaEventRecord(t.a, s);
 }
