@@ -48,7 +48,8 @@ def blob_data(n, d, seed):
     return rng.normal(size=(n, d)) * (3.0 / np.sqrt(1.0 + np.arange(d)))
 
 
-@pytest.mark.parametrize("n,d,a", [(777, 30, 12), (1300, 11, 3), (2049, 16, 16), (1000, 9, 10), (130, 40, 13), (3000, 20, 8)])
+@pytest.mark.parametrize("n,d,a", [(777, 30, 12), (1300, 11, 3), (2049, 16, 16), (1000, 9, 10), (130, 40, 13), (3000, 20, 8),
+                                   (300, 64, 16), (64, 3, 2), (129, 2, 5)])
 def test_alpha_step_variants_agree_with_each_other_and_the_oracle(n, d, a, monkeypatch):
     """The branch-free masked-Cholesky alpha kernel (n_archetypes <= 16) against the general active-set kernel
     (CHR_AA_ALPHA_GENERAL=1) and against the oracle: the NNLS minimisers are unique, so all agree to rounding."""
