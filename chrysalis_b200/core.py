@@ -112,8 +112,14 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         dense_buf = torch.empty((n, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
         side.wait_stream(main)
     _mark(t0, "coords uploaded, dense buffer allocated")
-    csr = dv.upload_csr(X if size == 1 else X[:, lo:hi])      # asynchronous host -> device copy on the current stream
-    _mark(t0, "counts upload enqueued")
+    Xs = X if size == 1 else X[:, lo:hi]
+    # counts already in pinned (or device) memory upload asynchronously: enqueue that first, then the side-stream work.
+    # Anything else (scipy CSR in pageable memory) is a blocking copy: the side-stream work is launched before it.
+    async_upload = isinstance(Xs, (dv.PinnedCSR, dv.DeviceCSR))
+    csr = None
+    if async_upload:
+        csr = dv.upload_csr(Xs)
+        _mark(t0, "counts upload enqueued")
     with _stream_ctx(side):
         # core.py:64-65  kNN weights, row-standardised
         bbox = dv.spatial_bbox(xy)
@@ -124,6 +130,9 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
         if dense_buf is not None:
             dense_buf.zero_()
+    if csr is None:
+        csr = dv.upload_csr(Xs)
+        _mark(t0, "counts uploaded (blocking copy)")
     if side is not None:
         main.wait_stream(side)
         for t in (rank_of, nbr) + ((plan.buf,) if plan is not None else ()):
@@ -299,7 +308,7 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     V = V * signs[:, None]
     scores = dd.allgather_ragged(dv.pca_scores(P, s, mean, V), n)
     ratio = (evals / total_var).to(torch.float32)
-    return scores.cpu().numpy(), V.to(torch.float32).cpu().numpy(), ratio.cpu().numpy()
+    return dv.to_host(scores), V.to(torch.float32).cpu().numpy(), ratio.cpu().numpy()
 
 
 def pca(adata, n_pcs: int = 50):
@@ -402,7 +411,7 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
     for f in fits:                                              # first restart with the smallest RSS, as a sequential loop keeps it
         if best is None or f["rss"] < best["rss"]:
             best = f
-    out = {"alphas": best["alphas"].cpu().numpy(), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
+    out = {"alphas": dv.to_host(best["alphas"]), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
            "n_iter": best["n_iter"], "init_rows": used}
     return out
 

@@ -78,9 +78,14 @@ class _FakeDevice:
         from oracle import moran as om, weights as ow
         self.om, self.ow = om, ow
 
+    from chrysalis_b200.device import DeviceCSR, PinnedCSR      # svg_stage only asks "is the input already pinned?"
+
     def upload_csr(self, X):
         import scipy.sparse as sp
         return sp.csr_matrix(X)
+
+    def to_host(self, t):
+        return t.cpu().numpy()
 
     def csr_gene_nnz(self, csr):
         return torch.from_numpy(np.asarray((csr > 0).sum(0)).ravel().astype(np.int32))

@@ -7,6 +7,7 @@ by ~1e-7 - the oracle's float32 and float64 statements differ by that much on th
 for |I| < 0.02.  Exact known answers on lattices are held to 1e-12.
 """
 import numpy as np
+import scipy.sparse as sp
 import pytest
 import torch
 
@@ -250,6 +251,29 @@ def test_preprocessing_kernels_match_scanpy_semantics(golden_hex):
     assert np.array_equal(got == 0, ref == 0)
     assert np.allclose(got, ref, rtol=3e-7, atol=0)
     assert float(dense[:, ref.shape[1]:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("n,g", [(301, 500), (64, 51300), (1000, 96)])
+def test_densify_through_a_row_permutation_matches_the_host(n, g):
+    """csr_densify (scale in float64, log1p, scatter through a row permutation) against scipy's todense, and with a
+    caller-provided pre-zeroed buffer."""
+    rng = np.random.default_rng(n + g)
+    X = sp.random(n, g, density=0.03, format="csr", random_state=rng, data_rvs=lambda k: rng.integers(1, 40, k).astype(np.float32))
+    X = sp.csr_matrix(X, dtype=np.float32)
+    csr = dv.upload_csr(X)
+    keep = torch.from_numpy(rng.random(g) < 0.7).cuda()
+    gene_col = torch.where(keep, torch.cumsum(keep.int(), 0, dtype=torch.int32) - 1, torch.tensor(-1, dtype=torch.int32, device="cuda"))
+    n_keep = int(keep.sum())
+    perm = torch.from_numpy(rng.permutation(n)).cuda()
+    scale = torch.from_numpy(rng.uniform(0.5, 2.0, n)).cuda()
+    dense = dv.csr_densify(csr, gene_col, n_keep, scale, perm, True)
+    ref = np.log1p((X[:, keep.cpu().numpy()].toarray().astype(np.float64) * scale.cpu().numpy()[:, None]).astype(np.float32))
+    got = dense.cpu().numpy()
+    assert np.array_equal(got[perm.cpu().numpy(), :n_keep] == 0, ref == 0)
+    assert np.allclose(got[perm.cpu().numpy(), :n_keep], ref, rtol=3e-7, atol=0)
+    assert float(np.abs(got[:, n_keep:]).sum()) == 0.0
+    again = dv.csr_densify(csr, gene_col, n_keep, scale, perm, True, out=torch.zeros_like(dense))
+    assert torch.equal(again, dense)
 
 
 @pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
