@@ -129,7 +129,7 @@ def build_device_workload(args, rank, torch, dv, synth):
     xy = lattice_coords(n, 42)
     xy_d = dv.to_device(xy, torch.float64)
     bbox = dv.spatial_bbox(xy_d)
-    order = dv.hilbert_order(xy_d, bbox)
+    order = dv.spatial_order(xy_d, bbox)
     xy_s = xy_d[order].contiguous()
     nbr = dv.knn_build(xy_s, k, bbox)
     # counts, generated on device in Hilbert row order, kept as CSR pieces

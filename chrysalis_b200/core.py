@@ -123,7 +123,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     with _stream_ctx(side):
         # core.py:64-65  kNN weights, row-standardised
         bbox = dv.spatial_bbox(xy)
-        order = dv.hilbert_order(xy, bbox)          # spatially coherent row order of the dense matrix
+        order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
         rank_of = torch.empty_like(order)
         rank_of[order] = torch.arange(n, device=order.device)
         nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)

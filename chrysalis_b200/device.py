@@ -159,6 +159,53 @@ def hilbert_order(xy: torch.Tensor, bbox: torch.Tensor | None = None) -> torch.T
     return torch.sort(keys, stable=True).indices
 
 
+def square_lattice_pitch(xy: torch.Tensor, bbox: torch.Tensor) -> float | None:
+    """Pitch of the square lattice the spots sit on (Visium HD / Stereo-seq bins), or None.
+
+    The pitch candidate is the median nearest-neighbour distance (one exact k = 1 pass of the kNN kernel); the spots
+    form a lattice when, measured from the bounding-box corner, 98 % of them lie within a tenth of a pitch of a lattice
+    node on both axes (a jittered lattice passes, a hex lattice or random beads do not).  One host round trip."""
+    n = xy.shape[0]
+    if n < 64:
+        return None
+    nb = knn_build(xy, 1, bbox)
+    d1 = (xy[nb[:, 0].long()] - xy).norm(dim=1)
+    p = d1.median()
+    # the nearest of four jittered neighbours is biased low by a fraction of the jitter, which adds up over hundreds of
+    # nodes: refit the pitch by least squares on the node numbers, first near the corner, then over the whole lattice
+    rel = xy - bbox[:2]
+    for limit in (64.0, 1e18):
+        u = rel / p
+        k = u.round() * (u < limit)
+        p = (rel * k).sum() / (k * k).sum().clamp_min(1.0)
+    u = rel / p
+    near = ((u - u.round()).abs() < 0.1).all(dim=1).double().mean()
+    extent = (bbox[2:] - bbox[:2]).max() / p
+    p_h, near_h, extent_h = (float(v) for v in torch.stack([p, near, extent]).cpu())
+    if not (p_h > 0.0 and near_h >= 0.98 and extent_h < 32000.0):
+        return None
+    return p_h
+
+
+def spatial_order(xy: torch.Tensor, bbox: torch.Tensor | None = None) -> torch.Tensor:
+    """Row order of the dense matrix: spots sorted along a Hilbert curve.  On a square lattice the dyadic grid of the
+    curve is aligned with the lattice (node i -> cell block [m i, m i + m), m a power of two), so that 4 consecutive
+    spots are an exact 2 x 2 block: 6 of the 16 unordered neighbour pairs of a quad then live inside it and the W plan
+    needs fewer list rows (11.83 -> 11.50 ms for the cfg4 Moran pass)."""
+    bbox = spatial_bbox(xy) if bbox is None else bbox
+    p = square_lattice_pitch(xy, bbox)
+    if p is None:
+        return hilbert_order(xy, bbox)
+    b = [float(v) for v in bbox.cpu()]
+    w = max(b[2] - b[0], b[3] - b[1]) / p + 1.0
+    m = 1
+    while (w + 1.0) * m * 2 <= 65536.0:
+        m *= 2
+    span = 65535.0 * p / m                               # chr_hilbert_keys quantises with 65535 / span: m cells per pitch
+    snapped = torch.tensor([b[0] - p / 2, b[1] - p / 2, b[0] - p / 2 + span, b[1] - p / 2 + span], dtype=torch.float64, device=xy.device)
+    return hilbert_order(xy, snapped)
+
+
 def knn_build(xy: torch.Tensor, k: int, bbox: torch.Tensor | None = None) -> torch.Tensor:
     """k nearest other spots of every spot: int32 [n, k] (row-standardised W is implicit)."""
     assert xy.dtype == torch.float64 and xy.is_contiguous() and xy.shape[1] == 2

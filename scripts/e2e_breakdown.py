@@ -26,7 +26,7 @@ for rep in range(3):
     t1 = sync(); t["h2d"] = t1 - t0
     pts = np.array(xy_host, dtype=np.float64, copy=True); pts[:, 1] *= -1
     xy = dv.to_device(pts, torch.float64)
-    bbox = dv.spatial_bbox(xy); order = dv.hilbert_order(xy, bbox)
+    bbox = dv.spatial_bbox(xy); order = dv.spatial_order(xy, bbox)
     rank_of = torch.empty_like(order); rank_of[order] = torch.arange(n, device=order.device)
     nb = dv.knn_build(xy[order].contiguous(), k, bbox)
     plan = dv.moran_plan(nb)

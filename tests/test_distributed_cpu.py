@@ -107,6 +107,8 @@ class _FakeDevice:
     def hilbert_order(self, xy, bbox):
         return torch.arange(xy.shape[0])
 
+    spatial_order = hilbert_order
+
     def knn_build(self, xy, k, bbox):
         return torch.from_numpy(self.ow.knn_neighbors(xy.numpy(), k).astype(np.int32))
 

@@ -235,6 +235,40 @@ def test_hilbert_order_is_a_permutation_and_local():
     assert np.median(step) < 3 * np.sqrt(np.ptp(xy[:, 0]) * np.ptp(xy[:, 1]) / len(xy))
 
 
+def test_spatial_order_aligns_quads_with_a_square_lattice():
+    """On a (jittered) square lattice the row order is a Hilbert curve whose grid is snapped to the lattice: groups of 4
+    consecutive spots are 2 x 2 blocks.  Hex lattices and random beads keep the plain curve."""
+    xy = synth.make_coords("square", 40000, seed=1)
+    xyd = dv.to_device(xy, torch.float64)
+    bbox = dv.spatial_bbox(xyd)
+    assert abs(dv.square_lattice_pitch(xyd, bbox) - 100.0) < 0.1
+    order = dv.spatial_order(xyd, bbox).cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(len(xy)))
+    quads = xy[order].reshape(-1, 4, 2)
+    span = quads.max(1) - quads.min(1)
+    assert (np.abs(span - 100.0) < 5.0).all(1).mean() > 0.95                  # exact 2 x 2 blocks
+    plain = xy[dv.hilbert_order(xyd, bbox).cpu().numpy()].reshape(-1, 4, 2)
+    assert (np.abs(plain.max(1) - plain.min(1) - 100.0) < 5.0).all(1).mean() < 0.9
+    for kind in ("hex", "random"):
+        other = dv.to_device(synth.make_coords(kind, 20000, seed=3), torch.float64)
+        assert dv.square_lattice_pitch(other, dv.spatial_bbox(other)) is None
+        assert torch.equal(dv.spatial_order(other), dv.hilbert_order(other))
+
+
+def test_detect_svgs_on_a_square_lattice_matches_the_oracle():
+    """The lattice-snapped row order only relabels the spots: Moran's I, Geary's C and the selection follow the oracle."""
+    xy = synth.make_coords("square", 3600, seed=5)
+    X, _ = synth.make_counts_csr(xy, 400, n_zones=5, seed=5)
+    ad = ch.AnnDataLite(X, obsm={"spatial": xy})
+    ch.detect_svgs(ad, neighbors=8, top_svg=60, geary=True)
+    ref = osvg.detect_svgs(X, xy, neighbors=8, top_svg=60)
+    m = ref["gene_mask"]
+    got = ad.var["Moran's I"].to_numpy()
+    assert np.array_equal(np.isnan(got), ~m)
+    assert np.allclose(got[m], ref["morans"][m], rtol=1e-5, atol=2e-7)
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+
+
 def test_preprocessing_kernels_match_scanpy_semantics(golden_hex):
     z = golden_hex
     X = golden_csr(z)
