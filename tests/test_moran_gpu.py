@@ -323,6 +323,30 @@ def test_detect_svgs_end_to_end(name, request):
     assert np.array_equal(ad.var["spatially_variable"].to_numpy(), z["spatially_variable"])
 
 
+def test_detect_svgs_with_empty_spots_and_with_no_gene_passing_the_filter():
+    """Spots without any count (scanpy leaves their rows untouched: total 0 is not scaled) and the degenerate call in
+    which the min_spots filter removes every gene (all NaN, nothing selected) follow the oracle."""
+    xy = synth.make_coords("hex", 900, seed=11)
+    X, _ = synth.make_counts_csr(xy, 300, n_zones=4, seed=11)
+    X = X.tolil()
+    for i in (0, 17, 450, 899):
+        X[i, :] = 0
+    X = sp.csr_matrix(X.tocsr(), dtype=np.float32)
+    X.eliminate_zeros()
+    ad = ch.AnnDataLite(X, obsm={"spatial": xy})
+    ch.detect_svgs(ad, neighbors=6, top_svg=40)
+    ref = osvg.detect_svgs(X, xy, neighbors=6, top_svg=40)
+    m = ref["gene_mask"]
+    got = ad.var["Moran's I"].to_numpy()
+    assert m.any() and np.array_equal(np.isnan(got), ~m)
+    assert np.allclose(got[m], ref["morans"][m], rtol=1e-5, atol=2e-7)
+    assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+    ad2 = ch.AnnDataLite(X, obsm={"spatial": xy})
+    ch.detect_svgs(ad2, min_spots=0.999, neighbors=6)
+    assert np.isnan(ad2.var["Moran's I"].to_numpy()).all()
+    assert not ad2.var["spatially_variable"].to_numpy().any()
+
+
 def test_detect_svgs_respects_existing_log1p(golden_hex):
     z = golden_hex
     Xn = osvg.normalize_total_log1p(golden_csr(z))
