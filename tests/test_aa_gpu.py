@@ -27,7 +27,7 @@ def one_hot_betas(rows, n):
     return B
 
 
-@pytest.mark.parametrize("n,d,a", [(600, 5, 4), (1500, 8, 6), (4035, 20, 8)])
+@pytest.mark.parametrize("n,d,a", [(600, 5, 4), (1500, 8, 6), (4035, 20, 8), (900, 24, 20), (700, 40, 33)])
 def test_single_iteration_matches_oracle(n, d, a):
     X = simplex_data(n, d, a, seed=n)
     rows = np.random.default_rng(1).choice(n, a, replace=False)
