@@ -159,20 +159,13 @@ def hilbert_order(xy: torch.Tensor, bbox: torch.Tensor | None = None) -> torch.T
     return torch.sort(keys, stable=True).indices
 
 
-def square_lattice_pitch(xy: torch.Tensor, bbox: torch.Tensor) -> float | None:
-    """Pitch of the square lattice the spots sit on (Visium HD / Stereo-seq bins), or None.
-
-    The pitch candidate is the median nearest-neighbour distance (one exact k = 1 pass of the kNN kernel); the spots
-    form a lattice when, measured from the bounding-box corner, 98 % of them lie within a tenth of a pitch of a lattice
-    node on both axes (a jittered lattice passes, a hex lattice or random beads do not).  One host round trip."""
-    n = xy.shape[0]
-    if n < 64:
-        return None
-    nb = knn_build(xy, 1, bbox)
-    d1 = (xy[nb[:, 0].long()] - xy).norm(dim=1)
+def lattice_pitch_from_nn(xy: torch.Tensor, bbox: torch.Tensor, d1: torch.Tensor) -> float | None:
+    """The decision behind ``square_lattice_pitch`` given every spot's nearest-neighbour distance ``d1`` (plain tensor
+    arithmetic, device-agnostic).  The pitch candidate is the median of ``d1``; the nearest of four jittered neighbours
+    is biased low by a fraction of the jitter, which adds up over hundreds of nodes, so the pitch is refitted by least
+    squares on the node numbers, first near the corner, then over the whole lattice.  The spots form a lattice when,
+    measured from the bounding-box corner, 98 % of them lie within a tenth of a pitch of a node on both axes."""
     p = d1.median()
-    # the nearest of four jittered neighbours is biased low by a fraction of the jitter, which adds up over hundreds of
-    # nodes: refit the pitch by least squares on the node numbers, first near the corner, then over the whole lattice
     rel = xy - bbox[:2]
     for limit in (64.0, 1e18):
         u = rel / p
@@ -181,10 +174,20 @@ def square_lattice_pitch(xy: torch.Tensor, bbox: torch.Tensor) -> float | None:
     u = rel / p
     near = ((u - u.round()).abs() < 0.1).all(dim=1).double().mean()
     extent = (bbox[2:] - bbox[:2]).max() / p
-    p_h, near_h, extent_h = (float(v) for v in torch.stack([p, near, extent]).cpu())
+    p_h, near_h, extent_h = (float(v) for v in torch.stack([p, near, extent]).cpu())    # one host round trip
     if not (p_h > 0.0 and near_h >= 0.98 and extent_h < 32000.0):
         return None
     return p_h
+
+
+def square_lattice_pitch(xy: torch.Tensor, bbox: torch.Tensor) -> float | None:
+    """Pitch of the square lattice the spots sit on (Visium HD / Stereo-seq bins), or None (hex lattice, random beads).
+    Nearest-neighbour distances come from one exact k = 1 pass of the kNN kernel."""
+    if xy.shape[0] < 64:
+        return None
+    nb = knn_build(xy, 1, bbox)
+    d1 = (xy[nb[:, 0].long()] - xy).norm(dim=1)
+    return lattice_pitch_from_nn(xy, bbox, d1)
 
 
 def spatial_order(xy: torch.Tensor, bbox: torch.Tensor | None = None) -> torch.Tensor:

@@ -145,3 +145,26 @@ def test_estimate_compartments_fields(monkeypatch):
     ad2 = ch.AnnDataLite(np.zeros((4, 3), np.float32), obsm={"spatial": np.zeros((4, 2))})
     with pytest.raises(ValueError, match="chr_X_pca"):
         ch.estimate_compartments(ad2)
+
+
+@pytest.mark.parametrize("kind,n,expect", [("square", 90000, 100.0), ("square", 4000, 100.0), ("hex", 20000, None), ("random", 20000, None)])
+def test_square_lattice_detection(kind, n, expect):
+    """The row-order heuristic of device.spatial_order: a (jittered) square lattice yields its pitch to 1e-4 even though
+    the nearest-neighbour distance is biased low by the jitter; hex lattices and random beads are left alone."""
+    import torch
+    from scipy.spatial import cKDTree
+    from chrysalis_b200 import device as dv, synth
+    xy = synth.make_coords(kind, n, seed=3)
+    d1 = cKDTree(xy).query(xy, k=2)[0][:, 1]
+    t = torch.from_numpy(xy)
+    bbox = torch.cat([t.min(0).values, t.max(0).values])
+    p = dv.lattice_pitch_from_nn(t, bbox, torch.from_numpy(d1))
+    if expect is None:
+        assert p is None
+    else:
+        assert np.median(d1) < expect * (1 - 5e-4)          # the raw estimate drifts by more than a node over the lattice
+        assert abs(p - expect) < 1e-2
+    # exact lattice, duplicated coordinates (median distance 0): no lattice claimed, no division blow-up
+    dup = torch.zeros((100, 2), dtype=torch.float64)
+    assert dv.lattice_pitch_from_nn(dup, torch.zeros(4, dtype=torch.float64), torch.zeros(100, dtype=torch.float64)) is None
+
