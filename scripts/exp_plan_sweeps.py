@@ -6,7 +6,7 @@ from chrysalis_b200 import device as dv, synth
 n, g, k = 700_000, 2304, 8
 xy = torch.from_numpy(synth.make_coords("square", n, seed=0)).cuda()
 bbox = dv.spatial_bbox(xy)
-order = dv.hilbert_order(xy, bbox)
+order = dv.spatial_order(xy, bbox)   # lattice-snapped on this square lattice
 nbr = dv.knn_build(xy[order].contiguous(), k, bbox)
 X = torch.rand((n, dv.dense_ld(g)), device="cuda")
 for sweeps in sys.argv[1:]:

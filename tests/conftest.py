@@ -34,5 +34,10 @@ def golden_random():
 
 
 @pytest.fixture(scope="session")
+def golden_square():
+    return load_golden("svg_square_k8")
+
+
+@pytest.fixture(scope="session")
 def golden_pca_aa():
     return load_golden("pca_aa_hex")

@@ -6,7 +6,8 @@ or golden vectors, so these fixtures pin the ORACLE (a drift guard) and give the
 fixed inputs; they are not outputs of the reference.  sklearn PCA outputs ARE the reference's
 own call (core.py:127).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # everything
+    python tests/golden/make_golden.py square     # only svg_square_k8.npz
 """
 import os
 import sys
@@ -42,9 +43,13 @@ def svg_case(name, kind, n, g, k, seed, **kw):
 
 
 def main():
-    # cfg1-shaped (hex, k=6) and cfg2-shaped (random beads, k=8), down-scaled
+    if sys.argv[1:] == ["square"]:     # add the lattice case without rewriting the other fixtures
+        svg_case("svg_square_k8", "square", 1600, 300, 8, 11, top_svg=40, min_morans=0.05)
+        return
+    # cfg1-shaped (hex, k=6), cfg2-shaped (random beads, k=8) and cfg3/cfg4-shaped (square lattice of bins, k=8), down-scaled
     X, xy, r = svg_case("svg_hex_k6", "hex", 900, 400, 6, 42, top_svg=60)
     svg_case("svg_random_k8", "random", 1200, 300, 8, 7, top_svg=40, min_morans=0.05)
+    svg_case("svg_square_k8", "square", 1600, 300, 8, 11, top_svg=40, min_morans=0.05)
 
     # PCA + AA on the hex case's SVG matrix (reference flow: normalise full adata, then pca/aa)
     Xn = osvg.normalize_total_log1p(X)

@@ -15,7 +15,7 @@ def _oracle_stage(z):
     return stage
 
 
-@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random", "golden_square"])
 def test_fields_and_selection_match_oracle(name, request, monkeypatch):
     z = request.getfixturevalue(name)
     monkeypatch.setattr(core, "svg_stage", _oracle_stage(z))

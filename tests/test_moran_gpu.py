@@ -47,7 +47,7 @@ def gpu_moran(dense, nbr, geary=False, ld=None, **kw):
     return I.cpu().numpy(), (C.cpu().numpy() if geary else None), st
 
 
-@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random", "golden_square"])
 def test_moran_kernel_matches_golden(name, request):
     z = request.getfixturevalue(name)
     m = z["gene_mask"]
@@ -310,7 +310,7 @@ def test_densify_through_a_row_permutation_matches_the_host(n, g):
     assert torch.equal(again, dense)
 
 
-@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random", "golden_square"])
 def test_detect_svgs_end_to_end(name, request):
     z = request.getfixturevalue(name)
     ad = ch.AnnDataLite(golden_csr(z), obsm={"spatial": z["xy"]})

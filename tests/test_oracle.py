@@ -83,7 +83,7 @@ def test_selection_rule():
     assert osvg.select_svgs(I, scored, 3, 0.25).tolist() == [True, True, False, True, False, False, False]
 
 
-@pytest.mark.parametrize("name", ["golden_hex", "golden_random"])
+@pytest.mark.parametrize("name", ["golden_hex", "golden_random", "golden_square"])
 def test_oracle_reproduces_golden(name, request):
     z = request.getfixturevalue(name)
     r = osvg.detect_svgs(golden_csr(z), z["xy"], neighbors=int(z["k"]), top_svg=int(z["top_svg"]),
