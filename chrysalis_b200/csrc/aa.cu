@@ -10,10 +10,16 @@
 // with rows of alphas / betas renormalised to sum 1.  All arithmetic is fp64 (the reference
 // upcasts to float64 inside numpy / scipy.optimize.nnls).
 //
-// NNLS is Lawson-Hanson's active-set method on the normal equations (scipy.optimize.nnls is the
-// same method with QR updates): the alpha problems share G = Z Z^T + M^2 (kept in shared
-// memory, one thread per spot); the beta problems stream X once per active-set step for all
-// archetypes together (gradient = skinny GEMM + arg-max), then one CTA updates the passive sets.
+// NNLS is Lawson-Hanson's active-set method on the normal equations (scipy.optimize.nnls is the same method with QR
+// updates; the minimisers are unique, so any correct active-set path gives the same coefficients).
+//   alpha step  (N small problems sharing G = Z Z^T + M^2): one thread per spot.  Up to 16 archetypes a branch-free
+//               kernel solves every passive set as a masked full-size Cholesky system so that the lanes of a warp never
+//               diverge (aa_alpha_fixed_kernel); more archetypes take the index-list kernel (aa_alpha_kernel).  Both
+//               warm-start from the previous coefficients and leave the CTA's partial A^T A | A^T X behind.
+//   pinv step   one CTA: fixed-order reduction of the partials, Jacobi eigen-decomposition, numpy's cut-off.
+//   beta step   (A problems with N unknowns each): every archetype advances one active-set step per sweep over X -
+//               gradient = skinny product + arg-max (aa_beta_grad_*), then one warp per archetype refits its passive
+//               set in shared memory (beta_refit_warp).  Passive sets are warm-started from the previous iteration.
 #include "common.cuh"
 
 namespace chr {
