@@ -35,6 +35,17 @@ def test_library_exports_every_declared_symbol(lib):
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr), name
 
 
+def test_binding_argument_counts_match_the_header():
+    """Every ctypes signature in _lib.py has as many arguments as the prototype in the header."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = dict(re.findall(r"\b(chr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert sorted(protos) == _lib.exported_symbols()
+    for name, args in protos.items():
+        args = args.strip()
+        n_args = 0 if args in ("", "void") else len(args.split(","))
+        assert n_args == len(_lib._SIGNATURES[name][1]), name
+
+
 def test_version_and_error_string(lib):
     assert lib.chr_version() >= 100
     assert isinstance(lib.chr_last_error(), bytes)
@@ -55,6 +66,22 @@ def test_argument_validation_precedes_any_cuda_call(lib):
     assert rc != 0 and b"chr_knn_build" in lib.chr_last_error()
     rc = lib.chr_moran_plan_build(None, 10, 3, None, 0, None, None, 0, None)
     assert rc != 0 and b"chr_moran_plan_build" in lib.chr_last_error()
+
+
+def test_aa_and_pca_entry_points_validate_their_shapes(lib):
+    # limits of the archetype kernels (<= 64 archetypes, <= 64 dimensions) and of the eigensolver are reported, not hit
+    one = ctypes.c_double(0.0)
+    p = ctypes.addressof(one)
+    rc = lib.chr_aa_iterate(p, 100, 65, 8, 200.0, 0, p, p, p, None, p, 1 << 20, None)
+    assert rc != 0 and b"chr_aa_iterate" in lib.chr_last_error()
+    rc = lib.chr_aa_iterate(p, 100, 8, 1, 200.0, 0, p, p, p, None, p, 1 << 20, None)
+    assert rc != 0 and b"n_archetypes" in lib.chr_last_error()
+    rc = lib.chr_aa_iterate(p, 100, 8, 4, 200.0, 0, p, p, p, None, p, 16, None)
+    assert rc != 0 and b"workspace too small" in lib.chr_last_error()
+    rc = lib.chr_eigh_topk_f64(p, 50, 60, 60, p, p, p, p, 1 << 20, None)
+    assert rc != 0 and b"chr_eigh_topk_f64" in lib.chr_last_error()
+    assert lib.chr_eigh_default_steps(2000, 30) == 122 and lib.chr_eigh_default_steps(40, 30) == 40
+    assert lib.chr_aa_workspace_bytes(700000, 30, 12) < (1 << 28)
 
 
 def test_no_cpu_fallback_without_cuda():
