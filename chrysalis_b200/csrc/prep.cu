@@ -11,13 +11,6 @@
 
 namespace chr {
 
-__global__ void csr_gene_nnz_kernel(const int32_t* __restrict__ indices, const float* __restrict__ data, int64_t nnz,
-                                    int32_t* __restrict__ gene_nnz) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride)
-        if (data[e] > 0.f) atomicAdd(gene_nnz + indices[e], 1);
-}
-
 // nnz is read from indptr[n] on the device, so the launch needs no host sync
 __global__ void csr_gene_nnz_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                          const float* __restrict__ data, int64_t n, int32_t* __restrict__ gene_nnz) {
