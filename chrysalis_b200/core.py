@@ -41,6 +41,12 @@ def _make_unique(names) -> pd.Index:
     return pd.Index(out)
 
 
+# Limits of the device kernels that the reference does not have (documented deviations; checked up front so that a
+# call outside them raises a clear ValueError instead of failing inside the library)
+MAX_PCS = 128            # chr_eigh_topk_f64: Ritz pairs kept
+MAX_ARCHETYPES = 64      # aa.cu kAaMaxA
+MAX_AA_DIMS = 64         # aa.cu kAaMaxD
+
 _SIDE_STREAMS = {}
 SVG_TRACE = []     # CHR_SVG_TRACE=1: (label, host seconds since the call started) of the last svg_stage call
 
@@ -126,7 +132,9 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
         rank_of = torch.empty_like(order)
         rank_of[order] = torch.arange(n, device=order.device)
-        nbr = dv.knn_build(xy[order].contiguous(), neighbors, bbox)
+        # kNN on the spots as given: distance ties go to the lower ORIGINAL spot id (knn.cu), so W does not depend on the
+        # internal row order and is the W local_morans_i builds; then relabelled into the row order of the dense matrix
+        nbr = rank_of.to(torch.int32)[dv.knn_build(xy, neighbors, bbox)[order].long()].contiguous()
         plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
         if dense_buf is not None:
             dense_buf.zero_()
@@ -259,11 +267,12 @@ def local_morans_i(adata, keys, neighbors: int = 6, permutations: int = 999, see
     pts[:, 1] = pts[:, 1] * -1
     xy = dv.to_device(pts, torch.float64)
     nbr = dv.knn_build(xy, neighbors, dv.spatial_bbox(xy))
-    seed = int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
+    # one independent 64-bit key per variable (SeedSequence.spawn): adjacent variables never share redraw streams
+    seeds = [int(c.generate_state(1, np.uint64)[0]) for c in np.random.SeedSequence(seed).spawn(len(keys))]
     Is, q, ps = (np.empty((n, len(keys)), dtype=dt) for dt in (np.float32, np.int32, np.float32))
     yd = dv.to_device(np.ascontiguousarray(vals.T), torch.float32)
     for j in range(len(keys)):
-        res = dv.local_moran(yd[j], nbr, permutations=int(permutations), seed=seed + j)
+        res = dv.local_moran(yd[j], nbr, permutations=int(permutations), seed=seeds[j])
         Is[:, j], q[:, j] = res["Is"].cpu().numpy(), res["q"].cpu().numpy()
         if permutations:
             ps[:, j] = res["p_sim"].cpu().numpy()
@@ -290,6 +299,8 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     if not 0 < n_pcs < min(n, s):
         raise ValueError(f"n_components={n_pcs} must be strictly less than min(n_samples, n_features)={min(n, s)} "
                          "with svd_solver='arpack'")
+    if n_pcs > MAX_PCS:       # deviation from the reference (no such limit there): the eigensolver keeps <= 128 Ritz pairs
+        raise ValueError(f"n_pcs={n_pcs} exceeds this implementation's limit of {MAX_PCS} principal components")
     rank, size = dd.world()
     lo, hi = dd.shard_range(n, rank, size)
     csr = dv.upload_csr(X if size == 1 else X[lo:hi])
@@ -300,7 +311,11 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
     mean = dd.allreduce_sum_(dv.column_sums(P, s)) / n
     C = dd.allreduce_sum_(dv.gram_centered(P, s, mean, timing=timing)) / (n - 1)   # covariance (ddof=1)
     total_var = torch.diagonal(C).sum()
-    evals, V, _ = dv.eigh_topk(C, n_pcs)
+    evals, V, worst = dv.eigh_topk(C, n_pcs)
+    if worst > 1e-6:          # Krylov depth capped before the Ritz residuals met the bound: say so, do not hand back silently
+        import warnings
+        warnings.warn(f"chrysalis_b200.pca: eigensolver stopped at a relative residual of {worst:.2e} "
+                      f"({s} features, {n_pcs} components); the trailing components may be inaccurate", RuntimeWarning)
     # svd_flip(u, v, u_based_decision=False): largest-|.| entry of every component is positive
     idx = V.abs().argmax(dim=1)
     signs = torch.sign(V[torch.arange(V.shape[0], device=V.device), idx])
@@ -375,6 +390,11 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
     Returns a dict with alphas (N, A), archetypes (A, d), rss, n_iter and the initial rows used."""
     X = np.asarray(X)
     n, d = X.shape
+    if n_archetypes > MAX_ARCHETYPES or d > MAX_AA_DIMS:
+        raise ValueError(f"aa: this implementation supports n_archetypes <= {MAX_ARCHETYPES} and <= {MAX_AA_DIMS} embedding "
+                         f"dimensions (got n_archetypes={n_archetypes}, n_pcs={d})")
+    if not n_archetypes < n:
+        raise ValueError(f"aa: n_archetypes={n_archetypes} must be smaller than the number of observations ({n})")
     rs = np.random.RandomState(random_state)
     # numpy upcasts the float32 scores to float64 inside archetypes; here the (exact) widening happens on the device,
     # so half the bytes cross PCIe and the host never builds the float64 copy

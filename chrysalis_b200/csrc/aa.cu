@@ -1226,10 +1226,13 @@ __global__ void __launch_bounds__(256) aa_sum_kernel(const double* __restrict__ 
     }
 }
 
-__global__ void aa_gather_rows_kernel(const double* __restrict__ X, int d, const int64_t* __restrict__ rows, int na,
+// a row index outside [0, n) never touches X: the archetype becomes NaN, which every later step carries to the result
+__global__ void aa_gather_rows_kernel(const double* __restrict__ X, int64_t n, int d, const int64_t* __restrict__ rows, int na,
                                       double* __restrict__ Z) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < na * d) Z[e] = X[rows[e / d] * d + e % d];
+    if (e >= na * d) return;
+    const int64_t r = rows[e / d];
+    Z[e] = (r >= 0 && r < n) ? X[r * d + e % d] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // ---- FurthestSum seeding (Morup & Hansen 2012; the initialisation archetypes 0.4.x draws) -----------------
@@ -1331,7 +1334,9 @@ int chr_aa_init_archetypes(const double* X, int64_t n, int d, const int64_t* row
                            chr_stream_t stream) {
     using namespace chr;
     CHR_REQUIRE(X && rows && Z && n > 0 && d > 0 && n_archetypes > 0, "chr_aa_init_archetypes: bad arguments");
-    aa_gather_rows_kernel<<<(unsigned)ceil_div(n_archetypes * d, 256), 256, 0, (cudaStream_t)stream>>>(X, d, rows, n_archetypes, Z);
+    CHR_REQUIRE(d <= kAaMaxD && n_archetypes <= kAaMaxA, "chr_aa_init_archetypes: need d <= %d and n_archetypes <= %d (got %d, %d)",
+                kAaMaxD, kAaMaxA, d, n_archetypes);
+    aa_gather_rows_kernel<<<(unsigned)ceil_div(n_archetypes * d, 256), 256, 0, (cudaStream_t)stream>>>(X, n, d, rows, n_archetypes, Z);
     CHR_LAUNCH_CHECK();
     return 0;
 }
@@ -1350,6 +1355,8 @@ int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(X && rows_out && workspace, "chr_aa_furthest_sum: null pointer argument");
     CHR_REQUIRE(n > 0 && d > 0 && n_archetypes >= 1 && n_archetypes < n && first >= 0 && first < n, "chr_aa_furthest_sum: bad arguments");
+    CHR_REQUIRE(d <= kAaMaxD && n_archetypes <= kAaMaxA, "chr_aa_furthest_sum: need d <= %d and n_archetypes <= %d (got %d, %d)", kAaMaxD,
+                kAaMaxA, d, n_archetypes);
     CHR_REQUIRE(workspace_bytes >= chr_aa_furthest_sum_workspace_bytes(n) - 256, "chr_aa_furthest_sum: workspace too small");
     const int nb = (int)ceil_div<int64_t>(n, 4096);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -1366,7 +1373,7 @@ int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int
     // the host algorithm (chrysalis_b200/core.py:_furthest_sum): picks = [first]; for step in 1 .. A + 10:
     //   if step > A - 1: drop the oldest pick (subtract its distances, make it available again)
     //   add the distances to the current point; next = arg-max over available points; append
-    int64_t picks[kAaMaxA + 16];
+    int64_t picks[kAaMaxA + 16];                    // n_archetypes + 11 <= kAaMaxA + 11 entries (checked above)
     int np = 0, head = 0;
     picks[np++] = first;
     int64_t cur = first;
@@ -1412,7 +1419,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     int64_t* candi = (int64_t*)(ws + p.off_candi);
     double* rsspart = (double*)(ws + p.off_rsspart);
 
-    timer_begin(CHR_FAMILY_AA, true, st);
+    timer_begin(CHR_FAMILY_AA, timing_env(), st);
     // ---- alphas
     const size_t sm_alpha = (size_t)(na * na + na * d + p.nacc + 128 * na) * 8;
     if (na <= 16 && !getenv("CHR_AA_ALPHA_GENERAL")) {
@@ -1511,7 +1518,7 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
         aa_rss_direct_kernel<<<p.rss_blocks, 256, (size_t)na * d * 8, st>>>(X, n, d, alphas, Z, na, rsspart);
     }
     aa_sum_kernel<<<1, 256, 0, st>>>(rsspart, p.rss_blocks, rss_out);
-    timer_end(CHR_FAMILY_AA, true, st);
+    timer_end(CHR_FAMILY_AA, timing_env(), st);
     CHR_LAUNCH_CHECK();
     return 0;
 }

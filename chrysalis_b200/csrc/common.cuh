@@ -14,11 +14,12 @@ void set_error(const char* fmt, ...);
 // two events around the dominant kernel of a family (CHR_FLAG_TIMING)
 struct KernelTimer {
     cudaEvent_t a = nullptr, b = nullptr;
-    bool armed = false;
+    bool armed = false, started = false;
 };
 KernelTimer& timer(int family);
 void timer_begin(int family, bool on, cudaStream_t s);
 void timer_end(int family, bool on, cudaStream_t s);
+bool timing_env();   // CHR_TIMING=1: entry points without a flags argument (kNN, plan, prep, AA) record their kernel times too
 
 constexpr int kNumSMs = 148;  // B200
 

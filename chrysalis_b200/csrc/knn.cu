@@ -255,9 +255,9 @@ int chr_knn_build(const double* xy, int64_t n, int k, const double* bbox, int32_
     CHR_LAUNCH_CHECK();
     knn_fill_kernel<<<nb, 256, 0, st>>>(n, cell_of, cell_start, cursor, sorted_ids);
     CHR_LAUNCH_CHECK();
-    timer_begin(CHR_FAMILY_KNN, true, st);
+    timer_begin(CHR_FAMILY_KNN, timing_env(), st);
     knn_query_kernel<<<(unsigned)ceil_div<int64_t>(n, 128), 128, 0, st>>>(xy, n, k, bbox, cell_start, sorted_ids, nbr_out);
-    timer_end(CHR_FAMILY_KNN, true, st);
+    timer_end(CHR_FAMILY_KNN, timing_env(), st);
     CHR_LAUNCH_CHECK();
     return 0;
 }

@@ -1,4 +1,5 @@
 // Library-level plumbing of the C ABI: version, thread-local error string, kernel timers.
+#include <cstdlib>
 #include <mutex>
 #include "async.cuh"
 
@@ -13,30 +14,48 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static KernelTimer g_timers[8];
+// one event pair per (device, family): events belong to the device that was current when they were created, so a
+// stream of another device gets its own pair.  Creation and recording are serialised; a failed record disarms the
+// timer and is cleared, so it can never surface as the error of the kernel launch that follows.
+constexpr int kTimerDevices = 16, kTimerFamilies = 8;
+static KernelTimer g_timers[kTimerDevices][kTimerFamilies];
+static std::mutex g_timer_mu;
 
-KernelTimer& timer(int family) { return g_timers[family & 7]; }
+static int timer_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev & (kTimerDevices - 1);
+}
+
+KernelTimer& timer(int family) { return g_timers[timer_device()][family & (kTimerFamilies - 1)]; }
 
 void timer_begin(int family, bool on, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_timer_mu);
     KernelTimer& t = timer(family);
     t.armed = false;
     if (!on) return;
-    {
-        static std::mutex mu;                       // restarts of one fit may run on several host threads
-        std::lock_guard<std::mutex> lock(mu);
-        if (!t.a) {
-            cudaEventCreate(&t.b);
-            cudaEventCreate(&t.a);
-        }
+    if (!t.a && (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess)) {
+        cudaGetLastError();
+        t.a = t.b = nullptr;
+        return;
     }
-    cudaEventRecord(t.a, s);
+    if (cudaEventRecord(t.a, s) != cudaSuccess) { cudaGetLastError(); return; }
+    t.started = true;
 }
 
 void timer_end(int family, bool on, cudaStream_t s) {
     if (!on) return;
+    std::lock_guard<std::mutex> lock(g_timer_mu);
     KernelTimer& t = timer(family);
-    cudaEventRecord(t.b, s);
+    if (!t.started) return;
+    t.started = false;
+    if (cudaEventRecord(t.b, s) != cudaSuccess) { cudaGetLastError(); return; }
     t.armed = true;
+}
+
+bool timing_env() {
+    static const bool on = [] { const char* e = getenv("CHR_TIMING"); return e && e[0] == '1'; }();
+    return on;
 }
 
 EncodeTiledFn get_encode_tiled() {

@@ -370,7 +370,7 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
     int32_t* rec = (int32_t*)((char*)plan + rec_bytes);
 
     const unsigned gs = (unsigned)ceil_div<int64_t>(n_spots, 128), gq = (unsigned)ceil_div<int64_t>(nquads, 128);
-    timer_begin(CHR_FAMILY_KNN, true, st);
+    timer_begin(CHR_FAMILY_KNN, timing_env(), st);
     CHR_CUDA(cudaMemsetAsync(indeg, 0, (size_t)n_spots * 4, st));
     plan_init_kernel<<<gs, 128, 0, st>>>(nbr, n_spots, k, own[0], cnt[0], indeg);
     int cur = 0;
@@ -384,7 +384,7 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
     plan_scan_kernel<<<1, 1024, 0, st>>>(qsize, nquads, off, 1 + kPlanOffPad);
     plan_header_kernel<<<1, 256, 0, st>>>(off, n_spots, k, nquads, hdr, off_bytes, rec_bytes);
     plan_fill_kernel<<<gq, 128, 0, st>>>(nbr, n_spots, k, nquads, own[cur], indeg, off, qrounds, rec);
-    timer_end(CHR_FAMILY_KNN, true, st);
+    timer_end(CHR_FAMILY_KNN, timing_env(), st);
     CHR_LAUNCH_CHECK();
     if (info_host) {
         PlanHeader h;

@@ -132,10 +132,10 @@ int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const f
     cudaStream_t st = (cudaStream_t)stream;
     CHR_REQUIRE(indptr && indices && data && gene_col && dense && n > 0 && ld > 0, "chr_csr_densify_log1p: bad arguments");
     if (!(apply_log1p & 2)) CHR_CUDA(cudaMemsetAsync(dense, 0, (size_t)n * ld * sizeof(float), st));   // bit 1: caller zeroed it
-    timer_begin(CHR_FAMILY_PREP, true, st);
+    timer_begin(CHR_FAMILY_PREP, timing_env(), st);
     csr_densify_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n, gene_col, scale, row_of_spot, dense, ld,
                                                     apply_log1p & 1);
-    timer_end(CHR_FAMILY_PREP, true, st);
+    timer_end(CHR_FAMILY_PREP, timing_env(), st);
     CHR_LAUNCH_CHECK();
     return 0;
 }

@@ -309,7 +309,8 @@ def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | No
         raise _lib.ChrysalisNativeError("permutation inference needs the plan-based kernel (k <= 64)")
     I, _, _ = moran_dense(X, nbr, g, plan=plan)
     gen = torch.Generator(device=X.device)
-    gen.manual_seed(int(torch.seed() if seed is None else seed))
+    # a private generator: torch's global RNG state is not touched (seed=None draws fresh entropy for it)
+    gen.manual_seed(int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0] >> 1))
     larger = torch.zeros(g, dtype=torch.int64, device=X.device)
     s1 = torch.zeros(g, dtype=torch.float64, device=X.device)
     s2 = torch.zeros(g, dtype=torch.float64, device=X.device)

@@ -56,6 +56,21 @@ def test_moran_kernel_matches_golden(name, request):
     assert_close(C, z["geary"][m], what="C")
 
 
+@pytest.mark.parametrize("name", ["svg_hex_k6", "svg_random_k8", "svg_square_k8"])
+def test_moran_kernel_matches_reference_run_vectors(name):
+    """CUDA Moran's I against numbers the reference itself produced (``get_moransI``,
+    /root/reference/chrysalis/functions.py:15-35, executed by tests/golden/make_reference_vectors.py) - no oracle
+    arithmetic between the two: inputs are built the same way, the statistic is compared directly."""
+    from conftest import load_golden
+    ref = load_golden("reference_get_moransI")
+    z = load_golden(name)
+    m = z["gene_mask"]
+    nbr = ow.knn_neighbors(ow.reference_points(z["xy"]), int(z["k"]))
+    I, _, _ = gpu_moran(dense_from(golden_csr(z), m), nbr)
+    cols = np.searchsorted(np.flatnonzero(m), ref[f"{name}_genes"])
+    assert_close(I[cols], ref[f"{name}_I_f64in"], atol=2e-7 + 5e-9)
+
+
 @pytest.mark.parametrize("variant", [0, 4])
 def test_all_kernel_variants_agree(variant, golden_random):
     """The TMA tile kernel over the quad plan (0, default) and the per-spot stream kernel (4): same statistic."""

@@ -1,5 +1,8 @@
-"""CPU tests of the oracle itself: pinned against the in-repo formula of the reference
-(chrysalis/functions.py:26-35), hand-computed lattices and the committed golden vectors."""
+"""CPU tests of the oracle itself: pinned against outputs of the reference's own ``get_moransI``
+(chrysalis/functions.py:15-35, EXECUTED - tests/golden/make_reference_vectors.py), hand-computed
+lattices and the committed golden vectors."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -44,6 +47,52 @@ def test_matches_in_repo_dense_formula(golden_hex):
         y = np.asarray(X[:, j].todense()).ravel()
         assert om.morans_I_dense_formula(wd, y) == pytest.approx(om.morans_I(y, w), abs=2e-7)
         assert om.morans_I_dense_formula(wd, y) == pytest.approx(om.morans_I_f64(y, w), abs=1e-8)
+
+
+REFERENCE_FIXTURES = ["svg_hex_k6", "svg_random_k8", "svg_square_k8"]
+
+
+def _reference_case(name):
+    """Inputs of one reference-run fixture: (w CSR, dense float32 scored-gene matrix, scored ids, reference vectors)."""
+    from conftest import load_golden
+    ref = load_golden("reference_get_moransI")
+    z = load_golden(name)
+    mask = z["gene_mask"]
+    dense = np.asarray(osvg.normalize_total_log1p(golden_csr(z)[:, mask]).todense(), dtype=np.float32)
+    w = ow.row_standardised_csr(ow.knn_neighbors(ow.reference_points(z["xy"]), int(z["k"])))
+    cols = np.searchsorted(np.flatnonzero(mask), ref[f"{name}_genes"])
+    return w, dense, cols, ref[f"{name}_I_f32in"], ref[f"{name}_I_f64in"]
+
+
+@pytest.mark.parametrize("name", REFERENCE_FIXTURES)
+def test_oracle_pinned_to_reference_run_get_moransI(name):
+    """``oracle.moran.morans_I`` against numbers the REFERENCE produced: ``get_moransI`` of
+    /root/reference/chrysalis/functions.py:15-35 was cut out with ``ast`` and executed on these inputs
+    (tests/golden/make_reference_vectors.py).  The reference rounds to 8 decimals (functions.py:35)."""
+    w, dense, cols, ref32, ref64 = _reference_case(name)
+    got64 = np.array([om.morans_I_f64(dense[:, j], w) for j in cols])
+    assert np.abs(got64 - ref64).max() <= 5.1e-9                      # float64 in, float64 out: the rounding only
+    got32 = np.array([om.morans_I(dense[:, j], w) for j in cols])      # the dtype path of core.py:59,72
+    assert np.abs(got32 - ref64).max() <= 2e-7                        # float32 centring (core.py:59 hands esda float32): ~1e-7
+    # fed float32, get_moransI itself forms D_i D_j in float32 and adds D^2 with Python's sequential float32 sum():
+    # its own float32 noise reaches ~7e-6 (n = 1600), well above esda's (float64 lag); the oracle sits inside that band
+    assert np.abs(got32 - ref32).max() <= 2e-5
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/chrysalis/functions.py"), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("name", REFERENCE_FIXTURES)
+def test_committed_reference_vectors_reproduce_live(name):
+    """Where the reference tree is mounted, run its ``get_moransI`` again: the committed vectors are its output."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(os.path.dirname(__file__), "golden", "make_reference_vectors.py"))
+    mrv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mrv)
+    fn, lines = mrv.load_reference_get_moransI()
+    w, dense, cols, ref32, ref64 = _reference_case(name)
+    wd = np.asarray(w.todense())
+    for t in range(0, len(cols), 9):
+        assert fn(wd, dense[:, cols[t]].astype(np.float64)) == ref64[t]
+        assert float(fn(wd, dense[:, cols[t]])) == pytest.approx(ref32[t], abs=1e-12)
 
 
 def test_knn_is_libpysal_shaped():
