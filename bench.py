@@ -152,8 +152,8 @@ def build_device_workload(args, rank, torch, dv, synth):
     return xy_s, nbr, csr
 
 
-def dense_from_csr(csr, min_spots, torch, dv):
-    """The product's own front-end (K2) on the device-resident counts."""
+def dense_from_csr(csr, min_spots, torch, dv, lat=None):
+    """The product's own front-end (K2) on the device-resident counts; with a lattice plan the rows go to lattice layout."""
     n, g = csr.shape
     gene_nnz = dv.csr_gene_nnz(csr)
     keep = gene_nnz >= int(n * min_spots)
@@ -161,7 +161,10 @@ def dense_from_csr(csr, min_spots, torch, dv):
                            torch.full_like(gene_nnz, -1))
     n_keep = int(keep.sum().item())
     scale = dv.median_scale(dv.csr_spot_totals(csr, gene_col))
-    return dv.csr_densify(csr, gene_col, n_keep, scale, None, apply_log1p=True), n_keep
+    if lat is None:
+        return dv.csr_densify(csr, gene_col, n_keep, scale, None, apply_log1p=True), n_keep
+    out = torch.zeros((lat.n_rows, dv.dense_ld(n_keep)), dtype=torch.float32, device="cuda")
+    return dv.csr_densify(csr, gene_col, n_keep, scale, lat.row_of_spot, apply_log1p=True, out=out), n_keep
 
 
 def pipeline_stages(args, csr, I, g_scored, svg_e2e_ms, torch, dv, _lib, core):
@@ -279,16 +282,23 @@ def run_native(args):
     n, g, k = args.n, args.g, args.k
     t0 = time.time()
     xy_s, nbr, csr = build_device_workload(args, rank, torch, dv, synth)
-    X, g_scored = dense_from_csr(csr, MIN_SPOTS, torch, dv)
+    # square lattice, k = 8: lattice layout + stencil kernel (what detect_svgs picks for this input); otherwise the quad plan
+    lat = dv.lattice_plan(xy_s, nbr) if (args.variant == 0 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0") else None
+    X, g_scored = dense_from_csr(csr, MIN_SPOTS, torch, dv, lat)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     density = csr.data.numel() / (n * g)
 
     gathered = [torch.empty(g_scored, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
-    plan = dv.moran_plan(nbr)      # W's device plan: part of building W (K1), reused by every pass over genes
+    plan = dv.moran_plan(nbr) if lat is None else None     # W's device plan: part of building W (K1), reused by every pass over genes
+
+    def moran(timing=False, variant=args.variant):
+        if lat is not None and variant == 0:
+            return dv.moran_lattice(X, lat, g_scored, timing=timing)
+        return dv.moran_dense(X, nbr, g_scored, timing=timing, variant=variant, plan=plan)
 
     def step(timing=False):
-        I, _, _ = dv.moran_dense(X, nbr, g_scored, timing=timing, variant=args.variant, plan=plan)
+        I, _, _ = moran(timing)
         if world > 1:
             # every rank scores the same number of genes only if the filter keeps the same count;
             # pad to a common length for the all-gather of per-gene statistics
@@ -331,7 +341,7 @@ def run_native(args):
     # inputs > L2), so reading the events does not perturb the timed region above
     kms = []
     for _ in range(min(args.steps, 10)):
-        dv.moran_dense(X, nbr, g_scored, timing=True, variant=args.variant, plan=plan)
+        moran(True)
         kms.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
     kernel_ms = float(np.mean(kms))
 
@@ -339,7 +349,7 @@ def run_native(args):
     for v in [int(x) for x in args.sweep.split(",") if x != ""]:
         ts = []
         for _ in range(6):
-            Iv, _, _ = dv.moran_dense(X, nbr, g_scored, timing=True, variant=v, plan=plan)
+            Iv, _, _ = moran(True, v)
             ts.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
         sweep[str(v)] = {"kernel_ms": round(float(np.mean(ts[1:])), 4), "bit_identical_to_default": bool(torch.equal(Iv, I))}
 
@@ -359,11 +369,13 @@ def run_native(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
-    if args.variant == 4:
+    if lat is not None:
+        kernels = ["moran_lattice_pilot_kernel", "moran_lattice_fill_kernel", "moran_lattice_kernel", "moran_lattice_corr_kernel", "moran_finalize_kernel"]
+    elif args.variant == 4:
         kernels = ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"]
     else:
         kernels = ["moran_pilot_kernel", "moran_tile_kernel", "moran_finalize_kernel"]
-    main_kernel = kernels[1]
+    main_kernel = kernels[2] if lat is not None else kernels[1]
     roofline = {"bound": "hbm", "kernel": main_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
@@ -421,7 +433,7 @@ def run_native(args):
                       "steps": e_steps, "path": "core.svg_stage(PinnedCSR counts, coords): H2D + filter/normalise/log1p/densify + "
                                                 "Hilbert sort + kNN + Moran + D2H",
                       "bit_identical_to_resident_run": same}
-        X, _ = dense_from_csr(csr, MIN_SPOTS, torch, dv)
+        X, _ = dense_from_csr(csr, MIN_SPOTS, torch, dv, lat)
 
     # ---- the rest of the path on the same resident data: PCA (tcgen05 Gram) + AA, stage seconds -----------
     if rank == 0 and world == 1 and not args.no_pipeline:
@@ -436,7 +448,8 @@ def run_native(args):
         cols = cols[np.random.default_rng(0).permutation(len(cols))]          # any prefix is spread over the gene range
         sample = np.empty((n, len(cols)), dtype=np.float32)
         for b in range(0, len(cols), 128):
-            sample[:, b:b + 128] = X[:, torch.from_numpy(cols[b:b + 128]).cuda()].cpu().numpy()
+            cb = torch.from_numpy(cols[b:b + 128]).cuda()
+            sample[:, b:b + 128] = (X[:, cb] if lat is None else X[lat.row_of_spot[:, None], cb[None, :]]).cpu().numpy()
         nbr_h = nbr.cpu().numpy()
         w = ow.row_standardised_csr(nbr_h)
         I_dev = I.cpu().numpy()

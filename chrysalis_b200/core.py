@@ -104,8 +104,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     rank, size = dd.world() if shard else (0, 1)
     lo, hi = dd.shard_range(g_all, rank, size)
     # While the counts are in flight: W (core.py:61-65, needs the coordinates only) and the zero fill of the dense
-    # matrix run on a side stream.  The dense buffer comes from the main stream's pool; the side stream waits for
-    # everything enqueued so far (whatever used that memory before), not for the upload enqueued next.
+    # matrix run on a side stream; the side stream waits for everything enqueued so far, not for the upload enqueued next.
     main = torch.cuda.current_stream() if torch.cuda.is_available() else None
     side = _side_stream()
     dense_buf = None
@@ -115,9 +114,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     pts[:, 1] = pts[:, 1] * -1
     xy = dv.to_device(pts, torch.float64)
     if side is not None:
-        dense_buf = torch.empty((n, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
         side.wait_stream(main)
-    _mark(t0, "coords uploaded, dense buffer allocated")
+    _mark(t0, "coords uploaded")
     Xs = X if size == 1 else X[:, lo:hi]
     # counts already in pinned (or device) memory upload asynchronously: enqueue that first, then the side-stream work.
     # Anything else (scipy CSR in pageable memory) is a blocking copy: the side-stream work is launched before it.
@@ -127,23 +125,35 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         csr = dv.upload_csr(Xs)
         _mark(t0, "counts upload enqueued")
     with _stream_ctx(side):
-        # core.py:64-65  kNN weights, row-standardised
+        # core.py:64-65  kNN weights, row-standardised.  kNN on the spots as given: distance ties go to the lower ORIGINAL
+        # spot id (knn.cu), so W does not depend on the internal row order and is the W local_morans_i builds
         bbox = dv.spatial_bbox(xy)
-        order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
-        rank_of = torch.empty_like(order)
-        rank_of[order] = torch.arange(n, device=order.device)
-        # kNN on the spots as given: distance ties go to the lower ORIGINAL spot id (knn.cu), so W does not depend on the
-        # internal row order and is the W local_morans_i builds; then relabelled into the row order of the dense matrix
-        nbr = rank_of.to(torch.int32)[dv.knn_build(xy, neighbors, bbox)[order].long()].contiguous()
-        plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
-        if dense_buf is not None:
+        nbr0 = dv.knn_build(xy, neighbors, bbox)
+        # square lattice with k = 8 (Visium HD / Stereo-seq bins): lattice layout + stencil kernel; otherwise rows in
+        # Hilbert order + the quad plan of W.  (Permutation inference relabels rows, which only the general kernel does.)
+        lat = None
+        if neighbors == 8 and not permutations and os.environ.get("CHR_MORAN_LATTICE", "1") != "0":
+            lat = dv.lattice_plan(xy, nbr0, bbox)
+        if lat is not None:
+            rank_of, nbr, plan, n_rows = lat.row_of_spot, None, None, lat.n_rows
+        else:
+            order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
+            rank_of = torch.empty_like(order)
+            rank_of[order] = torch.arange(n, device=order.device)
+            nbr = rank_of.to(torch.int32)[nbr0[order].long()].contiguous()      # relabelled into the row order
+            plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
+            n_rows = n
+        if torch.cuda.is_available():
+            dense_buf = torch.empty((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
             dense_buf.zero_()
     if csr is None:
         csr = dv.upload_csr(Xs)
         _mark(t0, "counts uploaded (blocking copy)")
     if side is not None:
         main.wait_stream(side)
-        for t in (rank_of, nbr) + ((plan.buf,) if plan is not None else ()):
+        keep_alive = [rank_of, dense_buf] + ([nbr, plan.buf] if plan is not None else []) + \
+            ([lat.bands, lat.chunks, lat.corr, lat.absent, lat.pilot_rows] if lat is not None else [])
+        for t in keep_alive:
             t.record_stream(main)
     _mark(t0, "W build + zero fill enqueued (side stream)")
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
@@ -166,7 +176,10 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
         dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p, out=dense_buf)
         # core.py:71-76  the gene loop
-        I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
+        if lat is not None:
+            I, C, _ = dv.moran_lattice(dense, lat, n_keep, geary=geary, timing=timing)
+        else:
+            I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
         sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None
     else:
         I = torch.empty(0, dtype=torch.float64, device=keep.device)

@@ -688,6 +688,15 @@ moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad,
     }
 }
 
+// shared with moran_lattice.cu: `part` is [nsplit][kNStat][gpad] in the tile kernel's convention (x'Ax', (indeg - k) parts)
+int launch_moran_finalize(const double* part, int nsplit, int64_t gpad, int64_t n_genes, int64_t n_spots, int k, const float* pilot,
+                          bool geary, double* out_I, double* out_C, double* out_stats, cudaStream_t st) {
+    moran_finalize_kernel<<<(unsigned)ceil_div<int64_t>(n_genes, 64), 64 * kFinSplit, 0, st>>>(part, nsplit, gpad, n_genes, n_spots, k, pilot,
+                                                                                             geary, true, out_I, out_C, out_stats);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
 // spots per CTA of the tile kernel: depends on n only, so the summation tree of a gene is identical
 // however genes are sharded.  Long CTAs amortise the pipeline fill; small n keeps enough CTAs.
 static int tile_tiles_per_cta(int64_t n) {

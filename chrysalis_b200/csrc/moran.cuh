@@ -39,6 +39,10 @@ inline size_t plan_rec_capacity_bytes(int64_t n, int k) {
     return (size_t)nquads * kPlanHdrUnits * 16 + (size_t)n * (size_t)(k + 1) * 2 * kPlanRoundUnits * 16;
 }
 
+// fixed-order fp64 sum of the per-CTA partials + the statistics (moran.cu); used by the lattice kernel as well
+int launch_moran_finalize(const double* part, int nsplit, int64_t gpad, int64_t n_genes, int64_t n_spots, int k, const float* pilot,
+                          bool geary, double* out_I, double* out_C, double* out_stats, cudaStream_t st);
+
 // ---- packed f32x2 arithmetic --------------------------------------------------------------------
 typedef unsigned long long f2_t;  // two packed fp32 values in a 64-bit register pair
 

@@ -117,15 +117,16 @@ def dense_ld(n_cols: int) -> int:
 
 def csr_densify(csr: DeviceCSR, gene_col: torch.Tensor, n_cols: int, scale: torch.Tensor | None,
                 row_of_spot: torch.Tensor | None, apply_log1p: bool, out: torch.Tensor | None = None) -> torch.Tensor:
-    """``out``: optional pre-ZEROED [n, ld >= n_cols] float32 buffer (e.g. filled on a side stream while the
-    counts were still in flight from the host); the kernel then only scatters."""
+    """``out``: optional pre-ZEROED [>= n, ld >= n_cols] float32 buffer (e.g. filled on a side stream while the
+    counts were still in flight from the host; more than n rows in lattice layout, where ``row_of_spot`` leaves
+    filler rows); the kernel then only scatters."""
     n, _ = csr.shape
     if out is None:
         ld = dense_ld(n_cols)
         dense = torch.empty((n, ld), dtype=torch.float32, device=csr.data.device)
     else:
         dense, ld = out, out.stride(0)
-        assert out.dtype == torch.float32 and out.shape[0] == n and ld >= n_cols and out.stride(1) == 1
+        assert out.dtype == torch.float32 and out.shape[0] >= n and ld >= n_cols and out.stride(1) == 1
     _lib.call("chr_csr_densify_log1p", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), n, _ptr(gene_col),
               _ptr(scale), _ptr(row_of_spot), _ptr(dense), ld, int(apply_log1p) | (2 if out is not None else 0), _stream())
     return dense
@@ -288,6 +289,151 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
     _lib.call("chr_moran_dense_f32", _ptr(X), n, g, ld, _ptr(nbr), k, _ptr(plan.buf) if plan is not None else 0,
               plan.chunk_units if plan is not None else 0, _ptr(row_map), flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
+              _ptr(ws), ws_bytes, _stream())
+    return out_I, out_C, stats
+
+
+# ---- K3/K4 on a square lattice: layout + corrections for the stencil kernel ----------------------------------------
+
+LATTICE_BAND_ROWS = 60      # CHR_LATTICE_BAND_ROWS (include/chrysalis_b200.h)
+LATTICE_CHUNK_COLS = 256    # longest run of lattice columns one CTA walks
+
+
+@dataclass
+class LatticePlan:
+    """Square-lattice representation of W for ``chr_moran_lattice_f32`` (see csrc/moran_lattice.cu).
+
+    ``row_of_spot`` [n] int64 maps a spot to its row of the dense matrix in lattice layout (``n_rows`` rows: the stored
+    range of every band, absent nodes included as filler rows)."""
+    row_of_spot: torch.Tensor
+    n_rows: int
+    n: int
+    k: int
+    bands: torch.Tensor        # int32 [n_bands, 4]
+    chunks: torch.Tensor       # int32 [n_chunks, 4]
+    corr: torch.Tensor         # int32 [n_corr, 4]
+    absent: torch.Tensor       # int32 [n_absent]
+    pilot_rows: torch.Tensor   # int32 [<= 512]
+    lattice_shape: tuple       # (W, H) nodes
+
+
+def lattice_nodes(xy: torch.Tensor, bbox: torch.Tensor, pitch: float):
+    """Integer lattice node (ix, iy) of every spot, counted from the bounding-box corner."""
+    rel = (xy - bbox[:2]) / pitch
+    node = rel.round().to(torch.int64)
+    return node[:, 0].contiguous(), node[:, 1].contiguous()
+
+
+def lattice_layout(ix: torch.Tensor, iy: torch.Tensor, band_rows: int = LATTICE_BAND_ROWS, chunk_cols: int = LATTICE_CHUNK_COLS):
+    """Bands / chunks / row map of the lattice layout for spots on nodes (ix, iy) (unique).  Device-agnostic tensor
+    arithmetic; the per-band tables are tiny and assembled on the host (one round trip)."""
+    n = ix.numel()
+    W, H = int(ix.max().item()) + 1, int(iy.max().item()) + 1
+    n_bands = (H + band_rows - 1) // band_rows
+    band = iy // band_rows
+    big = torch.iinfo(torch.int64).max
+    xmin = torch.full((n_bands,), big, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amin")
+    xmax = torch.full((n_bands,), -1, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amax")
+    xmin_h, xmax_h = xmin.cpu().numpy(), xmax.cpu().numpy()
+    bands_h = np.zeros((n_bands, 4), dtype=np.int64)
+    chunks = []
+    row = 0
+    for b in range(n_bands):
+        bh = min(band_rows, H - b * band_rows)
+        ncols = int(xmax_h[b] - xmin_h[b] + 1) if xmax_h[b] >= 0 else 0
+        bands_h[b] = (row, xmin_h[b] if ncols else 0, ncols, bh)
+        row += ncols * bh
+        pieces = (ncols + chunk_cols - 1) // chunk_cols
+        size = (ncols + pieces - 1) // pieces if pieces else 0
+        for c0 in range(0, ncols, size if size else 1):
+            chunks.append((b, c0, min(size, ncols - c0), 0))
+    bands_d = torch.from_numpy(bands_h).to(ix.device)
+    row_of_spot = bands_d[band, 0] + (ix - bands_d[band, 1]) * bands_d[band, 3] + (iy - band * band_rows)
+    return row_of_spot, int(row), bands_d.to(torch.int32).contiguous(), \
+        torch.tensor(chunks, dtype=torch.int32, device=ix.device).reshape(-1, 4).contiguous(), (W, H)
+
+
+def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, shape: tuple):
+    """D = A - B as a coalesced COO list (i, j, coefficient) plus the (indeg - k) weights of W's column sums.
+
+    A: kNN adjacency counts of ``nbr`` [n, k] (spot ids); B: 1 for every ordered pair of present nodes that are
+    8-neighbours on the lattice.  Any list is legal (duplicates, self loops): coefficients are exact integers."""
+    n, k = nbr.shape
+    W, H = shape
+    dev = ix.device
+    grid = torch.full(((H + 2) * (W + 2),), -1, dtype=torch.int64, device=dev)
+    grid[(iy + 1) * (W + 2) + ix + 1] = torch.arange(n, device=dev)
+    me = torch.arange(n, device=dev)
+    keys, vals = [me[:, None].expand(n, k).reshape(-1) * n + nbr.reshape(-1).long()], [torch.ones(n * k, dtype=torch.int64, device=dev)]
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dx == 0 and dy == 0:
+                continue
+            j = grid[(iy + 1 + dy) * (W + 2) + ix + 1 + dx]
+            ok = j >= 0
+            keys.append(me[ok] * n + j[ok])
+            vals.append(torch.full((int(ok.sum().item()),), -1, dtype=torch.int64, device=dev))
+    key, inv = torch.unique(torch.cat(keys), return_inverse=True)
+    coef = torch.zeros(key.numel(), dtype=torch.int64, device=dev).scatter_add_(0, inv, torch.cat(vals))
+    nz = coef != 0
+    key, coef = key[nz], coef[nz]
+    indeg = torch.bincount(nbr.reshape(-1).long(), minlength=n)
+    wj = torch.nonzero(indeg != k).squeeze(1)
+    return key // n, key % n, coef, wj, (indeg[wj] - k)
+
+
+def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None = None, pitch: float | None = None,
+                 max_fill: float = 1.6, max_corr_frac: float = 0.2) -> LatticePlan | None:
+    """Lattice layout + corrections for the kNN lists ``nbr`` [n, 8] of spots on a square lattice, or None when the
+    stencil kernel does not apply (k != 8, no lattice, two spots on one node, a tissue so ragged that the stored
+    range or the correction list would dominate): the caller then takes the general quad-plan kernel."""
+    n, k = nbr.shape
+    if k != 8 or n < 64:
+        return None
+    bbox = spatial_bbox(xy) if bbox is None else bbox
+    pitch = square_lattice_pitch(xy, bbox) if pitch is None else pitch
+    if pitch is None:
+        return None
+    ix, iy = lattice_nodes(xy, bbox, pitch)
+    W, H = int(ix.max().item()) + 1, int(iy.max().item()) + 1
+    if torch.unique(iy * W + ix).numel() != n:
+        return None
+    row_of_spot, n_rows, bands, chunks, shape = lattice_layout(ix, iy)
+    if n_rows > max_fill * n or n_rows >= 2 ** 31 or chunks.shape[0] >= 65536:
+        return None
+    ci, cj, cc, wj, ww = lattice_corrections(ix, iy, nbr, shape)
+    if ci.numel() + wj.numel() > max_corr_frac * n * k:
+        return None
+    f32bits = lambda t: t.to(torch.float32).view(torch.int32)
+    quad = torch.stack([row_of_spot[ci].to(torch.int32), row_of_spot[cj].to(torch.int32), f32bits(cc), torch.zeros_like(ci, dtype=torch.int32)], 1)
+    lin = torch.stack([row_of_spot[wj].to(torch.int32), torch.zeros_like(wj, dtype=torch.int32), f32bits(ww), torch.ones_like(wj, dtype=torch.int32)], 1)
+    corr = torch.cat([quad, lin], 0)
+    corr = corr[torch.argsort(corr[:, 0].long() * 2 + corr[:, 3].long(), stable=True)].contiguous()    # by row: neighbouring entries share rows
+    present = torch.zeros(n_rows, dtype=torch.bool, device=xy.device)
+    present[row_of_spot] = True
+    absent = torch.nonzero(~present).squeeze(1).to(torch.int32).contiguous()
+    ns = min(n, 512)
+    pilot_rows = row_of_spot[(torch.arange(ns, device=xy.device) * n) // ns].to(torch.int32).contiguous()
+    return LatticePlan(row_of_spot, n_rows, n, k, bands, chunks, corr, absent, pilot_rows, shape)
+
+
+def moran_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None, geary: bool = False, timing: bool = False,
+                  want_stats: bool = False, preshifted: bool = False):
+    """Moran's I (and Geary's C) of every column of ``X`` [plan.n_rows, ld] float32 in lattice layout.
+    Returns ``(I, C, stats)`` like ``moran_dense``.  The filler rows of ``X`` (absent nodes) are overwritten."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1 and X.shape[0] == plan.n_rows
+    ld = X.stride(0)
+    g = X.shape[1] if n_genes is None else n_genes
+    flags = ((_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PRESHIFTED if preshifted else 0))
+    n_chunks, n_corr = plan.chunks.shape[0], plan.corr.shape[0]
+    ws_bytes = _lib.query("chr_moran_lattice_workspace_bytes", g, n_chunks, n_corr)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    out_I = torch.empty(g, dtype=torch.float64, device=X.device)
+    out_C = torch.empty(g, dtype=torch.float64, device=X.device) if geary else None
+    stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
+    _lib.call("chr_moran_lattice_f32", _ptr(X), plan.n_rows, g, ld, plan.n, plan.k, _ptr(plan.bands), plan.bands.shape[0],
+              _ptr(plan.chunks), n_chunks, _ptr(plan.corr) if n_corr else 0, n_corr, _ptr(plan.absent) if plan.absent.numel() else 0,
+              plan.absent.numel(), _ptr(plan.pilot_rows), plan.pilot_rows.numel(), flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
               _ptr(ws), ws_bytes, _stream())
     return out_I, out_C, stats
 

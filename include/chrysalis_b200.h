@@ -118,6 +118,28 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
                         double* out_stats, void* workspace, size_t workspace_bytes,
                         chr_stream_t stream);
 
+/* ---- K3/K4 on an exact square lattice (stencil kernel) -----------------------------------
+ * Same statistic, same reference call sites as chr_moran_dense_f32, for spots that sit on a square lattice with the
+ * 8-neighbour kNN graph (core.py:64-65 with neighbors=8: Visium HD / Stereo-seq bins).  The kNN adjacency is split as
+ * A = B + D: B = the symmetric 8-neighbour stencil between present lattice nodes (evaluated in registers while the
+ * matrix streams through shared memory once), D = a short list of corrections at tissue edges and holes.
+ * X: [n_rows][ld] float32 in LATTICE LAYOUT (device.lattice_plan): bands of <= CHR_LATTICE_BAND_ROWS lattice rows; inside
+ *    a band column after column, each column the band's rows as consecutive matrix rows; n_rows >= n_spots (absent nodes
+ *    of a stored column are filler rows, listed in absent_rows - the call overwrites them with the per-gene shift value).
+ * bands:  int32 [n_bands][4]  = {first matrix row, lattice x of the first stored column, stored columns, lattice rows}
+ * chunks: int32 [n_chunks][4] = {band, first column relative to the band's first stored column, columns, 0} (one CTA each)
+ * corr:   int32 [n_corr][4]   = {row_i, row_j, coefficient as float bits, kind}; kind 0: x'Ax' += c x_i x_j,
+ *                                kind 1: sum_j (indeg_j - k) x_j += c x_i  (column sums of A differ from k at the edges)
+ * pilot_rows: int32 [n_pilot <= 512] matrix rows of present spots whose mean is the per-gene shift.
+ * n_spots = number of present spots (the n of the statistic).  Outputs as chr_moran_dense_f32. */
+#define CHR_LATTICE_BAND_ROWS 60
+size_t chr_moran_lattice_workspace_bytes(int64_t n_genes, int n_chunks, int64_t n_corr);
+int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int64_t n_spots, int k,
+                          const int32_t* bands, int n_bands, const int32_t* chunks, int n_chunks,
+                          const int32_t* corr, int64_t n_corr, const int32_t* absent_rows, int64_t n_absent,
+                          const int32_t* pilot_rows, int n_pilot, unsigned flags, double* out_I, double* out_C,
+                          double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream);
+
 /* ---- Local Moran's I (LISA) ---------------------------------------------------------------
  * replaces  esda.moran.Moran_Local(y, w, transformation='r', permutations=P)
  *           (/root/reference/article/A2_human_lymph_node/morans_i.ipynb:150; not called by core.py)

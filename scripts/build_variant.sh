@@ -8,6 +8,6 @@ mkdir -p ../../ab_libs build
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr -Xptxas -v $EXTRA -c $SRC.cu -o build/var_${SRC}_$NAME.o 2> build/${SRC}_$NAME.log
-if [ "$SRC" = moran ]; then grep -A1 "moran_tile_kernelILb0ELb1ELb0E" build/moran_$NAME.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo; fi
+grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" build/${SRC}_$NAME.log | sort | uniq -c | tr "\n" " "; echo
 OBJS=$(ls build/*.o | grep -v "build/$SRC.o\|build/var_")
 $NVCC $ARCH -shared -o ../../ab_libs/$NAME.so $OBJS build/var_${SRC}_$NAME.o -lcudart_static -ldl -lrt -lpthread

@@ -168,3 +168,50 @@ def test_square_lattice_detection(kind, n, expect):
     dup = torch.zeros((100, 2), dtype=torch.float64)
     assert dv.lattice_pitch_from_nn(dup, torch.zeros(4, dtype=torch.float64), torch.zeros(100, dtype=torch.float64)) is None
 
+
+
+@pytest.mark.parametrize("shape", ["full", "blob", "exact"])
+def test_lattice_plan_splits_the_knn_adjacency_exactly(shape):
+    """device.lattice_plan (plain tensor arithmetic, runs on the CPU): the kNN adjacency A equals the 8-neighbour
+    stencil B between present nodes plus the correction list D, and the (indeg - k) weights give A's column sums -
+    the identity the stencil kernel (csrc/moran_lattice.cu) rests on.  W is the oracle's cKDTree kNN."""
+    import torch
+    from chrysalis_b200 import device as dv
+    from chrysalis_b200 import synth
+    from oracle import weights as ow
+
+    xy = synth.make_coords("square", 70 * 70 if shape == "blob" else 2000, seed=3, jitter=0.0 if shape == "exact" else 1e-3)
+    if shape == "blob":
+        c = xy.mean(0)
+        keep = (np.hypot(*(xy - c).T) < 3000) & ~((np.abs(xy[:, 0] - c[0]) < 400) & (np.abs(xy[:, 1] - c[1]) < 300))
+        xy = xy[keep]
+    n = len(xy)
+    pts = ow.reference_points(xy)
+    nbr = ow.knn_neighbors(pts, 8)
+    xt = torch.from_numpy(pts)
+    bbox = torch.tensor([pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max()])
+    pitch = dv.lattice_pitch_from_nn(xt, bbox, torch.from_numpy(np.linalg.norm(pts[nbr[:, 0]] - pts, axis=1)))
+    plan = dv.lattice_plan(xt, torch.from_numpy(nbr.astype(np.int32)), bbox, pitch)
+    assert plan is not None and plan.n_rows >= n and plan.absent.numel() == plan.n_rows - n
+    rows = plan.row_of_spot.numpy()
+    assert len(np.unique(rows)) == n and rows.max() < plan.n_rows
+    # every chunk lies inside its band's stored range, and the chunks tile the bands
+    bands, chunks = plan.bands.numpy(), plan.chunks.numpy()
+    assert (bands[:, 3] <= dv.LATTICE_BAND_ROWS).all() and int((bands[:, 2] * bands[:, 3]).sum()) == plan.n_rows
+    assert all(chunks[chunks[:, 0] == b, 2].sum() == bands[b, 2] for b in range(len(bands)))
+    # x'Ax' = stencil over the layout + corrections;  1'A x = k sum x + weights
+    x = np.random.default_rng(0).normal(size=n)
+    A = np.zeros((n, n))
+    np.add.at(A, (np.repeat(np.arange(n), 8), nbr.ravel()), 1.0)
+    ix, iy = (t.numpy() for t in dv.lattice_nodes(xt, bbox, pitch))
+    Wd, Hd = plan.lattice_shape
+    g = np.zeros((Hd + 2, Wd + 2))
+    g[iy + 1, ix + 1] = x
+    Q = sum((g[1:-1, 1:-1] * g[1 + dy:Hd + 1 + dy, 1 + dx:Wd + 1 + dx]).sum() for dy in (-1, 0, 1) for dx in (-1, 0, 1) if dx or dy)
+    xr = np.zeros(plan.n_rows)
+    xr[rows] = x
+    corr = plan.corr.numpy()
+    coef = corr[:, 2].copy().view(np.float32).astype(np.float64)
+    quad = corr[:, 3] == 0
+    assert Q + (coef[quad] * xr[corr[quad, 0]] * xr[corr[quad, 1]]).sum() == pytest.approx(x @ A @ x, rel=1e-12, abs=1e-9)
+    assert 8 * x.sum() + (coef[~quad] * xr[corr[~quad, 0]]).sum() == pytest.approx(A.sum(0) @ x, rel=1e-12, abs=1e-9)
