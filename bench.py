@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""Headline benchmark: Moran's I genes/sec at Visium-HD scale (BASELINE.json cfg 4).
+"""Headline benchmark: Moran's I genes/sec at Visium-HD scale (BASELINE.json cfg 4) + end-to-end SVG+PCA+AA seconds.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
 
-A "step" is one pass of the hot path over one batch: Moran's I for every gene of the
-700,000-bin x 18,000-gene dense float32 log1p matrix already resident in HBM (50.4 GB, far
-larger than L2, so no flush is needed between steps).  Under torchrun every rank holds its own
-18,000-gene shard of a N*18,000-gene matrix (genes shard with no data-path collective; only the
-per-gene statistics are all-gathered), i.e. weak scaling.  One JSON line is printed by rank 0.
+A "step" is one pass of the hot path over one batch: Moran's I for every gene of the 700,000-bin x 18,000-gene
+dense float32 log1p matrix already resident in HBM (50.4 GB, far larger than L2, so no flush is needed between steps).
 
-`e2e` is the same metric through the public host-buffer path: pinned host CSR counts ->
-H2D -> filter/normalise/log1p/densify -> kNN W -> Moran -> D2H of the per-gene statistics.
+N = 1: the whole matrix on one GPU.  N > 1 (torchrun): STRONG scaling by default - the SAME 18,000 genes are sharded
+across the ranks (2,250 per GPU at N = 8, BASELINE cfg4 "genes sharded across 8 B200"); every rank holds all spots of its
+gene range, W is replicated, the only exchange is the all-gather of the per-gene statistics, which is inside the timed
+region.  ``--scaling weak`` gives every rank its own 18,000 genes instead (reported under "weak" at N > 1 by default).
+
+`e2e` is the same metric through the public API with HOST buffers: ``ch.detect_svgs(adata)`` on an AnnData-like object
+whose ``X`` is a scipy CSR count matrix in page-locked host arrays (at N > 1: this rank's gene shard, flagged with
+``.uns['chr_gene_shard']``): H2D + filter/normalise/log1p/densify + kNN + lattice plan + Moran + D2H + the pandas tail.
+`e2e_pageable` is the same call on ordinary (pageable) numpy arrays.  `pipeline` times ch.detect_svgs -> ch.pca -> ch.aa
+through the API on host data (cfg4: 2,000 SVGs, 30 PCs, 12 archetypes) and checks PCA / AA against sklearn / the oracle.
 """
 from __future__ import annotations
 
@@ -30,6 +35,11 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(name="cfg4_visium_hd", n=700_000, g=18_000, k=8)
 METRIC = "morans_I_genes_per_sec"
 UNIT = "genes/s"
+MIN_SPOTS = 1e-4          # keeps (nearly) every synthetic gene: the metric counts genes scored
+
+
+def workload_string(n, g, k):
+    return f"{WORKLOAD['name']}: {n} bins x {g} genes, square lattice, kNN k={k}, float32 log1p(normalize_total(counts))"
 
 
 def parse_args():
@@ -39,14 +49,18 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=WORKLOAD["n"], help="spots (debug: smaller workloads)")
-    ap.add_argument("--g", type=int, default=WORKLOAD["g"], help="genes per GPU")
+    ap.add_argument("--g", type=int, default=WORKLOAD["g"], help="genes of the workload (strong scaling: sharded over the ranks)")
     ap.add_argument("--k", type=int, default=WORKLOAD["k"])
+    ap.add_argument("--coords", default="square", choices=["square", "hex", "random"], help="spot layout (cfg4: square lattice)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: shard the same genes (strong) or g genes per rank (weak)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the additional weak-scaling measurement")
     ap.add_argument("--variant", type=int, default=int(os.environ.get("CHR_MORAN_VARIANT", "0")), help="kernel variant (tuning)")
     ap.add_argument("--sweep", default="", help="comma list of kernel variants to time (kernel ms only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-pipeline", action="store_true", help="skip the PCA + AA stage timings")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the detect_svgs -> pca -> aa pipeline through the API")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory variants")
     ap.add_argument("--svgs", type=int, default=2000, help="SVGs fed to PCA (cfg4: 2,000)")
     ap.add_argument("--pcs", type=int, default=30)
     ap.add_argument("--archetypes", type=int, default=12)
@@ -58,8 +72,8 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return d, float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {}, 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -71,8 +85,7 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # honour CUDA_VISIBLE_DEVICES ordering when it is a plain index list
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")          # honour CUDA_VISIBLE_DEVICES when it is a plain index list
             phys = index
             if vis:
                 try:
@@ -118,28 +131,20 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------------------------
-def lattice_coords(n, seed):
+def make_coords(args, seed=42):
     from chrysalis_b200 import synth
-    return synth.make_coords("square", n, seed=seed)          # Visium HD bins: square lattice, k=8 (A5:41)
+    return synth.make_coords(args.coords, args.n, seed=seed)       # cfg4: Visium HD bins on a square lattice, k = 8 (A5:41)
 
 
-def build_device_workload(args, rank, torch, dv, synth):
-    """Coordinates -> Hilbert order -> W, device CSR counts and the resident dense log1p matrix."""
-    n, g, k = args.n, args.g, args.k
-    xy = lattice_coords(n, 42)
-    xy_d = dv.to_device(xy, torch.float64)
-    bbox = dv.spatial_bbox(xy_d)
-    order = dv.spatial_order(xy_d, bbox)
-    xy_s = xy_d[order].contiguous()
-    nbr = dv.knn_build(xy_s, k, bbox)
-    # counts, generated on device in Hilbert row order, kept as CSR pieces
-    model = synth.make_expression_model(xy, g, n_zones=12, seed=42 + rank, log_rate_mean=-3.3, log_rate_sd=1.0,
-                                        device="cuda")
-    xy32 = xy_s.to(torch.float32)
+def build_counts(args, xy, g_total, lo, hi, seed, torch, dv, synth):
+    """Device CSR counts (spots in the order of ``xy``) of genes [lo, hi) of a ``g_total``-gene expression model."""
+    n = xy.shape[0]
+    model = synth.make_expression_model(xy, g_total, n_zones=12, seed=seed, log_rate_mean=-3.3, log_rate_sd=1.0, device="cuda")
+    xy32 = torch.as_tensor(xy, dtype=torch.float32, device="cuda")
     chunk = 4096
     row_nnz, idx_parts, val_parts = [], [], []
     for b, i0 in enumerate(range(0, n, chunk)):
-        c = model.counts(xy32[i0:i0 + chunk], b)
+        c = model.counts(xy32[i0:i0 + chunk], b)[:, lo:hi]
         nz = c > 0
         row_nnz.append(nz.sum(1))
         idx_parts.append(nz.nonzero()[:, 1].to(torch.int32))
@@ -147,117 +152,171 @@ def build_device_workload(args, rank, torch, dv, synth):
         del c, nz
     indptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
     indptr[1:] = torch.cumsum(torch.cat(row_nnz), 0)
-    csr = dv.DeviceCSR(indptr, torch.cat(idx_parts), torch.cat(val_parts), (n, g))
-    del idx_parts, val_parts, row_nnz
-    return xy_s, nbr, csr
+    return dv.DeviceCSR(indptr, torch.cat(idx_parts), torch.cat(val_parts), (n, hi - lo))
 
 
-def dense_from_csr(csr, min_spots, torch, dv, lat=None):
-    """The product's own front-end (K2) on the device-resident counts; with a lattice plan the rows go to lattice layout."""
+def pinned_scipy_csr(csr, torch, pin=True):
+    """Host scipy CSR over page-locked (or ordinary) numpy arrays holding the device CSR's content; float32 counts,
+    int32 indices, int64 indptr - what an AnnData of raw counts holds."""
+    import scipy.sparse as sp
+
+    def host(t):
+        h = t.cpu()
+        return (h.pin_memory() if pin else h).numpy()
+
+    m = sp.csr_matrix((host(csr.data), host(csr.indices), host(csr.indptr)), shape=csr.shape, copy=False)
+    assert m.indices.dtype == np.int32
+    return m
+
+
+def timed_calls(fn, n_warm, n_timed, torch, dist=None):
+    """ms per call of a host-level call (wall clock around a device sync), max over ranks."""
+    for _ in range(n_warm):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        fn()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / n_timed
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------------------------
+# detect_svgs -> pca -> aa through the public API on host data (N = 1)
+# ---------------------------------------------------------------------------------------------
+def pipeline_through_api(args, csr, xy_host, var_names, torch, dv, _lib, ch, core):
+    """The README flow (/root/reference/README.md:66-88): ch.detect_svgs(adata) on raw counts; normalise + log1p the
+    full matrix (scanpy's step, done here once outside the timings); ch.pca(adata); ch.aa(adata).  Each call gets host
+    arrays and leaves its results on the host; page-locked arrays first, ordinary numpy arrays second."""
+    import scipy.sparse as sp
+    from oracle import aa as oaa
+    from oracle import pca as opca
+
     n, g = csr.shape
-    gene_nnz = dv.csr_gene_nnz(csr)
-    keep = gene_nnz >= int(n * min_spots)
-    gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
-                           torch.full_like(gene_nnz, -1))
-    n_keep = int(keep.sum().item())
-    scale = dv.median_scale(dv.csr_spot_totals(csr, gene_col))
-    if lat is None:
-        return dv.csr_densify(csr, gene_col, n_keep, scale, None, apply_log1p=True), n_keep
-    out = torch.zeros((lat.n_rows, dv.dense_ld(n_keep)), dtype=torch.float32, device="cuda")
-    return dv.csr_densify(csr, gene_col, n_keep, scale, lat.row_of_spot, apply_log1p=True, out=out), n_keep
-
-
-def pipeline_stages(args, csr, I, g_scored, svg_e2e_ms, torch, dv, _lib, core):
-    """ch.pca + ch.aa on the cfg4 workload (2,000 top-ranked SVGs, 30 PCs, 12 archetypes), device resident:
-    the README flow normalises the full matrix, then PCA densifies the SVG columns (core.py:126)."""
-    n, g = csr.shape
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    r, A, S = args.pcs, args.archetypes, min(args.svgs, g - 1)
+    peaks, _, _ = measured_peaks()
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
     sync = torch.cuda.synchronize
 
-    def now():
+    def clock(fn, reps=1):
         sync()
-        return time.perf_counter()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        sync()
+        return (time.perf_counter() - t0) / reps
 
-    gene_nnz = dv.csr_gene_nnz(csr)
-    keep = gene_nnz >= int(n * 1e-4)
-    kept_idx = torch.nonzero(keep).squeeze(1)[:g_scored]
-    S = min(args.svgs, g_scored - 1)
-    top = torch.topk(torch.nan_to_num(I, nan=-2.0), S).indices
-    sel = torch.zeros(g, dtype=torch.bool, device="cuda")
-    sel[kept_idx[top]] = True
-    scale = dv.median_scale(dv.csr_spot_totals(csr, torch.arange(g, dtype=torch.int32, device="cuda")))
-    gene_col = torch.where(sel, torch.cumsum(sel.int(), 0, dtype=torch.int32) - 1,
-                           torch.full((g,), -1, dtype=torch.int32, device="cuda"))
-    r, A = args.pcs, args.archetypes
-    t0 = now()
-    P = dv.csr_densify(csr, gene_col, S, scale, None, apply_log1p=True)
-    mean = dv.column_sums(P, S) / n
-    t1 = now()
-    C = dv.gram_centered(P, S, mean, timing=True) / (n - 1)
-    t2 = now()
+    # normalised copy of the matrix (what the user's sc.pp.normalize_total + log1p leaves in adata.X), built on the device
+    totals = dv.csr_spot_totals(csr, torch.zeros(g, dtype=torch.int32, device="cuda"))
+    scale = dv.median_scale(totals)
+    rows = torch.repeat_interleave(torch.arange(n, device="cuda"), csr.indptr[1:] - csr.indptr[:-1])
+    norm = torch.log1p((csr.data.double() * scale[rows]).float())
+    del rows
+
+    out = {"workload": f"ch.detect_svgs(top_svg={S}, min_morans=-1) -> ch.pca(n_pcs={r}) -> ch.aa(n_archetypes={A}, n_pcs={r}, "
+                       f"max_iter={args.aa_max_iter}) on a host AnnData-like object ({n} x {g} CSR)"}
+    keep_ad = None
+    for label, pin in (("pinned", True),) + ((("pageable", False),) if not args.no_pageable else ()):
+        Xc = pinned_scipy_csr(csr, torch, pin)
+        ad = ch.AnnDataLite(Xc, obsm={"spatial": xy_host}, var_names=var_names)
+        svg = lambda: ch.detect_svgs(ad, min_spots=MIN_SPOTS, top_svg=S, min_morans=-1.0, neighbors=args.k)  # noqa: E731
+        svg()                                                         # warm-up: allocator pools, pinned ring, side stream
+        t_svg = clock(svg, 2)
+        n_svg = int(ad.var["spatially_variable"].sum())
+        # the user's normalisation between the calls (not part of the path): same sparsity, new values
+        hn = norm.cpu()
+        ad.X = sp.csr_matrix(((hn.pin_memory() if pin else hn).numpy(), Xc.indices, Xc.indptr), shape=Xc.shape, copy=False)
+        ad.uns["log1p"] = {"base": None}
+        pca = lambda: ch.pca(ad, n_pcs=r)  # noqa: E731
+        pca()
+        t_pca = clock(pca, 2)
+        aa = lambda: ch.aa(ad, n_archetypes=A, n_pcs=r, max_iter=args.aa_max_iter)  # noqa: E731
+        aa()
+        t_aa = clock(aa, 1)
+        out[label] = {"detect_svgs_s": round(t_svg, 4), "pca_s": round(t_pca, 4), "aa_s": round(t_aa, 4),
+                      "end_to_end_s": round(t_svg + t_pca + t_aa, 4), "n_svgs": n_svg, "aa_rss": float(ad.uns["chr_aa"]["RSS"])}
+        if label == "pinned":
+            keep_ad = ad
+        del Xc
+    ad = keep_ad
+    out["end_to_end_s"] = out["pinned"]["end_to_end_s"]
+
+    # ---- stage breakdown of pca on the device + the Gram kernel's tensor roofline (useful flops = 2 N S^2) ----
+    sel = np.asarray(ad.var["spatially_variable"] == True)  # noqa: E712
+    col_map = torch.from_numpy(np.where(sel, np.cumsum(sel) - 1, -1).astype(np.int32)).cuda()
+    S_eff = int(sel.sum())
+    csr_n = dv.DeviceCSR(csr.indptr, csr.indices, norm, csr.shape)
+    sync(); t0 = time.perf_counter()
+    P = dv.csr_densify(csr_n, col_map, S_eff, None, None, apply_log1p=False)
+    mean = dv.column_sums(P, S_eff) / n
+    sync(); t1 = time.perf_counter()
+    C = dv.gram_centered(P, S_eff, mean, timing=True) / (n - 1)
+    sync(); t2 = time.perf_counter()
     gram_ms = dv.last_kernel_ms(_lib.FAMILY_GRAM)
     evals, V, worst = dv.eigh_topk(C, r)
-    t3 = now()
-    scores = dv.pca_scores(P, S, mean, V)
-    t4 = now()
-    emb = scores[:, :r].cpu().numpy()
-    t5 = now()
-    fit = core.aa_stage(emb, A, max_iter=args.aa_max_iter)
-    t6 = now()
-    # executed tensor flops: upper-triangular 128 x 128 tiles, 3 bf16 MMAs per product (hi*hi, hi*lo, lo*hi)
-    nb = (S + 127) // 128
-    n_pad = (n + 63) // 64 * 64
-    executed = 3 * 2.0 * n_pad * (nb * (nb + 1) // 2) * 128 * 128
-    pca_s = t4 - t0
-    aa_s = t6 - t5
-    cpu = pipeline_cpu_baseline(P, S, emb, r, A, n, int(fit["n_iter"]), args, torch)
-    return {"cpu_baseline": cpu, "workload": f"top {S} SVGs of the resident matrix -> {r} PCs -> {A} archetypes, max_iter={args.aa_max_iter}, n_init=3",
-            "svg_e2e_s": None if svg_e2e_ms is None else round(svg_e2e_ms * 1e-3, 4), "pca_s": round(pca_s, 4), "aa_s": round(aa_s, 3),
-            "end_to_end_s": None if svg_e2e_ms is None else round(svg_e2e_ms * 1e-3 + pca_s + aa_s, 3),
-            "pca_breakdown_s": {"densify_colsum": round(t1 - t0, 4), "gram": round(t2 - t1, 4), "eigh": round(t3 - t2, 4),
-                                "scores": round(t4 - t3, 4)},
-            "gram_roofline": {"bound": "tensor", "kernel": "gram_tcgen05_kernel", "kernel_ms": round(gram_ms, 4),
-                              "useful_flops": 2.0 * n * S * S, "executed_flops": executed,
-                              "achieved": round(executed / (gram_ms * 1e-3) / 1e12, 1), "peak": bf16_peak, "unit": "TFLOP/s",
-                              "frac": round(executed / (gram_ms * 1e-3) / 1e12 / bf16_peak, 4),
-                              "useful_tflops": round(2.0 * n * S * S / (gram_ms * 1e-3) / 1e12, 1),
-                              "peak_source": "measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s",
-                              "note": "split-bf16: 3 MMAs per product over the upper-triangular tiles are the executed flops"},
-            "eigh_residual": float(worst), "aa_iterations_best_restart": int(fit["n_iter"]), "aa_rss": float(fit["rss"])}
+    sync(); t3 = time.perf_counter()
+    dv.pca_scores(P, S_eff, mean, V)
+    sync(); t4 = time.perf_counter()
+    useful = 2.0 * n * S_eff * S_eff
+    out["pca_breakdown_s"] = {"densify_colsum": round(t1 - t0, 4), "gram_stage": round(t2 - t1, 4), "eigh": round(t3 - t2, 4),
+                              "scores": round(t4 - t3, 4)}
+    out["gram_roofline"] = {"bound": "tensor", "kernel": "gram_tcgen05_kernel", "kernel_ms": round(gram_ms, 4), "useful_flops": useful,
+                            "achieved": round(useful / (gram_ms * 1e-3) / 1e12, 1), "peak": bf16_peak, "unit": "TFLOP/s",
+                            "frac": round(useful / (gram_ms * 1e-3) / 1e12 / bf16_peak, 4),
+                            "stage_frac": round(useful / (t2 - t1) / 1e12 / bf16_peak, 4),
+                            "peak_source": "measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s",
+                            "note": "useful flops 2 N S^2 (the kernel executes 3 split-bf16 MMAs per product over the upper-triangular tiles)"}
+    out["eigh_residual"] = float(worst)
 
-
-def pipeline_cpu_baseline(P, S, emb, r, A, n, aa_iters, args, torch):
-    """The reference's own CPU calls for PCA (sklearn arpack, core.py:127) and AA (archetypes 0.4.x restated,
-    oracle/aa.py) on BOUNDED row samples of the same data, extrapolated linearly in the number of spots
-    (both are O(N) per Lanczos step / per iteration); every extrapolated figure is labelled as such."""
-    from oracle import aa as oaa
-    from oracle import pca as opca
-    cores = os.cpu_count() or 1
+    # ---- parity at this scale: PCA vs sklearn arpack, AA vs the oracle, on bounded row samples of the same data ----
     rng = np.random.default_rng(0)
     n_pca = min(n, 40_000)
     rows = np.sort(rng.choice(n, n_pca, replace=False))
-    sample = P[torch.from_numpy(rows).cuda(), :S].cpu().numpy()
+    sample = P[torch.from_numpy(rows).cuda()].contiguous()
     t0 = time.perf_counter()
-    opca.pca_arpack(sample, r)
+    ref = opca.pca_arpack(sample[:, :S_eff].cpu().numpy(), r)                    # the reference's own call (core.py:127)
     pca_sample_s = time.perf_counter() - t0
+    ms = dv.column_sums(sample, S_eff) / n_pca
+    Cs = dv.gram_centered(sample, S_eff, ms) / (n_pca - 1)
+    _, Vs, _ = dv.eigh_topk(Cs, r)
+    cos = opca.subspace_cosines(ref["loadings"], Vs.cpu().numpy())
+    # full-size run: the loadings returned through the API span the same space as the device eigenvectors of this breakdown
+    cos_api = opca.subspace_cosines(ad.uns["chr_pca"]["loadings"], V.cpu().numpy())
+    out["pca_parity"] = {"rows": n_pca, "features": S_eff, "components": r, "min_subspace_cosine_vs_sklearn_arpack": float(cos.min()),
+                         "tolerance": 0.9999, "api_vs_breakdown_min_cosine_full_size": float(cos_api.min()),
+                         "note": "GPU Gram + eigensolver and sklearn PCA(arpack) on the same row sample of the cfg4 SVG matrix"}
     n_aa = min(n, 4_000)
     rows = np.sort(rng.choice(n, n_aa, replace=False))
-    X = emb[rows].astype(np.float64)
+    emb = np.asarray(ad.obsm["chr_X_pca"][rows][:, :r], dtype=np.float64)
     init_rows = rng.choice(n_aa, A, replace=False)
-    B0 = np.zeros((A, n_aa)); B0[np.arange(A), init_rows] = 1.0
+    B0 = np.zeros((A, n_aa))
+    B0[np.arange(A), init_rows] = 1.0
+    iters = 3
     t0 = time.perf_counter()
-    it = 3
-    oaa.fit_single(X, np.zeros((n_aa, A)), B0, max_iter=it, tol=0.0)
-    aa_iter_s = (time.perf_counter() - t0) / it
-    n_init = 3
-    return {"kind": "port", "cores": cores,
-            "pca": {"sample": f"sklearn PCA(arpack, {r} comps) on {n_pca} of {n} spots x {S} SVGs", "sample_s": round(pca_sample_s, 3),
-                    "extrapolated_full_s": round(pca_sample_s * n / n_pca, 1), "blas_threads": cores},
-            "aa": {"sample": f"{it} iterations of the restated archetypes loop (scipy.optimize.nnls per row) on {n_aa} of {n} spots",
-                   "s_per_iteration_sample": round(aa_iter_s, 3), "extrapolated_s_per_iteration_full": round(aa_iter_s * n / n_aa, 1),
-                   "extrapolated_full_s": round(aa_iter_s * n / n_aa * aa_iters * n_init, 0),
-                   "note": f"{n_init} restarts x {aa_iters} iterations as in the GPU run; single-threaded Python loop"}}
+    oref = oaa.fit_single(emb, np.zeros((n_aa, A)), B0, max_iter=iters, tol=0.0)
+    aa_iter_s = (time.perf_counter() - t0) / iters
+    st = dv.AAState(torch.from_numpy(emb).cuda(), A)
+    st.init_from_rows(init_rows)
+    for _ in range(iters):
+        rss = st.iterate()
+    out["aa_parity"] = {"rows": n_aa, "iterations": iters, "max_abs_alpha_err_vs_oracle": float(np.abs(st.alphas.cpu().numpy() - oref["alphas"]).max()),
+                        "rss_rel_err": float(abs(rss - oref["rss"]) / oref["rss"]), "tolerance": 1e-3,
+                        "note": "matched initialisation, same rows of the cfg4 PCA scores; oracle = restated archetypes 0.4.x (unpinned)"}
+    cores = os.cpu_count() or 1
+    out["cpu_baseline"] = {"kind": "port", "cores": cores,
+                           "pca": {"sample": f"sklearn PCA(arpack, {r} comps) on {n_pca} of {n} spots x {S_eff} SVGs", "sample_s": round(pca_sample_s, 3),
+                                   "extrapolated_full_s": round(pca_sample_s * n / n_pca, 1), "blas_threads": cores},
+                           "aa": {"sample": f"{iters} iterations of the restated archetypes loop (scipy.optimize.nnls per row) on {n_aa} of {n} spots",
+                                  "s_per_iteration_sample": round(aa_iter_s, 3),
+                                  "extrapolated_s_per_iteration_full": round(aa_iter_s * n / n_aa, 1)}}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -271,188 +330,259 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # host threads of the library's upload pool: the cores this process may use, shared between the ranks of the node
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    os.environ.setdefault("CHR_HOST_THREADS", str(max(1, min(32, cores // max(world, 1)))))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dgroup = dist if world > 1 else None
 
+    import chrysalis_b200 as ch
     from chrysalis_b200 import _lib, core, synth
     from chrysalis_b200 import device as dv
+    from chrysalis_b200 import distributed as dd
 
     _lib.load()
-    MIN_SPOTS = 1e-4
     n, g, k = args.n, args.g, args.k
     t0 = time.time()
-    xy_s, nbr, csr = build_device_workload(args, rank, torch, dv, synth)
-    # square lattice, k = 8: lattice layout + stencil kernel (what detect_svgs picks for this input); otherwise the quad plan
-    lat = dv.lattice_plan(xy_s, nbr) if (args.variant == 0 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0") else None
-    X, g_scored = dense_from_csr(csr, MIN_SPOTS, torch, dv, lat)
+    xy = make_coords(args)                                          # host, spot order = the order the "loader" delivers
+    xy_d = dv.to_device(xy, torch.float64)
+    bbox = dv.spatial_bbox(xy_d)
+    nbr = dv.knn_build(xy_d, k, bbox)
+    # square lattice, k = 8: lattice layout + stencil kernel (what detect_svgs picks for this input); otherwise rows in
+    # Hilbert order + the quad plan of W
+    use_lat = args.variant == 0 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0"
+    lat = dv.lattice_plan(xy_d, nbr, bbox) if use_lat else None
+    rank_of = nbr_rows = plan = None
+    if lat is None:
+        order = dv.spatial_order(xy_d, bbox)
+        rank_of = torch.empty_like(order)
+        rank_of[order] = torch.arange(n, device="cuda")
+        nbr_rows = rank_of.to(torch.int32)[nbr[order].long()].contiguous()
+        plan = dv.moran_plan(nbr_rows)
+    row_of_spot = lat.row_of_spot if lat is not None else rank_of
+    n_rows = lat.n_rows if lat is not None else n
+    strong = world > 1 and args.scaling == "strong"
+
+    def local_counts(scaling):
+        if scaling == "strong":
+            lo, hi = dd.shard_range(g, rank, world)
+            return build_counts(args, xy, g, lo, hi, 42, torch, dv, synth)
+        return build_counts(args, xy, g, 0, g, 42 + rank, torch, dv, synth)
+
+    def densify(csr, scaling):
+        """The product's own front-end (K2) on the device-resident counts -> (dense resident matrix, genes scored)."""
+        gene_nnz = dv.csr_gene_nnz(csr)
+        keep = gene_nnz >= int(n * MIN_SPOTS)
+        gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(gene_nnz, -1))
+        n_keep = int(keep.sum().item())
+        totals = dv.csr_spot_totals(csr, gene_col)
+        if scaling == "strong" and world > 1:
+            dist.all_reduce(totals)                                   # normalize_total sums over the kept genes of every rank
+        buf = torch.zeros((n_rows, dv.dense_ld(n_keep)), dtype=torch.float32, device="cuda")
+        return dv.csr_densify(csr, gene_col, n_keep, dv.median_scale(totals), row_of_spot, apply_log1p=True, out=buf), n_keep
+
+    def moran(X, g_sc, timing=False, variant=args.variant):
+        if lat is not None and variant == 0:
+            return dv.moran_lattice(X, lat, g_sc, timing=timing)
+        return dv.moran_dense(X, nbr_rows, g_sc, timing=timing, variant=variant, plan=plan)
+
+    def measure(X, g_sc):
+        """Device-timed resident throughput: K steps bracketed by barrier + synchronize, max over ranks."""
+        counts = torch.tensor([g_sc], device="cuda")
+        sizes = [torch.zeros_like(counts) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(sizes, counts)
+        else:
+            sizes = [counts]
+        sizes = [int(s.item()) for s in sizes]
+        g_max, g_tot = max(sizes), sum(sizes)
+        padded = torch.zeros(g_max, dtype=torch.float64, device="cuda")
+        gathered = [torch.empty(g_max, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+        def step(timing=False):
+            I, _, _ = moran(X, g_sc, timing)
+            if world > 1:                                             # the one exchange of the path: per-gene statistics
+                padded[:g_sc] = I
+                dist.all_gather(gathered, padded)
+            return I
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            I = step(timing=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+        total_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        # dominant-kernel duration: a separate short loop with per-launch events (same stream, same inputs > L2), so
+        # reading the events does not perturb the timed region above
+        kms = []
+        for _ in range(min(args.steps, 10)):
+            moran(X, g_sc, True)
+            kms.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
+        return dict(I=I, g_tot=g_tot, ms_per_step=total_ms / args.steps, kernel_ms=float(np.mean(kms)), clocks=clocks)
+
+    weak_rec = None
+    if strong and not args.no_weak:
+        # weak scaling beside the strong figure: every rank its own g genes (the round-1 measurement)
+        csr_w = local_counts("weak")
+        Xw, gw = densify(csr_w, "weak")
+        del csr_w
+        w = measure(Xw, gw)
+        weak_rec = {"value": round(w["g_tot"] / (w["ms_per_step"] * 1e-3), 1), "unit": UNIT, "ms_per_step": round(w["ms_per_step"], 4),
+                    "genes": w["g_tot"], "genes_per_gpu": gw, "scaling": "weak", "kernel_ms_rank0": round(w["kernel_ms"], 4)}
+        del Xw, w
+        torch.cuda.empty_cache()
+
+    scaling = "strong" if (strong or world == 1) else "weak"
+    csr = local_counts(scaling)
+    X, g_sc = densify(csr, scaling)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
-    density = csr.data.numel() / (n * g)
-
-    gathered = [torch.empty(g_scored, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
-    plan = dv.moran_plan(nbr) if lat is None else None     # W's device plan: part of building W (K1), reused by every pass over genes
-
-    def moran(timing=False, variant=args.variant):
-        if lat is not None and variant == 0:
-            return dv.moran_lattice(X, lat, g_scored, timing=timing)
-        return dv.moran_dense(X, nbr, g_scored, timing=timing, variant=variant, plan=plan)
-
-    def step(timing=False):
-        I, _, _ = moran(timing)
-        if world > 1:
-            # every rank scores the same number of genes only if the filter keeps the same count;
-            # pad to a common length for the all-gather of per-gene statistics
-            dist.all_gather(gathered, I)
-        return I
-
-    # every rank must all-gather equal sizes: agree on min g_scored (synthetic shards differ by seed)
-    if world > 1:
-        t = torch.tensor([g_scored], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        g_scored = int(t.item())
-        gathered = [torch.empty(g_scored, dtype=torch.float64, device="cuda") for _ in range(world)]
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    sampler.start()
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        I = step(timing=True)
-        kernel_ms.append(None)  # filled after the region (reading an event would synchronise)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    total_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-
-    # dominant-kernel duration: a separate short loop with per-launch events (same stream, same
-    # inputs > L2), so reading the events does not perturb the timed region above
-    kms = []
-    for _ in range(min(args.steps, 10)):
-        moran(True)
-        kms.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
-    kernel_ms = float(np.mean(kms))
+    m = measure(X, g_sc)
+    I = m["I"]
+    density = csr.data.numel() / (n * csr.shape[1])
+    value = m["g_tot"] / (m["ms_per_step"] * 1e-3)
 
     sweep = {}
     for v in [int(x) for x in args.sweep.split(",") if x != ""]:
+        if lat is not None and v != 0:
+            continue                                                  # the quad-plan variants need Hilbert-ordered rows
         ts = []
         for _ in range(6):
-            Iv, _, _ = moran(True, v)
+            Iv, _, _ = moran(X, g_sc, True, v)
             ts.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
         sweep[str(v)] = {"kernel_ms": round(float(np.mean(ts[1:])), 4), "bit_identical_to_default": bool(torch.equal(Iv, I))}
 
-    ms_per_step = total_ms / args.steps
-    value = world * g_scored / (ms_per_step * 1e-3)
-
-    # roofline of the dominant kernel: algorithmic bytes = one read of X
-    # + W indices + per-split partial sums + outputs  
+    # roofline of the dominant kernel: algorithmic bytes = one read of X + W indices + outputs (DESIGN.md, SURVEY.md 8d)
     ld = X.stride(0)
-    alg_bytes = 4.0 * n * g_scored + 4.0 * n * k + 8.0 * g_scored
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    alg_bytes = 4.0 * n * g_sc + 4.0 * n * k + 8.0 * g_sc
+    _, peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (m["kernel_ms"] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "moran_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # measured on a gene slab: DRAM bytes scale with the genes of this launch
+            traffic = tj["dram_bytes_per_gene"] * g_sc if "dram_bytes_per_gene" in tj else tj.get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
     if lat is not None:
-        kernels = ["moran_lattice_pilot_kernel", "moran_lattice_fill_kernel", "moran_lattice_kernel", "moran_lattice_corr_kernel", "moran_finalize_kernel"]
-    elif args.variant == 4:
-        kernels = ["moran_pilot_kernel", "moran_stream_kernel", "moran_finalize_kernel"]
+        kernels = ["moran_lattice_pilot_kernel"] + (["moran_lattice_fill_kernel"] if lat.absent.numel() else []) + ["moran_lattice_kernel"] + \
+                  (["moran_lattice_corr_kernel"] if lat.corr.shape[0] else []) + ["moran_finalize_kernel"]
+        main_kernel = "moran_lattice_kernel"
     else:
-        kernels = ["moran_pilot_kernel", "moran_tile_kernel", "moran_finalize_kernel"]
-    main_kernel = kernels[2] if lat is not None else kernels[1]
+        main_kernel = "moran_stream_kernel" if args.variant == 4 else "moran_tile_kernel"
+        kernels = ["moran_pilot_kernel", main_kernel, "moran_finalize_kernel"]
     roofline = {"bound": "hbm", "kernel": main_kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kernel_ms, 4),
-                "kernel_share_of_step": round(kernel_ms / ms_per_step, 4)}
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(m["kernel_ms"], 4),
+                "kernel_share_of_step": round(m["kernel_ms"] / m["ms_per_step"], 4),
+                "note": "rank 0's launch (its gene shard at N > 1)"}
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes per GPU, square lattice, kNN k={k}, "
-                               f"dense float32 log1p(normalize_total(counts)) resident in HBM",
-                   "n_spots": n, "genes_per_gpu": g, "genes_scored_per_gpu": g_scored, "genes_total": world * g_scored,
-                   "neighbors": k, "ld": ld, "counts_density": round(density, 4), "parallelism": f"gene-shard x{world}",
-                   "l2_policy": "inputs_exceed_l2 (X = %.1f GB per GPU >> 126 MB L2)" % (4.0 * n * ld / 1e9),
+        "warmup": max(args.warmup, 3), "ms_per_step": round(m["ms_per_step"], 4), "higher_is_better": True,
+        "scaling": scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(n, g, k), "n_spots": n, "genes": m["g_tot"], "genes_per_gpu": g_sc, "neighbors": k,
+                   "ld": ld, "rows_resident": int(X.shape[0]), "counts_density": round(density, 4),
+                   "parallelism": f"gene-shard x{world}" + ("" if world == 1 else f" ({scaling} scaling; all-gather of per-gene statistics timed)"),
+                   "layout": "lattice layout (60-row bands), stencil kernel" if lat is not None else "Hilbert row order, quad plan of W",
+                   "l2_policy": "inputs_exceed_l2 (X = %.1f GB per GPU >> 126 MB L2)" % (4.0 * X.shape[0] * ld / 1e9),
                    "variant": args.variant, "setup_s": round(setup_s, 1)},
-        "roofline": roofline, "clocks": clocks, "gpu_launches": len(kernels) * args.steps,
-        "kernels_per_step": kernels,
+        "roofline": roofline, "clocks": m["clocks"], "gpu_launches": len(kernels) * args.steps, "kernels_per_step": kernels,
     }
     if sweep:
         out["variant_sweep"] = sweep
+    if weak_rec:
+        out["weak"] = weak_rec
 
-    # ---- e2e: host CSR (pinned) -> device -> full SVG stage -> host -------------------------------
+    # ---- e2e: the public call on host buffers ---------------------------------------------------------------------------
+    var_names = [f"gene{j}" for j in range(*(dd.shard_range(g, rank, world) if strong else (0, g)))]
+    I_res = I.cpu().numpy()
     if not args.no_e2e:
-        host = dv.PinnedCSR(csr.indptr.cpu().pin_memory(), csr.indices.cpu().pin_memory(), csr.data.cpu().pin_memory(),
-                            csr.shape)
-        xy_host = xy_s.cpu().numpy()
-        xy_host[:, 1] *= -1                                       # svg_stage negates y like core.py:62
-        del X
+        X = None
         torch.cuda.empty_cache()
+        Xh = pinned_scipy_csr(csr, torch, pin=True)
+        ad = ch.AnnDataLite(Xh, obsm={"spatial": xy}, var_names=var_names, uns={"chr_gene_shard": True} if strong else None)
         e_steps = max(2, min(args.steps, 5))
 
-        def e2e_step():
-            keep, I_h, _ = core.svg_stage(host, xy_host, MIN_SPOTS, k, False, already_log1p=False, shard=False)
-            return I_h
+        def e2e_step(a=ad):
+            # every rank works on its own AnnData: its gene shard (strong, one exchange inside) or its own matrix (weak: no group call)
+            if world > 1 and not strong:
+                keep, I_, _ = core.svg_stage(a.X, a.obsm["spatial"], MIN_SPOTS, k, False, already_log1p=False, shard=False)
+                a.var["Moran's I"] = I_ if len(I_) == a.X.shape[1] else np.nan
+            else:
+                ch.detect_svgs(a, min_spots=MIN_SPOTS, neighbors=k)
 
-        for _ in range(3):                                        # warm-up: allocator pools, pinned staging, side stream
-            I_h = e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t1 = time.perf_counter()
-        for _ in range(e_steps):
-            I_h = e2e_step()
-        torch.cuda.synchronize()
-        e_ms = (time.perf_counter() - t1) * 1e3 / e_steps
-        if core.SVG_TRACE:                                        # CHR_SVG_TRACE=1: host timeline of the last step
+        e_ms = timed_calls(e2e_step, 3, e_steps, torch, dgroup)
+        if core.SVG_TRACE:                                            # CHR_SVG_TRACE=1: host timeline of the last step
             sys.stderr.write(f"svg_stage trace (ms): {core.SVG_TRACE}\n")
+        I_h = np.asarray(ad.var["Moran's I"], dtype=np.float64)
+        scored = int(np.isfinite(I_h).sum())
+        tot = torch.tensor([scored], device="cuda")
         if world > 1:
-            t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
-        same = bool(len(I_h) >= g_scored and np.array_equal(I_h[:g_scored], I.cpu().numpy()))
-        out["e2e"] = {"value": round(world * len(I_h) / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 2),
-                      "h2d_bytes_per_step": int(host.nbytes + xy_host.nbytes), "d2h_bytes_per_step": int(8 * len(I_h) + g),
-                      "steps": e_steps, "path": "core.svg_stage(PinnedCSR counts, coords): H2D + filter/normalise/log1p/densify + "
-                                                "Hilbert sort + kNN + Moran + D2H",
-                      "bit_identical_to_resident_run": same}
-        X, _ = dense_from_csr(csr, MIN_SPOTS, torch, dv, lat)
+            dist.all_reduce(tot)
+        h2d = int(Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes + xy.nbytes)
+        same = float(np.abs(I_h[np.isfinite(I_h)] - I_res).max()) if scored == g_sc else None
+        out["e2e"] = {"value": round(int(tot.item()) / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 2),
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * scored + csr.shape[1]), "steps": e_steps,
+                      "path": "ch.detect_svgs(adata): adata.X = scipy CSR counts in page-locked host arrays" +
+                              (" (this rank's gene shard, .uns['chr_gene_shard'])" if strong else "") +
+                              " -> H2D, filter/normalise/log1p/densify, kNN + W plan, Moran, D2H, pandas ranking + .var writes",
+                      "max_abs_diff_to_resident_run": same}
+        if world == 1 and not args.no_pageable:
+            Xp = pinned_scipy_csr(csr, torch, pin=False)
+            adp = ch.AnnDataLite(Xp, obsm={"spatial": xy}, var_names=var_names)
+            p_ms = timed_calls(lambda: e2e_step(adp), 1, 2, torch)
+            out["e2e_pageable"] = {"value": round(scored / (p_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(p_ms, 2),
+                                   "host_threads": int(_lib.query("chr_host_threads")),
+                                   "path": "same call, adata.X in ordinary (pageable) numpy arrays: multi-threaded pinned bounce ring"}
+            del Xp, adp
+        del Xh, ad
 
-    # ---- the rest of the path on the same resident data: PCA (tcgen05 Gram) + AA, stage seconds -----------
+    # ---- the rest of the path through the API on host data: detect_svgs -> pca -> aa ------------------------------------
     if rank == 0 and world == 1 and not args.no_pipeline:
-        out["pipeline"] = pipeline_stages(args, csr, I, g_scored, out.get("e2e", {}).get("ms_per_step"), torch, dv, _lib, core)
+        X = None
+        torch.cuda.empty_cache()
+        out["pipeline"] = pipeline_through_api(args, csr, xy, var_names, torch, dv, _lib, ch, core)
 
-    # ---- cpu baseline + parity on a bounded gene sample (rank 0, N=1 only) ---------------------------
+    # ---- cpu baseline + parity on a bounded gene sample (rank 0, N = 1 only) ---------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import moran as om
         from oracle import weights as ow
+        if X is None:
+            torch.cuda.empty_cache()
+            X, _ = densify(csr, scaling)
         # bounded sample: up to 1024 evenly spaced genes, stopped after --cpu-seconds of CPU work
-        cols = np.unique(np.linspace(0, g_scored - 1, min(g_scored, 1024)).astype(np.int64))
+        cols = np.unique(np.linspace(0, g_sc - 1, min(g_sc, 1024)).astype(np.int64))
         cols = cols[np.random.default_rng(0).permutation(len(cols))]          # any prefix is spread over the gene range
         sample = np.empty((n, len(cols)), dtype=np.float32)
         for b in range(0, len(cols), 128):
             cb = torch.from_numpy(cols[b:b + 128]).cuda()
-            sample[:, b:b + 128] = (X[:, cb] if lat is None else X[lat.row_of_spot[:, None], cb[None, :]]).cpu().numpy()
-        nbr_h = nbr.cpu().numpy()
-        w = ow.row_standardised_csr(nbr_h)
-        I_dev = I.cpu().numpy()
+            sample[:, b:b + 128] = X[row_of_spot[:, None], cb[None, :]].cpu().numpy()
+        pts = xy.copy()
+        pts[:, 1] *= -1
+        w = ow.row_standardised_csr(nbr.cpu().numpy())                        # the W the device used (its own kNN)
         t1 = time.perf_counter()
         done, ref = 0, []
         for j in range(sample.shape[1]):
@@ -463,7 +593,7 @@ def run_native(args):
         cpu_s = time.perf_counter() - t1
         ref = np.array(ref)
         # same bound as tests/test_moran_gpu.py: 1e-5 relative plus the float32-input floor of 2e-7
-        err = np.abs(I_dev[cols[:done]] - ref) / (np.abs(ref) + 2e-7 / 1e-5)
+        err = np.abs(I_res[cols[:done]] - ref) / (np.abs(ref) + 2e-7 / 1e-5)
         out["cpu_baseline"] = {"value": round(done / cpu_s, 3), "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"{done} genes spread over the same {n}-bin matrix, reference-style loop "
                                          f"(one scipy CSR.vector per gene, oracle/moran.py:morans_I), {cpu_s:.1f} s"}
@@ -504,7 +634,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     per_step = 16 * cores                                        # genes per step (bounded sample)
     n_sample = per_step
-    xy = lattice_coords(n, 42)
+    xy = make_coords(args)
     model = synth.make_expression_model(xy, n_sample, n_zones=12, seed=42, log_rate_mean=-3.3, log_rate_sd=1.0)
     xy_t = torch.as_tensor(xy, dtype=torch.float32)
     X = np.empty((n, n_sample), dtype=np.float32)
@@ -530,9 +660,9 @@ def run_reference(args):
     value = n_sample / (ms * 1e-3)
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{WORKLOAD['name']}: {n} bins x {g} genes, square lattice, kNN k={k}", "n_spots": n,
-                      "genes_per_gpu": g, "neighbors": k},
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_string(n, g, k), "n_spots": n, "genes": g, "neighbors": k,
+                      "sample_genes_per_step": n_sample},
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{n_sample} genes of the {n}-bin workload per step; reference-style per-gene loop "
                                       f"(scipy cKDTree W + one CSR.vector per gene, oracle/moran.py) run gene-parallel on "

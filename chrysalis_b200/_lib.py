@@ -31,6 +31,10 @@ _SIGNATURES = {
     "chr_version": (c_int, []),
     "chr_last_error": (c_char_p, []),
     "chr_last_kernel_ms": (c_float, [c_int]),
+    "chr_host_threads": (c_int, []),
+    "chr_host_upload": (c_int, [_P, _P, c_size_t, _P]),
+    "chr_host_csr_select_count": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
+    "chr_host_csr_select_upload": (c_int, [_P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P]),
     "chr_knn_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "chr_spatial_bbox": (c_int, [_P, c_int64, _P, _P]),
     "chr_knn_build": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),

@@ -82,7 +82,7 @@ class _stream_ctx:
 
 
 def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already_log1p: bool, timing: bool = False,
-              shard: bool = True, permutations: int = 0, seed: int | None = None):
+              shard: bool = True, permutations: int = 0, seed: int | None = None, local_shard: bool = False):
     """Device part of ``detect_svgs``: filter -> normalise/log1p -> kNN W -> Moran's I.
 
     Returns host arrays ``(keep_mask (G,), I (G',), C (G',) or None)``; also usable directly
@@ -93,6 +93,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     ``normalize_total`` are all-reduced, W is built on every rank, Moran's I needs no exchange,
     and the per-gene results are all-gathered so every rank returns the full arrays.
     ``shard=False`` keeps the call local to this rank (every rank works on its own matrix).
+    ``local_shard=True``: ``X`` already is this rank's gene shard (a loader that reads column ranges per rank): nothing
+    is sliced, the exchanges are the same; the returned arrays cover the genes of all ranks in rank order.
     ``permutations=P > 0`` (esda's ``Moran(..., permutations=P)``) appends a dict of the simulated
     quantities (p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim; host arrays over the scored genes).
     """
@@ -102,7 +104,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         SVG_TRACE.clear()
         t0 = time.perf_counter()
     rank, size = dd.world() if shard else (0, 1)
-    lo, hi = dd.shard_range(g_all, rank, size)
+    lo, hi = (0, g_all) if local_shard else dd.shard_range(g_all, rank, size)
     # While the counts are in flight: W (core.py:61-65, needs the coordinates only) and the zero fill of the dense
     # matrix run on a side stream; the side stream waits for everything enqueued so far, not for the upload enqueued next.
     main = torch.cuda.current_stream() if torch.cuda.is_available() else None
@@ -116,13 +118,22 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     if side is not None:
         side.wait_stream(main)
     _mark(t0, "coords uploaded")
-    Xs = X if size == 1 else X[:, lo:hi]
     # counts already in pinned (or device) memory upload asynchronously: enqueue that first, then the side-stream work.
-    # Anything else (scipy CSR in pageable memory) is a blocking copy: the side-stream work is launched before it.
-    async_upload = isinstance(Xs, (dv.PinnedCSR, dv.DeviceCSR))
+    # Anything else (scipy CSR in pageable memory) keeps the host busy filling bounce buffers: the side-stream work is
+    # launched before it.  A rank's gene shard of a host matrix is selected while uploading (no host-side slicing).
+    split = size > 1 and not local_shard
+
+    def upload_counts():
+        if not split:
+            return dv.upload_csr(X)
+        col_map = np.full(g_all, -1, dtype=np.int32)
+        col_map[lo:hi] = np.arange(hi - lo, dtype=np.int32)
+        return dv.upload_csr_selected(X, col_map)
+
+    async_upload = not split and dv.host_arrays_pinned(X)
     csr = None
     if async_upload:
-        csr = dv.upload_csr(Xs)
+        csr = upload_counts()
         _mark(t0, "counts upload enqueued")
     with _stream_ctx(side):
         # core.py:64-65  kNN weights, row-standardised.  kNN on the spots as given: distance ties go to the lower ORIGINAL
@@ -147,8 +158,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
             dense_buf = torch.empty((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
             dense_buf.zero_()
     if csr is None:
-        csr = dv.upload_csr(Xs)
-        _mark(t0, "counts uploaded (blocking copy)")
+        csr = upload_counts()
+        _mark(t0, "counts uploaded (bounce ring)")
     if side is not None:
         main.wait_stream(side)
         keep_alive = [rank_of, dense_buf] + ([nbr, plan.buf] if plan is not None else []) + \
@@ -165,7 +176,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     _mark(t0, "gene filter known on the host (upload finished)")
     gather = dd.allgather_ragged if size > 1 else (lambda t, n_total=None: t)
     reduce_ = dd.allreduce_sum_ if size > 1 else (lambda t: t)
-    keep_all = gather(keep, g_all)
+    keep_all = gather(keep, None if local_shard else g_all)
     if int(keep_all.sum().item()) == 0:
         return keep_all.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
     # core.py:55-57  normalize_total + log1p on the filtered copy unless the caller already did
@@ -214,11 +225,18 @@ def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans:
     """
     assert 0 < min_spots < 1
 
+    # Multi-GPU extension (no counterpart in the reference): under torch.distributed an AnnData flagged with
+    # .uns['chr_gene_shard'] holds this rank's GENES only (all spots) - a loader that reads column ranges per rank.
+    # Scores and the top_svg / min_morans rule are then global over the genes of all ranks; every rank writes its own .var.
+    local_shard = bool(dict(adata.uns).get('chr_gene_shard', False)) and dd.world()[1] > 1
     keep, I, C = svg_stage(adata.X, adata.obsm['spatial'], min_spots, neighbors, geary,
-                           already_log1p="log1p" in adata.uns_keys())
+                           already_log1p="log1p" in adata.uns_keys(), local_shard=local_shard)
 
     # names of the filtered copy after var_names_make_unique (core.py:53-54)
-    names = _make_unique(pd.Index(adata.var_names)[keep])
+    var_names = pd.Index(adata.var_names)
+    if local_shard:
+        var_names = pd.Index([v for part in dd.allgather_objects(list(var_names)) for v in part])
+    names = _make_unique(var_names[keep])
 
     moran_df = pd.DataFrame(data=I, index=names, columns=["Moran's I"])
     moran_df = moran_df.sort_values(ascending=False, by="Moran's I")
@@ -316,10 +334,15 @@ def pca_stage(X, sel: np.ndarray, n_pcs: int, timing: bool = False):
         raise ValueError(f"n_pcs={n_pcs} exceeds this implementation's limit of {MAX_PCS} principal components")
     rank, size = dd.world()
     lo, hi = dd.shard_range(n, rank, size)
-    csr = dv.upload_csr(X if size == 1 else X[lo:hi])
-    sel_d = dv.to_device(sel.astype(np.bool_))
-    gene_col = torch.where(sel_d, torch.cumsum(sel_d.to(torch.int32), 0, dtype=torch.int32) - 1,
-                           torch.full((sel_d.numel(),), -1, dtype=torch.int32, device=sel_d.device))
+    col_map = np.where(sel, np.cumsum(sel) - 1, -1).astype(np.int32)
+    if isinstance(X, (dv.DeviceCSR, dv.PinnedCSR)) or (size == 1 and dv.host_arrays_pinned(X)):
+        # resident or page-locked arrays: one asynchronous copy of everything, columns picked on the device
+        csr = dv.csr_rows(dv.upload_csr(X), lo, hi)
+        gene_col = dv.to_device(col_map)
+    else:
+        # ordinary host arrays: only the entries of the SVG columns (and of this rank's spots) cross PCIe
+        csr = dv.upload_csr_selected(X, col_map, lo, hi)
+        gene_col = torch.arange(s, dtype=torch.int32, device=csr.data.device)
     P = dv.csr_densify(csr, gene_col, s, None, None, apply_log1p=False)     # core.py:126  .X.todense()
     mean = dd.allreduce_sum_(dv.column_sums(P, s)) / n
     C = dd.allreduce_sum_(dv.gram_centered(P, s, mean, timing=timing)) / (n - 1)   # covariance (ddof=1)

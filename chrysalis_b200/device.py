@@ -77,20 +77,111 @@ class PinnedCSR:
         return sum(t.numel() * t.element_size() for t in (self.indptr, self.indices, self.data))
 
 
-def upload_csr(X) -> DeviceCSR:
-    """scipy CSR (or anything ``scipy.sparse.csr_matrix`` accepts, incl. dense) or PinnedCSR -> DeviceCSR."""
+_BOUNCE_MIN_BYTES = 8 << 20
+
+
+def upload_array(a: np.ndarray, dtype=None) -> torch.Tensor:
+    """Host ndarray -> device tensor at the best rate its memory allows: page-locked arrays (e.g. numpy views of pinned
+    torch tensors) go as one asynchronous copy; large pageable arrays through the library's multi-threaded pinned
+    bounce ring (``chr_host_upload``); small ones as a plain copy.  A dtype change happens on the DEVICE (the host never
+    makes a converted copy)."""
+    dev = _require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    nbytes = t.numel() * t.element_size()
+    if t.is_pinned():
+        d = t.to(dev, non_blocking=True)
+    elif nbytes >= _BOUNCE_MIN_BYTES:
+        d = torch.empty(t.shape, dtype=t.dtype, device=dev)
+        _lib.call("chr_host_upload", d.data_ptr(), t.data_ptr(), nbytes, _stream())
+    else:
+        d = t.to(dev)
+    if dtype is not None and d.dtype != dtype:
+        d = d.to(dtype)
+    return d
+
+
+def _as_csr(X):
     import scipy.sparse as sp
 
+    if not sp.issparse(X) or X.format != "csr":
+        X = sp.csr_matrix(X)
+    return X
+
+
+def upload_csr(X) -> DeviceCSR:
+    """scipy CSR (or anything ``scipy.sparse.csr_matrix`` accepts, incl. dense) or PinnedCSR -> DeviceCSR."""
     if isinstance(X, DeviceCSR):
         return X
     if isinstance(X, PinnedCSR):
         dev = _require_cuda()
         return DeviceCSR(X.indptr.to(dev, non_blocking=True), X.indices.to(dev, non_blocking=True),
                          X.data.to(dev, non_blocking=True), tuple(X.shape))
-    if not sp.issparse(X) or X.format != "csr":
-        X = sp.csr_matrix(X)
-    return DeviceCSR(to_device(X.indptr, torch.int64), to_device(X.indices, torch.int32),
-                     to_device(X.data, torch.float32), tuple(X.shape))
+    X = _as_csr(X)
+    return DeviceCSR(upload_array(X.indptr, torch.int64), upload_array(X.indices, torch.int32),
+                     upload_array(X.data, torch.float32), tuple(X.shape))
+
+
+def csr_rows(csr: DeviceCSR, lo: int, hi: int) -> DeviceCSR:
+    """Rows [lo, hi) of a device CSR (views; one small read-back for the two offsets)."""
+    n = csr.shape[0]
+    if lo == 0 and hi == n:
+        return csr
+    b, e = (int(v) for v in csr.indptr[[lo, hi]].cpu())
+    return DeviceCSR((csr.indptr[lo:hi + 1] - b).contiguous(), csr.indices[b:e], csr.data[b:e], (hi - lo, csr.shape[1]))
+
+
+def host_arrays_pinned(X) -> bool:
+    """True when the CSR arrays of ``X`` can be copied asynchronously as they are (pinned / device resident)."""
+    if isinstance(X, (PinnedCSR, DeviceCSR)):
+        return True
+    import scipy.sparse as sp
+
+    if not (sp.issparse(X) and X.format == "csr") or not torch.cuda.is_available():
+        return False
+    return all(torch.from_numpy(a).is_pinned() for a in (X.indices, X.data))
+
+
+_DATA_KINDS = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.float64): 2}
+
+
+def select_count(X, col_map: np.ndarray, row_lo: int = 0, row_hi: int | None = None):
+    """Host count pass of the column selection over rows [row_lo, row_hi) of the scipy CSR ``X``:
+    (indptr view int64, sel_indptr int64 [rows + 1], selected nnz).  Runs on the library's host thread pool."""
+    import ctypes
+
+    n, g = X.shape
+    row_hi = n if row_hi is None else row_hi
+    rows = row_hi - row_lo
+    indptr = np.ascontiguousarray(X.indptr[row_lo:row_hi + 1], dtype=np.int64)
+    col_map = np.ascontiguousarray(col_map, dtype=np.int32)
+    assert col_map.shape == (g,) and X.indices.dtype == np.int32 and X.indices.flags.c_contiguous
+    sel_indptr = np.empty(rows + 1, dtype=np.int64)
+    nnz = ctypes.c_int64(0)
+    _lib.call("chr_host_csr_select_count", indptr.ctypes.data, X.indices.ctypes.data, rows, g, col_map.ctypes.data,
+              sel_indptr.ctypes.data, ctypes.addressof(nnz))
+    return indptr, sel_indptr, int(nnz.value)
+
+
+def upload_csr_selected(X, col_map: np.ndarray, row_lo: int = 0, row_hi: int | None = None) -> DeviceCSR:
+    """Rows [row_lo, row_hi) of the host scipy CSR ``X`` restricted to the columns with ``col_map[c] >= 0`` (renumbered to
+    ``col_map[c]``) as a DeviceCSR - only the selected entries cross PCIe (``chr_host_csr_select_*``).  What ``pca`` needs
+    of ``adata.X`` (core.py:126) and what a rank needs of it under gene-sharded ``detect_svgs``."""
+    dev = _require_cuda()
+    X = _as_csr(X)
+    if X.indices.dtype != np.int32 or X.data.dtype not in _DATA_KINDS:
+        X = X.astype(np.float32) if X.data.dtype not in _DATA_KINDS else X
+        if X.indices.dtype != np.int32:
+            raise _lib.ChrysalisNativeError("CSR matrices with 64-bit column indices are not supported")
+    col_map = np.ascontiguousarray(col_map, dtype=np.int32)
+    indptr, sel_indptr, nnz = select_count(X, col_map, row_lo, row_hi)
+    rows = sel_indptr.shape[0] - 1
+    out_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    out_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    data = np.ascontiguousarray(X.data)
+    _lib.call("chr_host_csr_select_upload", indptr.ctypes.data, X.indices.ctypes.data, data.ctypes.data, _DATA_KINDS[data.dtype], rows,
+              col_map.ctypes.data, sel_indptr.ctypes.data, out_idx.data_ptr(), out_val.data_ptr(), _stream())
+    n_sel = int(col_map.max()) + 1 if col_map.size and col_map.max() >= 0 else 0
+    return DeviceCSR(upload_array(sel_indptr, torch.int64), out_idx[:nnz], out_val[:nnz], (rows, n_sel))
 
 
 # ---- K2 ----------------------------------------------------------------------------------

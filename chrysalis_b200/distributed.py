@@ -60,3 +60,13 @@ def allgather_ragged(t: torch.Tensor, n_total: int | None = None) -> torch.Tenso
     if n_total is not None and out.shape[0] != n_total:
         raise RuntimeError(f"all-gathered {out.shape[0]} items, expected {n_total}")
     return out
+
+
+def allgather_objects(obj) -> list:
+    """One picklable host object per rank, in rank order (gene names of a gene-sharded AnnData)."""
+    rank, size = world()
+    if size == 1:
+        return [obj]
+    out = [None] * size
+    dist.all_gather_object(out, obj)
+    return out

@@ -44,6 +44,23 @@ float chr_last_kernel_ms(int family);
 #define CHR_FLAG_PRESHIFTED 0x4u /* Moran: columns of X were already shifted to ~zero mean (no in-kernel shift) */
 #define CHR_VARIANT_SHIFT 8   /* bits 8..15 of `flags`: kernel variant (0 = default; tuning)  */
 
+/* ---- host side: AnnData's CSR arrays from PAGEABLE host memory to the device -----------------
+ * the reference passes adata.X (scipy CSR in numpy arrays) to CPU libraries (core.py:53-59, :126); here it crosses PCIe.
+ * A pool of host threads (CHR_HOST_THREADS, default all cores, <= 32) fills a ring of pinned bounce buffers
+ * (4 x 32 MB, allocated once) while earlier chunks are in flight.  All pointers named *_host / src_host are HOST
+ * pointers; the calls return once the last chunk has been queued on `stream`. */
+int chr_host_threads(void);
+int chr_host_upload(void* dst_device, const void* src_host, size_t bytes, chr_stream_t stream);
+/* column selection while uploading (pca densifies the SVG columns only, core.py:126; a rank's gene shard under
+ * multi-GPU detect_svgs): col_map_host[c] = new column index or -1.  count: sel_indptr_host [n + 1] int64 and the
+ * selected nnz; upload: new column indices (int32) and values (float32) of the selected entries, row by row, into
+ * device arrays of that length.  data_kind: 0 float32, 1 int32, 2 float64 values in the source. */
+int chr_host_csr_select_count(const int64_t* indptr_host, const int32_t* indices_host, int64_t n, int64_t n_genes,
+                              const int32_t* col_map_host, int64_t* sel_indptr_host, int64_t* nnz_out_host);
+int chr_host_csr_select_upload(const int64_t* indptr_host, const int32_t* indices_host, const void* data_host,
+                               int data_kind, int64_t n, const int32_t* col_map_host, const int64_t* sel_indptr_host,
+                               int32_t* out_indices_dev, float* out_data_dev, chr_stream_t stream);
+
 /* ---- K1: spatial weights -------------------------------------------------------------
  * replaces  weights.KNN.from_array(points, k=neighbors); w.transform = 'R'
  *           (/root/reference/chrysalis/core.py:64-65; libpysal -> scipy cKDTree.query(k+1))

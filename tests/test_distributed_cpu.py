@@ -84,6 +84,20 @@ class _FakeDevice:
         import scipy.sparse as sp
         return sp.csr_matrix(X)
 
+    def host_arrays_pinned(self, X):
+        return False
+
+    def upload_csr_selected(self, X, col_map, row_lo=0, row_hi=None):
+        """What chr_host_csr_select_* deliver: rows [row_lo, row_hi), the columns with col_map >= 0, renumbered."""
+        import scipy.sparse as sp
+        X = sp.csr_matrix(X)[row_lo:row_hi]
+        cols = np.flatnonzero(col_map >= 0)
+        assert np.array_equal(col_map[cols], np.arange(len(cols)))
+        return X[:, cols]
+
+    def lattice_plan(self, xy, nbr, bbox=None):
+        return None
+
     def to_host(self, t):
         return t.cpu().numpy()
 
