@@ -31,10 +31,20 @@ def shard_range(n_items: int, rank: int | None = None, size: int | None = None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _host_backend(t: torch.Tensor) -> bool:
+    """gloo exchanges device tensors through the host only for some collectives (no all_gather): stage them ourselves."""
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks (per-spot totals, partial Grams, column sums)."""
     if world()[1] > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if _host_backend(t):
+            h = t.cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.SUM)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 
@@ -47,6 +57,8 @@ def allgather_ragged(t: torch.Tensor, n_total: int | None = None) -> torch.Tenso
     rank, size = world()
     if size == 1:
         return t
+    if _host_backend(t):
+        return allgather_ragged(t.cpu(), n_total).to(t.device)
     n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
     lens = [torch.zeros_like(n_local) for _ in range(size)]
     dist.all_gather(lens, n_local)
