@@ -207,6 +207,101 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     return out
 
 
+def svg_stage_multi(samples, min_spots: float, neighbors: int, geary: bool):
+    """``detect_svgs``'s device part for SEVERAL samples that share one gene list, in one Moran launch
+    (``chr_moran_blockdiag_f32``): what the per-sample loop of ``integrate_adatas`` computes
+    (/root/reference/chrysalis/utils.py:210-212 calling core.py:53-76 once per sample) - every sample keeps its own gene
+    filter, its own ``normalize_total`` target, its own kNN graph, mean and variance; W over the stacked spots is block
+    diagonal.  ``samples``: list of ``(X, spatial, already_log1p)``.  Returns a list of ``(keep, I, C)`` host arrays per
+    sample, as ``svg_stage`` does.
+
+    Under an initialised ``torch.distributed`` group the samples are dealt out to the ranks (sample b -> rank b mod size,
+    one sample per GPU for an 8-sample cohort on 8 GPUs), each rank scores its samples in one launch, and the per-sample
+    results (8 bytes per gene) are all-gathered."""
+    B = len(samples)
+    g = samples[0][0].shape[1]
+    assert all(s[0].shape[1] == g for s in samples), "svg_stage_multi: the samples must share one gene list"
+    rank, size = dd.world()
+    mine = [b for b in range(B) if b % size == rank]
+    results = {}
+    if mine:
+        block_rows, block_n, pad_rows = dv.block_layout([samples[b][0].shape[0] for b in mine])
+        n_rows = int(block_rows[-1])
+        csrs, keeps, scales, row_maps = [], [], [], []
+        nbr_all = torch.arange(n_rows, dtype=torch.int32, device="cuda")[:, None].repeat(1, neighbors)   # padding rows list themselves
+        for t, b in enumerate(mine):
+            X, spatial, logged = samples[b]
+            n_b = X.shape[0]
+            csr = dv.upload_csr(X)
+            keep = dv.csr_gene_nnz(csr) >= int(n_b * min_spots)                      # core.py:53 on this sample
+            gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1,
+                                   torch.full((g,), -1, dtype=torch.int32, device=keep.device))
+            scales.append(None if logged else dv.median_scale(dv.csr_spot_totals(csr, gene_col)))   # core.py:55-57
+            pts = np.array(spatial, dtype=np.float64, copy=True)
+            pts[:, 1] = pts[:, 1] * -1                                                # core.py:61-62
+            xy = dv.to_device(pts, torch.float64)
+            bbox = dv.spatial_bbox(xy)
+            order = dv.spatial_order(xy, bbox)
+            rank_of = torch.empty_like(order)
+            rank_of[order] = torch.arange(n_b, device=order.device)
+            nbr = rank_of.to(torch.int32)[dv.knn_build(xy, neighbors, bbox)[order].long()]   # core.py:64-65
+            r0 = int(block_rows[t])
+            nbr_all[r0:r0 + n_b] = nbr + r0
+            csrs.append(csr); keeps.append(keep); row_maps.append(rank_of + r0)
+        union = torch.stack(keeps).any(0)
+        col_u = torch.where(union, torch.cumsum(union.to(torch.int32), 0, dtype=torch.int32) - 1,
+                            torch.full((g,), -1, dtype=torch.int32, device=union.device))
+        g_u = int(union.sum().item())
+        if g_u > 0:
+            dense = torch.zeros((n_rows, dv.dense_ld(g_u)), dtype=torch.float32, device="cuda")
+            for csr, scale, rows, (_, _, logged) in zip(csrs, scales, row_maps, [samples[b] for b in mine]):
+                dv.csr_densify(csr, col_u, g_u, scale, rows, apply_log1p=not logged, out=dense)    # core.py:59 per sample
+            plan = dv.moran_plan(nbr_all.contiguous())
+            I, C = dv.moran_blockdiag(dense, plan, block_rows, block_n, torch.from_numpy(pad_rows).cuda(), g_u, geary=geary)
+        for t, b in enumerate(mine):
+            pos = col_u[keeps[t]].long()                                              # this sample's kept genes inside the union
+            I_b = I[t][pos].cpu().numpy() if g_u > 0 else np.empty(0)
+            C_b = (C[t][pos].cpu().numpy() if g_u > 0 else np.empty(0)) if geary else None
+            results[b] = (keeps[t].cpu().numpy(), I_b, C_b)
+    if size > 1:
+        for part in dd.allgather_objects(results):
+            results.update(part)
+    return [results[b] for b in range(B)]
+
+
+def _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary):
+    """The tail of ``detect_svgs`` (core.py:78-92) for one AnnData given the scored genes."""
+    names = _make_unique(pd.Index(adata.var_names)[keep])
+    moran_df = pd.DataFrame(data=I, index=names, columns=["Moran's I"])
+    moran_df = moran_df.sort_values(ascending=False, by="Moran's I")
+    adata.var["Moran's I"] = moran_df["Moran's I"]
+    if geary:
+        geary_df = pd.DataFrame(data=C, index=names, columns=["Geary's C"])
+        geary_df = geary_df.sort_values(ascending=False, by="Geary's C")
+        adata.var["Geary's C"] = geary_df["Geary's C"]
+    if len(moran_df[:top_svg]) < len(moran_df[moran_df["Moran's I"] > min_morans]):
+        chosen = set(moran_df[:top_svg].index)
+    else:
+        chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
+    adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]
+
+
+def detect_svgs_multi(adatas, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
+                      geary: bool = False):
+    """``detect_svgs`` for a list of samples: same arguments, same per-sample results and ``.var`` fields as calling
+    ``detect_svgs`` on every element (what ``integrate_adatas(..., calculate_svgs=True)`` does, utils.py:210-212), but
+    samples that share a gene list are scored together in one block-diagonal launch."""
+    assert 0 < min_spots < 1
+    groups = {}
+    for i, ad in enumerate(adatas):
+        groups.setdefault(tuple(ad.var_names), []).append(i)
+    for idx in groups.values():
+        res = svg_stage_multi([(adatas[i].X, adatas[i].obsm['spatial'], "log1p" in adatas[i].uns_keys()) for i in idx],
+                              min_spots, neighbors, geary)
+        for i, (keep, I, C) in zip(idx, res):
+            _write_svg_fields(adatas[i], keep, I, C, top_svg, min_morans, geary)
+
+
 def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
                 geary: bool = False):
     """
@@ -419,27 +514,26 @@ def _furthest_sum(X: np.ndarray, n_archetypes: int, rs: np.random.RandomState) -
     return np.array(picks[:n_archetypes], dtype=np.int64)
 
 
-def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int = 3, tol: float = 0.001,
-             random_state: int = 42, init_rows=None):
-    """Device part of ``aa``: ``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit(X)``
-    (core.py:186-191).  ``init_rows``: optional list of n_init index arrays (matched initialisation).
-    Returns a dict with alphas (N, A), archetypes (A, d), rss, n_iter and the initial rows used."""
+def _aa_upload(X: np.ndarray) -> torch.Tensor:
+    """Embedding -> float64 device tensor.  numpy upcasts the float32 scores to float64 inside archetypes; here the (exact)
+    widening happens on the device, so half the bytes cross PCIe and the host never builds the float64 copy."""
     X = np.asarray(X)
-    n, d = X.shape
+    if X.dtype == np.float32:
+        return dv.to_device(np.ascontiguousarray(X), torch.float32).to(torch.float64)
+    return dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
+
+
+def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: int, tol: float, random_state: int, init_rows=None):
+    """``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit`` on a device-resident embedding."""
+    n, d = Xd.shape
     if n_archetypes > MAX_ARCHETYPES or d > MAX_AA_DIMS:
         raise ValueError(f"aa: this implementation supports n_archetypes <= {MAX_ARCHETYPES} and <= {MAX_AA_DIMS} embedding "
                          f"dimensions (got n_archetypes={n_archetypes}, n_pcs={d})")
     if not n_archetypes < n:
         raise ValueError(f"aa: n_archetypes={n_archetypes} must be smaller than the number of observations ({n})")
     rs = np.random.RandomState(random_state)
-    # numpy upcasts the float32 scores to float64 inside archetypes; here the (exact) widening happens on the device,
-    # so half the bytes cross PCIe and the host never builds the float64 copy
-    if X.dtype == np.float32:
-        Xd = dv.to_device(np.ascontiguousarray(X), torch.float32).to(torch.float64)
-    else:
-        Xd = dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
     # initial archetypes of every restart first: the RNG stream (one randint + one choice per restart) does not depend
-    # on the fits, so the restarts can then run side by side
+    # on the fits
     used = []
     for r in range(n_init):
         if init_rows is not None:
@@ -460,16 +554,53 @@ def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int 
             rss_prev = rss
         return {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
 
-    # (running the restarts on separate host threads / CUDA streams was measured: 0.52 s instead of 0.58 s at cfg4 once
-    # the per-stream allocator pools are warm, 0.99 s on a first call - not worth the threads)
-    fits = [fit_restart(rows) for rows in used]
     best = None
-    for f in fits:                                              # first restart with the smallest RSS, as a sequential loop keeps it
+    for rows in used:                                           # first restart with the smallest RSS, as a sequential loop keeps it
+        f = fit_restart(rows)
         if best is None or f["rss"] < best["rss"]:
             best = f
-    out = {"alphas": dv.to_host(best["alphas"]), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
-           "n_iter": best["n_iter"], "init_rows": used}
-    return out
+    best["init_rows"] = used
+    return best
+
+
+def aa_stage(X: np.ndarray, n_archetypes: int, max_iter: int = 200, n_init: int = 3, tol: float = 0.001,
+             random_state: int = 42, init_rows=None):
+    """Device part of ``aa``: ``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit(X)``
+    (core.py:186-191).  ``init_rows``: optional list of n_init index arrays (matched initialisation).
+    Returns a dict with alphas (N, A), archetypes (A, d), rss, n_iter and the initial rows used."""
+    best = _aa_fit_device(_aa_upload(X), n_archetypes, max_iter, n_init, tol, random_state, init_rows)
+    return {"alphas": dv.to_host(best["alphas"]), "archetypes": best["archetypes"].cpu().numpy(), "rss": best["rss"],
+            "n_iter": best["n_iter"], "init_rows": best["init_rows"]}
+
+
+def aa_sweep(X: np.ndarray, archetype_counts, max_iter: int = 10, n_init: int = 3, tol: float = 0.001, random_state: int = 42,
+             workers: int = 4):
+    """The fits of ``estimate_compartments`` (/root/reference/chrysalis/utils.py:123-130: one ``arch.AA(n_archetypes=a,
+    n_init=3, max_iter, tol=0.001, random_state=42).fit`` per archetype count) as CONCURRENT device fits: the embedding is
+    uploaded once, ``workers`` host threads drive one CUDA stream each (a fit of a few thousand spots is a chain of short
+    launches that leaves the GPU mostly idle on its own).  Returns {a: {"rss", "entropy" (per spot, natural log), "n_iter"}}."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    Xd = _aa_upload(X)
+    counts = [int(a) for a in archetype_counts]
+    device = Xd.device
+    torch.cuda.synchronize(device)
+
+    def one(a):
+        torch.cuda.set_device(device)
+        stream = torch.cuda.Stream(device=device)
+        with torch.cuda.stream(stream):
+            f = _aa_fit_device(Xd, a, max_iter, n_init, tol, random_state)
+            p = f["alphas"] / f["alphas"].sum(1, keepdim=True)          # scipy.stats.entropy normalises, then -sum p log p
+            ent = -(torch.where(p > 0, p * torch.log(p), torch.zeros_like(p))).sum(1)
+            out = {"rss": f["rss"], "entropy": ent.cpu().numpy(), "n_iter": f["n_iter"]}
+        stream.synchronize()
+        return a, out
+
+    if workers <= 1 or len(counts) <= 1:
+        return dict(one(a) for a in counts)
+    with ThreadPoolExecutor(max_workers=min(workers, len(counts))) as pool:
+        return dict(pool.map(one, counts))
 
 
 def aa(adata, n_archetypes: int = 8, pca_key: str = None, n_pcs: int = None, max_iter: int = 200):

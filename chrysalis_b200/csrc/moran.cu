@@ -22,6 +22,8 @@
 // with S1 = sum x', S2 = sum x'^2, SW = x''A x', SC = 1'A x' = sum_j indeg_j x'_j
 // carry no cancellation; partial sums are fp32 over the 16 spots a warp visits in two tiles, then fp32
 // (shared memory) over the CTA's spot range, then fp64 across warps and CTAs in fixed order.
+#include <vector>
+
 #include "async.cuh"
 #include "moran.cuh"
 
@@ -46,6 +48,32 @@ moran_pilot_kernel(const float* __restrict__ X, int64_t n, int64_t ld, int64_t n
             const int64_t i = (int64_t)t * n / ns;
             s += __ldg(X + i * ld + col);
         }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && col < ncol) {
+        float a = 0.f;
+#pragma unroll
+        for (int y = 0; y < kPilotSplit; ++y) a += red[y][tx];
+        pilot[col] = a / (float)ns;
+    }
+}
+
+// same per row block (block-diagonal input, blockIdx.y = block): a fixed sample of the block's REAL rows, so every sample
+// is shifted by a value near its own mean and the padding rows never enter
+__global__ void __launch_bounds__(64 * kPilotSplit)
+moran_pilot_blocks_kernel(const float* __restrict__ X, int64_t ld, int64_t ncol, const int64_t* __restrict__ block_rows,
+                          const int64_t* __restrict__ block_n, int64_t gpad, float* __restrict__ pilot_base) {
+    __shared__ float red[kPilotSplit][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int64_t col = (int64_t)blockIdx.x * 64 + tx;
+    const int64_t r0 = block_rows[blockIdx.y], nb = block_n[blockIdx.y];
+    const int ns = nb < kPilotSample ? (int)nb : kPilotSample;
+    float* __restrict__ pilot = pilot_base + (int64_t)blockIdx.y * gpad;
+    float s = 0.f;
+    if (col < ncol) {
+#pragma unroll 8
+        for (int t = ty; t < ns; t += kPilotSplit) s += __ldg(X + (r0 + (int64_t)t * nb / ns) * ld + col);
     }
     red[ty][tx] = s;
     __syncthreads();
@@ -339,8 +367,10 @@ template <bool GEARY, bool SHIFT, bool MAPPED>
 __global__ void __launch_bounds__(kTileThreads, 1)
 moran_tile_kernel(const float* __restrict__ X, int n, uint32_t row_bytes, int ncol, const int32_t* __restrict__ row_map,
                   const int32_t* __restrict__ plan_off, const int4* __restrict__ plan_rec, int buf_units, int nstages, int tiles_per_cta,
-                  const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
+                  const float* __restrict__ pilot_base, const int32_t* __restrict__ cta_block, double* __restrict__ part, int64_t gpad) {
     constexpr int NST = GEARY ? 5 : 4;
+    // block-diagonal input: every row block (sample) has its own shift vector, the CTA takes its block's
+    const float* __restrict__ pilot = pilot_base + (cta_block ? (int64_t)__ldg(cta_block + blockIdx.y) * gpad : 0);
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     uint32_t smem0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;            // everything below is addressed in the shared window
     asm volatile("" : "+r"(smem0));                                    // keep it in a register (do not recompute the window base in the loop)
@@ -688,6 +718,52 @@ moran_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t gpad,
     }
 }
 
+// block-diagonal W (one block per sample): the partials of the CTAs of block b, which cover whole blocks only, are summed
+// per block; every block has its own n, mean and z'z - one Moran's I / Geary's C per (block, gene).
+__global__ void __launch_bounds__(64 * kFinSplit)
+moran_finalize_blocks_kernel(const double* __restrict__ part, const int32_t* __restrict__ block_split, const int64_t* __restrict__ block_n,
+                             int64_t gpad, int64_t g, int k, bool geary, double* __restrict__ out_I, double* __restrict__ out_C) {
+    __shared__ double red[kFinSplit][kNStat][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int64_t col = (int64_t)blockIdx.x * 64 + tx;
+    const int b = blockIdx.y;
+    const int s0 = block_split[b], s1 = block_split[b + 1];
+    const int ns = geary ? kNStat : kNStat - 1;
+    double S[kNStat] = {0, 0, 0, 0, 0};
+    if (col < g)
+        for (int sp = s0 + ty; sp < s1; sp += kFinSplit)
+            for (int st = 0; st < ns; ++st) S[st] += part[((int64_t)sp * kNStat + st) * gpad + col];
+    for (int st = 0; st < kNStat; ++st) red[ty][st][tx] = S[st];
+    __syncthreads();
+    if (ty != 0 || col >= g) return;
+    for (int st = 0; st < kNStat; ++st) {
+        double a = 0.0;
+        for (int y = 0; y < kFinSplit; ++y) a += red[y][st][tx];
+        S[st] = a;
+    }
+    const double dn = (double)block_n[b], dk = (double)k;
+    S[3] += dk * S[0];                                            // the tile kernel accumulates the (indeg - k) parts only
+    S[4] += dk * S[1];
+    const double m = S[0] / dn;
+    const double zz = S[1] - dn * m * m;
+    const double zwz = (S[2] - m * (dk * S[0] + S[3]) + m * m * dn * dk) / dk;
+    out_I[(int64_t)b * g + col] = zwz / zz;
+    if (geary && out_C) out_C[(int64_t)b * g + col] = (dn - 1.0) * ((dk * S[1] + S[4] - 2.0 * S[2]) / dk) / (2.0 * dn * zz);
+}
+
+// padding rows of a block take their block's pilot value: exactly neutral after the shift
+__global__ void moran_fill_rows_kernel(float* __restrict__ X, int64_t ld, int64_t ncol4, const int32_t* __restrict__ rows, int64_t n_rows,
+                                       const int64_t* __restrict__ block_rows, int n_blocks, int64_t gpad, const float* __restrict__ pilot_base) {
+    const int64_t c4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= ncol4) return;
+    for (int64_t a = blockIdx.y; a < n_rows; a += gridDim.y) {
+        const int64_t r = rows[a];
+        int b = 0;
+        while (b + 1 < n_blocks && block_rows[b + 1] <= r) ++b;
+        *reinterpret_cast<float4*>(X + r * ld + 4 * c4) = *reinterpret_cast<const float4*>(pilot_base + (int64_t)b * gpad + 4 * c4);
+    }
+}
+
 // shared with moran_lattice.cu: `part` is [nsplit][kNStat][gpad] in the tile kernel's convention (x'Ax', (indeg - k) parts)
 int launch_moran_finalize(const double* part, int nsplit, int64_t gpad, int64_t n_genes, int64_t n_spots, int k, const float* pilot,
                           bool geary, double* out_I, double* out_C, double* out_stats, cudaStream_t st) {
@@ -712,9 +788,9 @@ struct MoranWs {
     size_t pilot_off, part_off, total;
 };
 
-static MoranWs moran_ws(int64_t n, int64_t ncol, bool tile) {
+static MoranWs moran_ws(int64_t n, int64_t ncol, bool tile, int tiles_per_cta = 0) {
     MoranWs p;
-    const int64_t spots_per_cta = tile ? (int64_t)tile_tiles_per_cta(n) * kTileSpots : kV2SpotsPerCta;
+    const int64_t spots_per_cta = tile ? (int64_t)(tiles_per_cta ? tiles_per_cta : tile_tiles_per_cta(n)) * kTileSpots : kV2SpotsPerCta;
     p.nsplit = (int)ceil_div<int64_t>(n, spots_per_cta);
     p.ntile = (int)ceil_div<int64_t>(ncol, kGeneTile);
     p.gpad = (int64_t)p.ntile * kGeneTile;
@@ -801,7 +877,7 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
         auto kern = moran_tile_kernel<GG, SH, MP>;                                                                 \
         CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
         kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_spots, rb, (int)ncol, row_map, plan_off, plan_rec, plan_chunk_units, nstages, \
-                                               tpc, pilot, part, p.gpad);                                          \
+                                               tpc, pilot, nullptr, part, p.gpad);                                 \
     } while (0)
         if (geary && preshifted) CHR_TILE(true, false);
         else if (geary) CHR_TILE(true, true);
@@ -840,6 +916,114 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
 
     moran_finalize_kernel<<<(unsigned)ceil_div<int64_t>(n_genes, 64), 64 * kFinSplit, 0, st>>>(
         part, p.nsplit, p.gpad, n_genes, n_spots, k, pilot, geary, tile, out_I, out_C, out_stats);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// scratch of the block-diagonal call behind the tile kernel's workspace: per-block shift vectors + three small tables
+static size_t blockdiag_extra_bytes(int64_t gpad, int n_blocks, int nsplit) {
+    return chr::round_up<size_t>((size_t)n_blocks * gpad * sizeof(float), 256) + chr::round_up<size_t>((size_t)(2 * n_blocks + 1) * 8, 256) +
+           chr::round_up<size_t>((size_t)(n_blocks + 1 + nsplit) * 4, 256);
+}
+
+size_t chr_moran_blockdiag_workspace_bytes(int64_t n_rows, int64_t n_genes, int n_blocks) {
+    if (n_rows <= 0 || n_genes <= 0 || n_blocks <= 0) return 256;
+    const int64_t ncol = chr::round_up<int64_t>(n_genes, 4);
+    chr::MoranWs p = chr::moran_ws(n_rows, ncol, true, CHR_BLOCK_ALIGN_ROWS / chr::kTileSpots);
+    return chr::round_up<size_t>(p.total, 256) + blockdiag_extra_bytes(p.gpad, n_blocks, p.nsplit) + 1024;
+}
+
+int chr_moran_blockdiag_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int k, const void* plan, int plan_chunk_units,
+                            const int64_t* block_rows_host, const int64_t* block_n_host, int n_blocks, const int32_t* pad_rows,
+                            int64_t n_pad, unsigned flags, double* out_I, double* out_C, void* workspace, size_t workspace_bytes,
+                            chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int kTpc = CHR_BLOCK_ALIGN_ROWS / kTileSpots;           // tiles per CTA: a CTA never straddles two blocks
+    static_assert(kTpc * kTileSpots == CHR_BLOCK_ALIGN_ROWS, "block alignment is a whole number of tiles");
+    CHR_REQUIRE(X && plan && block_rows_host && block_n_host && out_I && workspace, "chr_moran_blockdiag_f32: null pointer argument");
+    CHR_REQUIRE(n_rows > 1 && n_genes > 0 && k > 0 && n_blocks > 0 && n_blocks < 65536, "chr_moran_blockdiag_f32: bad sizes");
+    CHR_REQUIRE(ld >= n_genes && ld % 4 == 0 && ((uintptr_t)X & 15) == 0, "chr_moran_blockdiag_f32: X must be 16-byte aligned, ld %% 4 == 0, ld >= n_genes");
+    CHR_REQUIRE(n_rows < (1LL << 31) && ld * 4 < (1LL << 32), "chr_moran_blockdiag_f32: needs n_rows < 2^31, row bytes < 2^32");
+    CHR_REQUIRE(((uintptr_t)plan & 255) == 0 && plan_chunk_units > 0, "chr_moran_blockdiag_f32: bad plan (build it with chr_moran_plan_build)");
+    CHR_REQUIRE(n_pad == 0 || pad_rows, "chr_moran_blockdiag_f32: pad_rows missing");
+    CHR_REQUIRE(block_rows_host[0] == 0 && block_rows_host[n_blocks] == n_rows, "chr_moran_blockdiag_f32: block_rows must run from 0 to n_rows");
+    const bool geary = flags & CHR_FLAG_GEARY, timing = flags & CHR_FLAG_TIMING;
+    CHR_REQUIRE(!geary || out_C, "chr_moran_blockdiag_f32: CHR_FLAG_GEARY needs out_C");
+    const int64_t ncol = round_up<int64_t>(n_genes, 4);
+    MoranWs p = moran_ws(n_rows, ncol, true, kTpc);
+    // host tables: [block_n | block_rows] (int64) and [first split of every block | block of every CTA row range] (int32)
+    std::vector<int64_t> tab64((size_t)2 * n_blocks + 1);
+    std::vector<int32_t> tab32((size_t)n_blocks + 1 + p.nsplit);
+    for (int b = 0; b < n_blocks; ++b) {
+        const int64_t r0 = block_rows_host[b], r1 = block_rows_host[b + 1];
+        CHR_REQUIRE(r1 > r0 && r0 % CHR_BLOCK_ALIGN_ROWS == 0 && (r1 % CHR_BLOCK_ALIGN_ROWS == 0 || b == n_blocks - 1),
+                    "chr_moran_blockdiag_f32: block %d must start and end on a multiple of %d rows", b, CHR_BLOCK_ALIGN_ROWS);
+        CHR_REQUIRE(block_n_host[b] > 1 && block_n_host[b] <= r1 - r0, "chr_moran_blockdiag_f32: block %d holds %lld spots in %lld rows", b,
+                    (long long)block_n_host[b], (long long)(r1 - r0));
+        tab64[b] = block_n_host[b];
+        tab64[n_blocks + b] = r0;
+        tab32[b] = (int32_t)(r0 / CHR_BLOCK_ALIGN_ROWS);
+        for (int64_t sp = r0 / CHR_BLOCK_ALIGN_ROWS; sp < ceil_div<int64_t>(r1, CHR_BLOCK_ALIGN_ROWS); ++sp) tab32[n_blocks + 1 + sp] = b;
+    }
+    tab64[2 * n_blocks] = n_rows;
+    tab32[n_blocks] = p.nsplit;
+    const size_t base = round_up<size_t>(p.total, 256);
+    CHR_REQUIRE(workspace_bytes >= base + blockdiag_extra_bytes(p.gpad, n_blocks, p.nsplit) + 256, "chr_moran_blockdiag_f32: workspace too small");
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double* part = (double*)(ws + p.part_off);
+    float* pilot = (float*)(ws + base);                               // [n_blocks][gpad]: one shift vector per block
+    int64_t* tab64_dev = (int64_t*)((char*)pilot + round_up<size_t>((size_t)n_blocks * p.gpad * sizeof(float), 256));
+    int32_t* tab32_dev = (int32_t*)((char*)tab64_dev + round_up<size_t>(tab64.size() * 8, 256));
+    const int64_t* block_n_dev = tab64_dev;
+    const int64_t* block_rows_dev = tab64_dev + n_blocks;
+    const int32_t* split_dev = tab32_dev;
+    const int32_t* cta_block_dev = tab32_dev + n_blocks + 1;
+    CHR_CUDA(cudaMemcpyAsync(tab64_dev, tab64.data(), tab64.size() * 8, cudaMemcpyHostToDevice, st));
+    CHR_CUDA(cudaMemcpyAsync(tab32_dev, tab32.data(), tab32.size() * 4, cudaMemcpyHostToDevice, st));
+    CHR_CUDA(cudaStreamSynchronize(st));                              // the host tables live on this stack frame
+
+    // every block is shifted by the mean of a fixed sample of ITS real rows (the statistics are per block, and samples of a
+    // cohort can sit at different expression levels); the padding rows take their block's shift value
+    CHR_CUDA(cudaMemsetAsync(pilot, 0, (size_t)n_blocks * p.gpad * sizeof(float), st));
+    moran_pilot_blocks_kernel<<<dim3((unsigned)ceil_div<int64_t>(ncol, 64), (unsigned)n_blocks), 64 * kPilotSplit, 0, st>>>(
+        X, ld, ncol, block_rows_dev, block_n_dev, p.gpad, pilot);
+    CHR_LAUNCH_CHECK();
+    if (n_pad > 0) {
+        dim3 gf((unsigned)ceil_div<int64_t>(ncol / 4, 128), (unsigned)(n_pad < 1024 ? n_pad : 1024));
+        moran_fill_rows_kernel<<<gf, 128, 0, st>>>(X, ld, ncol / 4, pad_rows, n_pad, block_rows_dev, n_blocks, p.gpad, pilot);
+        CHR_LAUNCH_CHECK();
+    }
+    int nstages = kTileMaxStages;
+    auto tile_smem = [&](int ns) {
+        return (size_t)1024 + (size_t)ns * tile_stage_bytes(plan_chunk_units) + 16 * kTileMaxStages + (size_t)(geary ? 5 : 4) * kTileWarps * 32 * 16;
+    };
+    if (tile_smem(nstages) > 227 * 1024) nstages = 2;
+    const size_t smem = tile_smem(nstages);
+    CHR_REQUIRE(smem <= 227 * 1024, "chr_moran_blockdiag_f32: neighbour lists too long for the staged plan (%zu B of shared memory)", smem);
+    const int64_t nquads = (n_rows + 3) / 4;
+    const char* pb = (const char*)plan;
+    const int32_t* plan_off = (const int32_t*)(pb + kPlanHeaderBytes);
+    const int4* plan_rec = (const int4*)(pb + kPlanHeaderBytes + round_up<size_t>((size_t)(nquads + 1 + kPlanOffPad) * 4, 256));
+    dim3 grid((unsigned)p.ntile, (unsigned)p.nsplit);
+    const uint32_t rb = (uint32_t)(ld * 4);
+    timer_begin(CHR_FAMILY_MORAN, timing, st);
+    if (geary) {
+        auto kern = moran_tile_kernel<true, true, false>;
+        CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_rows, rb, (int)ncol, nullptr, plan_off, plan_rec, plan_chunk_units, nstages, kTpc, pilot,
+                                               cta_block_dev, part, p.gpad);
+    } else {
+        auto kern = moran_tile_kernel<false, true, false>;
+        CHR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTileThreads, smem, st>>>(X, (int)n_rows, rb, (int)ncol, nullptr, plan_off, plan_rec, plan_chunk_units, nstages, kTpc, pilot,
+                                               cta_block_dev, part, p.gpad);
+    }
+    timer_end(CHR_FAMILY_MORAN, timing, st);
+    CHR_LAUNCH_CHECK();
+    moran_finalize_blocks_kernel<<<dim3((unsigned)ceil_div<int64_t>(n_genes, 64), (unsigned)n_blocks), 64 * kFinSplit, 0, st>>>(
+        part, split_dev, block_n_dev, p.gpad, n_genes, k, geary, out_I, out_C);
     CHR_LAUNCH_CHECK();
     return 0;
 }

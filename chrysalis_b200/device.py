@@ -384,6 +384,44 @@ def moran_dense(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, 
     return out_I, out_C, stats
 
 
+# ---- K3/K4 with a block-diagonal W (several samples, one launch) ---------------------------------------------------
+
+BLOCK_ALIGN_ROWS = 448      # CHR_BLOCK_ALIGN_ROWS (include/chrysalis_b200.h): blocks start on whole CTA row ranges
+
+
+def block_layout(sizes):
+    """Row blocks of a multi-sample matrix: block b holds ``sizes[b]`` spots followed by padding up to the next multiple of
+    ``BLOCK_ALIGN_ROWS``.  Returns (block_rows int64 [B + 1], block_n int64 [B], pad_rows int32 - all host arrays)."""
+    sizes = np.asarray(list(sizes), dtype=np.int64)
+    padded = (sizes + BLOCK_ALIGN_ROWS - 1) // BLOCK_ALIGN_ROWS * BLOCK_ALIGN_ROWS
+    block_rows = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+    pad = [np.arange(block_rows[b] + sizes[b], block_rows[b + 1]) for b in range(len(sizes))]
+    return block_rows, sizes, (np.concatenate(pad) if pad else np.empty(0)).astype(np.int32)
+
+
+def moran_blockdiag(X: torch.Tensor, plan: MoranPlan, block_rows: np.ndarray, block_n: np.ndarray, pad_rows: torch.Tensor,
+                    n_genes: int | None = None, geary: bool = False, timing: bool = False):
+    """Moran's I (and Geary's C) per (block, gene) of the dense [n_rows, ld] float32 matrix ``X`` whose rows are laid out
+    by ``block_layout`` and whose W (``plan``) is block diagonal.  Returns (I [B, g], C [B, g] or None) float64 device
+    tensors.  The padding rows of ``X`` are overwritten."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1 and plan is not None
+    n_rows, ld = X.shape[0], X.stride(0)
+    g = X.shape[1] if n_genes is None else n_genes
+    B = len(block_n)
+    block_rows = np.ascontiguousarray(block_rows, dtype=np.int64)
+    block_n = np.ascontiguousarray(block_n, dtype=np.int64)
+    assert block_rows.shape == (B + 1,) and int(block_rows[-1]) == n_rows == plan.n
+    flags = (_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0)
+    ws_bytes = _lib.query("chr_moran_blockdiag_workspace_bytes", n_rows, g, B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    out_I = torch.empty((B, g), dtype=torch.float64, device=X.device)
+    out_C = torch.empty((B, g), dtype=torch.float64, device=X.device) if geary else None
+    _lib.call("chr_moran_blockdiag_f32", _ptr(X), n_rows, g, ld, plan.k, _ptr(plan.buf), plan.chunk_units, block_rows.ctypes.data,
+              block_n.ctypes.data, B, _ptr(pad_rows) if pad_rows.numel() else 0, pad_rows.numel(), flags, _ptr(out_I), _ptr(out_C),
+              _ptr(ws), ws_bytes, _stream())
+    return out_I, out_C
+
+
 # ---- K3/K4 on a square lattice: layout + corrections for the stencil kernel ----------------------------------------
 
 LATTICE_BAND_ROWS = 60      # CHR_LATTICE_BAND_ROWS (include/chrysalis_b200.h)

@@ -135,6 +135,22 @@ int chr_moran_dense_f32(const float* X, int64_t n_spots, int64_t n_genes, int64_
                         double* out_stats, void* workspace, size_t workspace_bytes,
                         chr_stream_t stream);
 
+/* ---- K3/K4 with a block-diagonal W: several samples in one launch ----------------------------
+ * replaces  the per-sample  detect_svgs(ad, **kwargs)  loop of  chrysalis.integrate_adatas
+ *           (/root/reference/chrysalis/utils.py:210-218): Moran's I is computed PER SAMPLE with that sample's own W,
+ *           mean and z'z; here the samples are row blocks of one matrix, W is block diagonal, one launch scores all.
+ * X: [n_rows][ld] float32; block b owns rows [block_rows[b], block_rows[b+1]), starts on a multiple of
+ *    CHR_BLOCK_ALIGN_ROWS and holds block_n[b] spots followed by padding rows (listed in pad_rows; the call overwrites them
+ *    with the per-gene shift value).  plan: chr_moran_plan_build of the block-diagonal neighbour lists over all n_rows rows
+ *    (padding rows list themselves k times).  block_rows_host / block_n_host: HOST int64 [n_blocks + 1] / [n_blocks].
+ * out_I / out_C: [n_blocks][n_genes] float64.  Synchronises the stream once (two small host arrays are uploaded). */
+#define CHR_BLOCK_ALIGN_ROWS 448
+size_t chr_moran_blockdiag_workspace_bytes(int64_t n_rows, int64_t n_genes, int n_blocks);
+int chr_moran_blockdiag_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int k, const void* plan,
+                            int plan_chunk_units, const int64_t* block_rows_host, const int64_t* block_n_host,
+                            int n_blocks, const int32_t* pad_rows, int64_t n_pad, unsigned flags, double* out_I,
+                            double* out_C, void* workspace, size_t workspace_bytes, chr_stream_t stream);
+
 /* ---- K3/K4 on an exact square lattice (stencil kernel) -----------------------------------
  * Same statistic, same reference call sites as chr_moran_dense_f32, for spots that sit on a square lattice with the
  * 8-neighbour kNN graph (core.py:64-65 with neighbors=8: Visium HD / Stereo-seq bins).  The kNN adjacency is split as

@@ -9,7 +9,7 @@ from conftest import golden_csr
 
 
 def _oracle_stage(z):
-    def stage(X, spatial, min_spots, neighbors, geary, already_log1p, timing=False):
+    def stage(X, spatial, min_spots, neighbors, geary, already_log1p, timing=False, **kw):
         m = z["gene_mask"]
         return m, z["morans"][m], (z["geary"][m] if geary else None)
     return stage
@@ -105,11 +105,14 @@ def test_integrate_adatas_union_and_varm(golden_hex, golden_random, monkeypatch)
 
     it = iter(refs)
 
-    def stage(X, spatial, min_spots, neighbors, geary, already_log1p, timing=False):
-        r = next(it)
-        m = r["gene_mask"]
-        return m, r["morans"][m], None
-    monkeypatch.setattr(core, "svg_stage", stage)
+    def stage(samples, min_spots, neighbors, geary):
+        out = []
+        for _ in samples:                                            # samples with different gene lists arrive in separate calls
+            r = next(it)
+            m = r["gene_mask"]
+            out.append((m, r["morans"][m], None))
+        return out
+    monkeypatch.setattr(core, "svg_stage_multi", stage)
     # each sample keeps its own neighbour count through kwargs of the per-sample call (here the same for both)
     out = ch.integrate_adatas(samples, sample_names=["a", "b"], calculate_svgs=True, top_svg=30, neighbors=6)
     g_common = 297
@@ -134,10 +137,9 @@ def test_estimate_compartments_fields(monkeypatch):
     n = 60
     ad = ch.AnnDataLite(np.zeros((n, 5), np.float32), obsm={"spatial": np.zeros((n, 2)), "chr_X_pca": np.random.default_rng(0).normal(size=(n, 8))})
 
-    def fake_stage(X, a, max_iter=200, **kw):
-        al = np.full((X.shape[0], a), 1.0 / a)
-        return {"alphas": al, "archetypes": np.zeros((a, X.shape[1])), "rss": float(100 - a), "n_iter": max_iter}
-    monkeypatch.setattr(core, "aa_stage", fake_stage)
+    def fake_sweep(X, counts, max_iter=10, **kw):
+        return {a: {"rss": float(100 - a), "entropy": np.full(X.shape[0], np.log(a)), "n_iter": max_iter} for a in counts}
+    monkeypatch.setattr(core, "aa_sweep", fake_sweep)
     ch.estimate_compartments(ad, n_pcs=6, range_archetypes=(3, 7), max_iter=4)
     assert ad.obsm["entropy"].shape == (n, 4)
     assert np.allclose(ad.obsm["entropy"][:, 0], np.log(3))
