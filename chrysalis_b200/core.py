@@ -141,9 +141,9 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         bbox = dv.spatial_bbox(xy)
         nbr0 = dv.knn_build(xy, neighbors, bbox)
         # square lattice with k = 8 (Visium HD / Stereo-seq bins): lattice layout + stencil kernel; otherwise rows in
-        # Hilbert order + the quad plan of W.  (Permutation inference relabels rows, which only the general kernel does.)
+        # Hilbert order + the quad plan of W
         lat = None
-        if neighbors == 8 and not permutations and os.environ.get("CHR_MORAN_LATTICE", "1") != "0":
+        if neighbors == 8 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0":
             lat = dv.lattice_plan(xy, nbr0, bbox)
         if lat is not None:
             rank_of, nbr, plan, n_rows = lat.row_of_spot, None, None, lat.n_rows
@@ -189,9 +189,10 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         # core.py:71-76  the gene loop
         if lat is not None:
             I, C, _ = dv.moran_lattice(dense, lat, n_keep, geary=geary, timing=timing)
+            sim = dv.moran_perm_lattice(dense, lat, n_keep, permutations, seed) if permutations else None
         else:
             I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
-        sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None
+            sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None
     else:
         I = torch.empty(0, dtype=torch.float64, device=keep.device)
         C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None

@@ -444,6 +444,16 @@ class LatticePlan:
     absent: torch.Tensor       # int32 [n_absent]
     pilot_rows: torch.Tensor   # int32 [<= 512]
     lattice_shape: tuple       # (W, H) nodes
+    _maps: tuple | None = None
+
+    def maps(self):
+        """(spot_of_row int32 [n_rows] with -1 for filler rows, row_of_spot int32 [n]) - what the permutation kernel needs."""
+        if self._maps is None:
+            ros = self.row_of_spot.to(torch.int32).contiguous()
+            sor = torch.full((self.n_rows,), -1, dtype=torch.int32, device=ros.device)
+            sor[self.row_of_spot] = torch.arange(self.n, dtype=torch.int32, device=ros.device)
+            self._maps = (sor, ros)
+        return self._maps
 
 
 def lattice_nodes(xy: torch.Tensor, bbox: torch.Tensor, pitch: float):
@@ -567,34 +577,21 @@ def moran_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None
     return out_I, out_C, stats
 
 
-def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, permutations: int = 999,
-                           seed: int | None = None, plan: MoranPlan | None = None):
-    """Permutation inference of ``esda.moran.Moran(y, w, permutations=P)`` for every column of ``X``.
+def perm_seed(seed: int | None) -> int:
+    """64-bit key of the device's counter-based permutations (``csrc/perm.cuh``); ``None`` draws fresh entropy.  torch's and
+    numpy's global RNG states are never touched."""
+    return int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
 
-    Each draw permutes the spots (rows) against a fixed W and is ONE pass of the Moran kernel over the
-    whole matrix (``row_map``), so a draw is shared by all genes; esda draws per gene from NumPy's global
-    RNG, so parity of the simulated quantities is statistical, parity of ``I`` exact.
-    Returns a dict of float64 device tensors [g]: I, p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim.
-    """
-    n = X.shape[0]
-    g = X.shape[1] if n_genes is None else n_genes
-    if plan is None:
-        plan = moran_plan(nbr)
-    if plan is None:
-        raise _lib.ChrysalisNativeError("permutation inference needs the plan-based kernel (k <= 64)")
-    I, _, _ = moran_dense(X, nbr, g, plan=plan)
-    gen = torch.Generator(device=X.device)
-    # a private generator: torch's global RNG state is not touched (seed=None draws fresh entropy for it)
-    gen.manual_seed(int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0] >> 1))
-    larger = torch.zeros(g, dtype=torch.int64, device=X.device)
-    s1 = torch.zeros(g, dtype=torch.float64, device=X.device)
-    s2 = torch.zeros(g, dtype=torch.float64, device=X.device)
-    for _ in range(int(permutations)):
-        perm = torch.randperm(n, device=X.device, generator=gen).to(torch.int32)
-        Ip, _, _ = moran_dense(X, nbr, g, plan=plan, row_map=perm)
-        larger += (Ip >= I)
-        s1 += Ip
-        s2 += Ip * Ip
+
+def perm_row_map(n: int, seed: int, draw: int, device) -> torch.Tensor:
+    """pi_draw as an int32 row map (spot i takes the row of spot pi(i))."""
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    _lib.call("chr_perm_row_map", n, seed & (2 ** 64 - 1), int(draw), _ptr(out), _stream())
+    return out
+
+
+def _perm_summary(I, larger, s1, s2, permutations: int):
+    """esda's simulation summaries from #{I_sim >= I}, sum I_sim, sum I_sim^2 (float64 device tensors over the genes)."""
     P = float(permutations)
     larger = torch.minimum(larger, int(permutations) - larger)                 # esda: two-sided fold
     ei = s1 / P
@@ -604,6 +601,57 @@ def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | No
     p_z = 0.5 * torch.erfc(z.abs() / 2.0 ** 0.5)                               # 1 - Phi(|z|)
     return {"I": I, "p_sim": (larger.to(torch.float64) + 1.0) / (P + 1.0), "EI_sim": ei, "VI_sim": vi, "seI_sim": se,
             "z_sim": z, "p_z_sim": p_z}
+
+
+def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | None = None, permutations: int = 999,
+                           seed: int | None = None, plan: MoranPlan | None = None):
+    """Permutation inference of ``esda.moran.Moran(y, w, permutations=P)`` for every column of ``X`` (general W).
+
+    Each draw permutes the spots (rows) against a fixed W and is ONE pass of the Moran kernel over the
+    whole matrix (``row_map`` = the device's counter-based permutation of that draw), so a draw is shared by all
+    genes; esda draws per gene from NumPy's global RNG, so parity of the simulated quantities is statistical, parity
+    of ``I`` exact.  Returns a dict of float64 device tensors [g]: I, p_sim, EI_sim, VI_sim, seI_sim, z_sim, p_z_sim.
+    """
+    n = X.shape[0]
+    g = X.shape[1] if n_genes is None else n_genes
+    if plan is None:
+        plan = moran_plan(nbr)
+    if plan is None:
+        raise _lib.ChrysalisNativeError("permutation inference needs the plan-based kernel (k <= 64)")
+    I, _, _ = moran_dense(X, nbr, g, plan=plan)
+    key = perm_seed(seed)
+    larger = torch.zeros(g, dtype=torch.int64, device=X.device)
+    s1 = torch.zeros(g, dtype=torch.float64, device=X.device)
+    s2 = torch.zeros(g, dtype=torch.float64, device=X.device)
+    for draw in range(int(permutations)):
+        Ip, _, _ = moran_dense(X, nbr, g, plan=plan, row_map=perm_row_map(n, key, draw, X.device))
+        larger += (Ip >= I)
+        s1 += Ip
+        s2 += Ip * Ip
+    return _perm_summary(I, larger, s1, s2, permutations)
+
+
+def moran_perm_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None, permutations: int = 999,
+                       seed: int | None = None, timing: bool = False):
+    """The same inference on a square lattice (``chr_moran_perm_lattice_f32``): all P draws inside the library, batches of
+    draws per launch, the gene slab reused from L2 across the draws of a batch.  ``X`` in lattice layout."""
+    assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1 and X.shape[0] == plan.n_rows
+    ld = X.stride(0)
+    g = X.shape[1] if n_genes is None else n_genes
+    n_chunks, n_corr = plan.chunks.shape[0], plan.corr.shape[0]
+    sor, ros = plan.maps()
+    ws_bytes = _lib.query("chr_moran_perm_lattice_workspace_bytes", plan.n_rows, g, n_chunks, n_corr, int(permutations))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    I = torch.empty(g, dtype=torch.float64, device=X.device)
+    larger = torch.empty(g, dtype=torch.int64, device=X.device)
+    s1 = torch.empty(g, dtype=torch.float64, device=X.device)
+    s2 = torch.empty(g, dtype=torch.float64, device=X.device)
+    _lib.call("chr_moran_perm_lattice_f32", _ptr(X), plan.n_rows, g, ld, plan.n, plan.k, _ptr(plan.bands), plan.bands.shape[0],
+              _ptr(plan.chunks), n_chunks, _ptr(plan.corr) if n_corr else 0, n_corr, _ptr(plan.absent) if plan.absent.numel() else 0,
+              plan.absent.numel(), _ptr(plan.pilot_rows), plan.pilot_rows.numel(), _ptr(sor), _ptr(ros), int(permutations),
+              perm_seed(seed) & (2 ** 64 - 1), _lib.FLAG_TIMING if timing else 0, _ptr(I), _ptr(larger), _ptr(s1), _ptr(s2), _ptr(ws), ws_bytes,
+              _stream())
+    return _perm_summary(I, larger, s1, s2, permutations)
 
 
 def local_moran(y: torch.Tensor, nbr: torch.Tensor, permutations: int = 999, seed: int = 0):

@@ -173,6 +173,28 @@ int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld,
                           const int32_t* pilot_rows, int n_pilot, unsigned flags, double* out_I, double* out_C,
                           double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream);
 
+/* ---- K3p: permutation inference ------------------------------------------------------------
+ * replaces  esda.moran.Moran(y, w, permutations=P)'s simulation (np.random.permutation(z), P times per gene;
+ *           /root/reference/article/A2_human_lymph_node/morans_i.ipynb:186; core.py:72 hard-codes permutations=0)
+ * Draws are counter-based: pi_draw(i) is a keyed Feistel function of (seed, draw, i) (csrc/perm.cuh), evaluated on the
+ * device; a draw permutes the spots against the fixed W and is shared by all genes.
+ * chr_perm_row_map: pi_draw as a row map for chr_moran_dense_f32 (row_map_out: device int32 [n]).
+ * chr_moran_perm_lattice_f32 (square lattice, k = 8; arguments as chr_moran_lattice_f32 plus the two maps of the lattice
+ *   layout: spot_of_row [n_rows] (-1 for filler rows) and row_of_spot [n_spots]): the observed I and, folded over all
+ *   P draws, out_larger[g] = #{I_sim >= I}, out_sum[g] = sum I_sim, out_sumsq[g] = sum I_sim^2 - all that p_sim,
+ *   EI_sim, VI_sim and z_sim need.  Batches of draws are launched with the gene slab as the slowest grid dimension so a
+ *   slab that fits L2 is read from HBM once per batch. */
+int chr_perm_row_map(int64_t n, uint64_t seed, int draw, int32_t* row_map_out, chr_stream_t stream);
+size_t chr_moran_perm_lattice_workspace_bytes(int64_t n_rows, int64_t n_genes, int n_chunks, int64_t n_corr,
+                                              int permutations);
+int chr_moran_perm_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int64_t n_spots, int k,
+                               const int32_t* bands, int n_bands, const int32_t* chunks, int n_chunks,
+                               const int32_t* corr, int64_t n_corr, const int32_t* absent_rows, int64_t n_absent,
+                               const int32_t* pilot_rows, int n_pilot, const int32_t* spot_of_row,
+                               const int32_t* row_of_spot, int permutations, uint64_t seed, unsigned flags,
+                               double* out_I, int64_t* out_larger, double* out_sum, double* out_sumsq,
+                               void* workspace, size_t workspace_bytes, chr_stream_t stream);
+
 /* ---- Local Moran's I (LISA) ---------------------------------------------------------------
  * replaces  esda.moran.Moran_Local(y, w, transformation='r', permutations=P)
  *           (/root/reference/article/A2_human_lymph_node/morans_i.ipynb:150; not called by core.py)
