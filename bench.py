@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-pipeline", action="store_true", help="skip the detect_svgs -> pca -> aa pipeline through the API")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory variants")
+    ap.add_argument("--no-perm", action="store_true", help="skip the cfg3 permutation-inference timing (120k bins x 25k genes, P = 999)")
     ap.add_argument("--svgs", type=int, default=2000, help="SVGs fed to PCA (cfg4: 2,000)")
     ap.add_argument("--pcs", type=int, default=30)
     ap.add_argument("--archetypes", type=int, default=12)
@@ -320,6 +321,37 @@ def pipeline_through_api(args, csr, xy_host, var_names, torch, dv, _lib, ch, cor
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE cfg3: Moran's I with 999 permutations on a Stereo-seq-shaped lattice (N = 1)
+# ---------------------------------------------------------------------------------------------
+def permutation_cfg3(torch, dv, synth, _lib, n=120_000, g=25_000, P=999):
+    """Resident dense log1p matrix of cfg3's shape (every gene scored), all P draws inside chr_moran_perm_lattice_f32."""
+    xy = synth.make_coords("square", n, seed=3)
+    xy_d = dv.to_device(xy, torch.float64)
+    bbox = dv.spatial_bbox(xy_d)
+    nbr = dv.knn_build(xy_d, 8, bbox)
+    lat = dv.lattice_plan(xy_d, nbr, bbox)
+    model = synth.make_expression_model(xy, g, n_zones=8, seed=3, log_rate_mean=-2.8, log_rate_sd=1.2, device="cuda")
+    X = torch.zeros((lat.n_rows, dv.dense_ld(g)), dtype=torch.float32, device="cuda")
+    xy32 = torch.as_tensor(xy, dtype=torch.float32, device="cuda")
+    for b, i0 in enumerate(range(0, n, 8192)):
+        X[lat.row_of_spot[i0:i0 + 8192], :g] = synth.normalize_log1p_dense(model.counts(xy32[i0:i0 + 8192], b))
+    X[:, :g] += 1e-3 * torch.rand((1, g), device="cuda")                # no exactly-constant column
+    dv.moran_perm_lattice(X, lat, g, permutations=8, seed=1)             # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = dv.moran_perm_lattice(X, lat, g, permutations=P, seed=1, timing=True)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    loop_ms = dv.last_kernel_ms(_lib.FAMILY_MORAN)
+    p = res["p_sim"]
+    return {"workload": f"cfg3_stereoseq: {n} bins x {g} genes resident, square lattice k=8, P={P} permutations (chr_moran_perm_lattice_f32)",
+            "seconds": round(wall, 3), "draw_loop_ms": round(loop_ms, 1), "ms_per_draw": round(loop_ms / P, 4),
+            "matrix_bytes_per_draw": 4.0 * n * g, "equivalent_GBps": round(4.0 * n * g * P / (loop_ms * 1e-3) / 1e9, 1),
+            "genes_at_min_p": int((p <= 1.0 / (P + 1) + 1e-12).sum().item()),
+            "note": "a draw permutes the spots against the fixed W for all genes; the 128-gene slab (61 MB) is served from L2 across the draws of a batch"}
+
+
+# ---------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------
 def run_native(args):
@@ -565,6 +597,12 @@ def run_native(args):
         X = None
         torch.cuda.empty_cache()
         out["pipeline"] = pipeline_through_api(args, csr, xy, var_names, torch, dv, _lib, ch, core)
+
+    # ---- BASELINE cfg3: permutation inference (N = 1 only) ---------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_perm:
+        X = None
+        torch.cuda.empty_cache()
+        out["permutations_cfg3"] = permutation_cfg3(torch, dv, synth, _lib)
 
     # ---- cpu baseline + parity on a bounded gene sample (rank 0, N = 1 only) ---------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
