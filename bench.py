@@ -352,6 +352,62 @@ def permutation_cfg3(torch, dv, synth, _lib, n=120_000, g=25_000, P=999):
 
 
 # ---------------------------------------------------------------------------------------------
+# spot-sharded PCA (N > 1): partial Grams + NCCL all-reduce, the one exchange of the PCA stage
+# ---------------------------------------------------------------------------------------------
+def gram_sharded(args, rank, world, torch, dist, dv, dd, _lib):
+    """cfg4's SVG matrix (700k x 2,000) sharded by SPOTS: every rank densifies nothing here (synthetic resident rows), forms
+    its partial Gram on tcgen05, the partial Grams are all-reduced (16-32 MB, fp64), eigensolver replicated, scores local.
+    Device-timed per part with CUDA events, max over ranks."""
+    n, S, r = args.n, min(args.svgs, args.g - 1), args.pcs
+    lo, hi = dd.shard_range(n, rank, world)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    P = torch.empty((hi - lo, dv.dense_ld(S)), dtype=torch.float32, device="cuda")
+    P.uniform_(0.0, 1.0, generator=gen)
+    P = torch.where(P > 0.8, torch.log1p(8.0 * (P - 0.8)), torch.zeros_like(P))      # sparse log1p-like values
+    P[:, :64] += torch.linspace(0, 1, hi - lo, device="cuda")[:, None] * (rank + 1) / world
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def run():
+        e0 = ev()
+        sums = dv.column_sums(P, S)
+        e1 = ev()
+        dist.all_reduce(sums)
+        mean = sums / n
+        e2 = ev()
+        C = dv.gram_centered(P, S, mean, timing=True)
+        e3 = ev()
+        dist.all_reduce(C)
+        e4 = ev()
+        C = C / (n - 1)
+        evals, V, worst = dv.eigh_topk(C, r)
+        e5 = ev()
+        Y = dv.pca_scores(P, S, mean, V)
+        e6 = ev()
+        torch.cuda.synchronize()
+        return {"colsum_ms": e0.elapsed_time(e1), "allreduce_sums_ms": e1.elapsed_time(e2), "gram_ms": e2.elapsed_time(e3),
+                "allreduce_gram_ms": e3.elapsed_time(e4), "eigh_ms": e4.elapsed_time(e5), "scores_ms": e5.elapsed_time(e6),
+                "stage_ms": e0.elapsed_time(e6), "gram_kernel_ms": dv.last_kernel_ms(_lib.FAMILY_GRAM), "eigh_residual": float(worst)}
+
+    for _ in range(3):
+        run()
+    dist.barrier()
+    recs = [run() for _ in range(5)]
+    keys = [k for k in recs[0] if k != "eigh_residual"]
+    t = torch.tensor([[rec[k] for k in keys] for rec in recs], device="cuda", dtype=torch.float64).mean(0)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {k: round(float(v), 4) for k, v in zip(keys, t.tolist())}
+    out.update({"workload": f"SVG matrix {n} x {S} float32 sharded by spots over {world} ranks ({hi - lo} rows on rank 0), {r} components",
+                "allreduce_bytes": int(S * S * 8), "useful_flops": 2.0 * n * S * S,
+                "useful_tflops_stage": round(2.0 * n * S * S / (out["stage_ms"] * 1e-3) / 1e12, 1),
+                "eigh_residual": recs[-1]["eigh_residual"], "timing": "CUDA events per part, mean of 5 runs, max over ranks"})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------
 def run_native(args):
@@ -547,6 +603,14 @@ def run_native(args):
         out["variant_sweep"] = sweep
     if weak_rec:
         out["weak"] = weak_rec
+
+    # ---- spot-sharded Gram + all-reduce (N > 1): the exchange step of the PCA stage ------------------------------------
+    if world > 1 and not args.no_pipeline:
+        X = None
+        torch.cuda.empty_cache()
+        g_rec = gram_sharded(args, rank, world, torch, dist, dv, dd, _lib)
+        out["pca_sharded"] = g_rec
+        X, _ = densify(csr, scaling)
 
     # ---- e2e: the public call on host buffers ---------------------------------------------------------------------------
     var_names = [f"gene{j}" for j in range(*(dd.shard_range(g, rank, world) if strong else (0, g)))]

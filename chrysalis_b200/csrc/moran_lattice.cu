@@ -278,21 +278,33 @@ moran_lattice_corr_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
     for (int s = 0; s < 3; ++s)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[s][c] = 0.0;
-    for (int64_t e = e0 + warp; e < e1; e += kCorrWarps) {
-        const int4 en = __ldg(corr + e);
-        const float c = __int_as_float(en.z);
-        const float4 xi = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)(uint32_t)en.x * row_bytes));
-        const float a[4] = {xi.x - pf.x, xi.y - pf.y, xi.z - pf.z, xi.w - pf.w};
-        if (en.w == 0) {
-            const float4 xj = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)(uint32_t)en.y * row_bytes));
-            const float b[4] = {xj.x - pf.x, xj.y - pf.y, xj.z - pf.z, xj.w - pf.w};
+    // four entries per warp in flight (the two row loads of an entry depend on the entry itself: without this the kernel is a
+    // chain of L2 round trips and costs 0.3 ms at cfg4)
+    constexpr int kU = 4;
+    for (int64_t e = e0 + warp * kU; e < e1; e += kCorrWarps * kU) {
+        int4 en[kU];
+        float4 xi[kU], xj[kU];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[0][q] += (double)c * (double)a[q] * (double)b[q];
-        } else {
+        for (int u = 0; u < kU; ++u) en[u] = e + u < e1 ? __ldg(corr + e + u) : make_int4(0, 0, 0, 1);       // kind 1, coefficient +0: no effect
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                acc[1][q] += (double)c * (double)a[q];
-                acc[2][q] += (double)c * (double)a[q] * (double)a[q];
+        for (int u = 0; u < kU; ++u) {
+            xi[u] = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)(uint32_t)en[u].x * row_bytes));
+            xj[u] = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)(uint32_t)(en[u].w == 0 ? en[u].y : en[u].x) * row_bytes));
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const float c = __int_as_float(en[u].z);
+            const float a[4] = {xi[u].x - pf.x, xi[u].y - pf.y, xi[u].z - pf.z, xi[u].w - pf.w};
+            if (en[u].w == 0) {
+                const float b[4] = {xj[u].x - pf.x, xj[u].y - pf.y, xj[u].z - pf.z, xj[u].w - pf.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[0][q] += (double)c * (double)a[q] * (double)b[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[1][q] += (double)c * (double)a[q];
+                    acc[2][q] += (double)c * (double)a[q] * (double)a[q];
+                }
             }
         }
     }
