@@ -9,8 +9,9 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CHRYSALIS_B200_LIB: development override (A/B builds made by scripts/build_variant.sh); the product is the in-tree library
-LIB_PATH = os.environ.get("CHRYSALIS_B200_LIB") or os.path.join(_HERE, "libchrysalis_b200.so")
+# the product is the in-tree library and nothing else (A/B builds of scripts/build_variant.sh are copied over it by
+# scripts/ab_kernels.sh on the GPU box's scratch copy)
+LIB_PATH = os.path.join(_HERE, "libchrysalis_b200.so")
 
 FLAG_GEARY = 0x1
 FLAG_TIMING = 0x2

@@ -30,7 +30,9 @@ constexpr int kAaMaxP = kAaMaxD + 2;   // passive-set bound for the beta problem
 
 // measurement aid (scripts/aa_breakdown.py): [0] spots solved by warm alpha steps, [1] of those through the general
 // active-set path, [2] warps with at least one such spot, [3] warps
-__device__ unsigned long long g_aa_stats[4];
+#ifdef CHR_AA_STATS
+__device__ unsigned long long g_aa_stats[4];   // measurement builds only (scripts/build_variant.sh aastats "-DCHR_AA_STATS" aa)
+#endif
 
 // ---- small dense helpers (per thread, column-major n x n in `a`, n <= 66) ----------------------
 // Cholesky solve of the SPD system  H s = r  restricted to the index list `idx` (size np) of a
@@ -1523,7 +1525,8 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     return 0;
 }
 
-// measurement aid, not part of the C ABI in include/
+#ifdef CHR_AA_STATS
+// measurement aid of -DCHR_AA_STATS builds (ab_libs/), absent from the product library
 int chr_debug_aa_stats(unsigned long long* out4, int reset) {
     using namespace chr;
     if (out4 && cudaMemcpyFromSymbol(out4, g_aa_stats, sizeof(unsigned long long) * 4) != cudaSuccess) return 2;
@@ -1533,5 +1536,6 @@ int chr_debug_aa_stats(unsigned long long* out4, int reset) {
     }
     return 0;
 }
+#endif
 
 }  // extern "C"

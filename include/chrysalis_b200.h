@@ -103,7 +103,7 @@ int chr_csr_densify_log1p(const int64_t* indptr, const int32_t* indices, const f
  * the device representation of the row-standardised kNN weights (core.py:64-65) that the
  * Moran kernel streams against: every unordered pair {i, j} once with coefficient
  * a_ij + a_ji, grouped by quads of 4 consecutive spots, each pair owned by one endpoint, the
- * owners balanced, entries split into rows inside / outside the quad's 128-spot tile.
+ * owners balanced, entries split into rows inside / outside the quad's 112-spot tile.
  * Built once per W (k <= 64; any list: duplicates, self loops, asymmetric kNN).
  * plan: device buffer of chr_moran_plan_bytes(), 256-byte aligned.  info_host (HOST, int32[4],
  * may be NULL): {largest tile slice in 16-byte units (pass to chr_moran_dense_f32), total units,
@@ -120,7 +120,7 @@ int chr_moran_plan_build(const int32_t* nbr, int64_t n_spots, int k, void* plan,
  * X: [n_spots][ld] float32 dense expression (ld % 4 == 0, X 16-byte aligned, columns
  *    n_genes..round_up(n_genes,4)-1 readable), nbr: [n_spots][k] int32 (K1 output or any kNN
  *    list), plan + plan_chunk_units: chr_moran_plan_build's output for the same nbr.
- *    With a plan the TMA tile kernel runs (nbr may be NULL); without one (plan NULL, any k) the
+ *    With a plan the tile kernel runs (cp.async producer warps + mbarrier pipeline; nbr may be NULL); without one (plan NULL, any k) the
  *    per-spot stream kernel runs from nbr.
  * row_map: NULL, or int32 [n_spots]: spot i takes row row_map[i] of X while W stays in place.  One
  *    call with a random permutation is one draw of esda's permutation inference

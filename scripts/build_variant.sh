@@ -1,6 +1,6 @@
 #!/bin/bash
 # builds ab_libs/<name>.so = the library with ONE source compiled with extra flags (experiment macros).
-# usage: build_variant.sh name "-DEXP_X=1" [source-stem, default moran]; select it with CHRYSALIS_B200_LIB=ab_libs/<name>.so
+# usage: build_variant.sh name "-DEXP_X=1" [source-stem, default moran]; scripts/ab_kernels.sh copies it over the in-tree library on the GPU box
 set -e
 NAME=$1; EXTRA=$2; SRC=${3:-moran}
 cd "$(dirname "$0")/../chrysalis_b200/csrc"

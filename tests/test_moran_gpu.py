@@ -73,7 +73,7 @@ def test_moran_kernel_matches_reference_run_vectors(name):
 
 @pytest.mark.parametrize("variant", [0, 4])
 def test_all_kernel_variants_agree(variant, golden_random):
-    """The TMA tile kernel over the quad plan (0, default) and the per-spot stream kernel (4): same statistic."""
+    """The tile kernel over the quad plan (0, default) and the per-spot stream kernel (4): same statistic."""
     z = golden_random
     m = z["gene_mask"]
     I, C, _ = gpu_moran(dense_from(golden_csr(z), m), z["nbr"], geary=True, variant=variant)
