@@ -13,9 +13,11 @@ gene range, W is replicated, the only exchange is the all-gather of the per-gene
 region.  ``--scaling weak`` gives every rank its own 18,000 genes instead (reported under "weak" at N > 1 by default).
 
 `e2e` is the same metric through the public API with HOST buffers: ``ch.detect_svgs(adata)`` on an AnnData-like object
-whose ``X`` is a scipy CSR count matrix in page-locked host arrays (at N > 1: this rank's gene shard, flagged with
-``.uns['chr_gene_shard']``): H2D + filter/normalise/log1p/densify + kNN + lattice plan + Moran + D2H + the pandas tail.
-`e2e_pageable` is the same call on ordinary (pageable) numpy arrays.  `pipeline` times ch.detect_svgs -> ch.pca -> ch.aa
+whose ``X`` holds the raw counts in page-locked host memory in the loader's compact format (``device.CompactCSR``: uint16
+columns + uint8 values, 3 bytes per stored entry; at N > 1: this rank's gene shard, flagged with ``.uns['chr_gene_shard']``):
+H2D + decode + filter/normalise/log1p/densify + kNN + lattice plan + Moran + D2H + ranking and ``.var`` writes.
+`e2e_scipy_pinned` is the same call on the float32/int32 scipy CSR an AnnData usually holds (8 bytes per entry),
+`e2e_pageable` on ordinary (pageable) numpy arrays.  `pipeline` times ch.detect_svgs -> ch.pca -> ch.aa
 through the API on host data (cfg4: 2,000 SVGs, 30 PCs, 12 archetypes) and checks PCA / AA against sklearn / the oracle.
 """
 from __future__ import annotations
@@ -168,6 +170,15 @@ def pinned_scipy_csr(csr, torch, pin=True):
     m = sp.csr_matrix((host(csr.data), host(csr.indices), host(csr.indptr)), shape=csr.shape, copy=False)
     assert m.indices.dtype == np.int32
     return m
+
+
+def compact_from_device(csr, torch, dv):
+    """device.CompactCSR (u16 columns, u8 values, overflow list) in page-locked host memory with the device CSR's content:
+    the 3-bytes-per-entry format a loader stages raw counts in."""
+    big = csr.data >= 255
+    pin = lambda t: t.cpu().pin_memory()
+    return dv.CompactCSR(pin(csr.indptr), pin(csr.indices.to(torch.uint16)), pin(torch.where(big, torch.full_like(csr.data, 255.0), csr.data).to(torch.uint8)),
+                         pin(torch.nonzero(big).squeeze(1)), pin(csr.data[big]), tuple(csr.shape))
 
 
 def timed_calls(fn, n_warm, n_timed, torch, dist=None):
@@ -618,11 +629,12 @@ def run_native(args):
     if not args.no_e2e:
         X = None
         torch.cuda.empty_cache()
-        Xh = pinned_scipy_csr(csr, torch, pin=True)
-        ad = ch.AnnDataLite(Xh, obsm={"spatial": xy}, var_names=var_names, uns={"chr_gene_shard": True} if strong else None)
         e_steps = max(2, min(args.steps, 5))
+        shard_uns = {"chr_gene_shard": True} if strong else None
+        tail = " -> H2D, filter/normalise/log1p/densify, kNN + W plan, Moran, D2H, ranking + .var writes"
+        shard_note = " (this rank's gene shard, .uns['chr_gene_shard'])" if strong else ""
 
-        def e2e_step(a=ad):
+        def e2e_step(a):
             # every rank works on its own AnnData: its gene shard (strong, one exchange inside) or its own matrix (weak: no group call)
             if world > 1 and not strong:
                 keep, I_, _ = core.svg_stage(a.X, a.obsm["spatial"], MIN_SPOTS, k, False, already_log1p=False, shard=False)
@@ -630,31 +642,37 @@ def run_native(args):
             else:
                 ch.detect_svgs(a, min_spots=MIN_SPOTS, neighbors=k)
 
-        e_ms = timed_calls(e2e_step, 3, e_steps, torch, dgroup)
+        def run_e2e(Xhost, h2d, n_warm, n_timed, path):
+            ad = ch.AnnDataLite(Xhost, obsm={"spatial": xy}, var_names=var_names, uns=dict(shard_uns) if shard_uns else None)
+            ms = timed_calls(lambda: e2e_step(ad), n_warm, n_timed, torch, dgroup)
+            I_h = np.asarray(ad.var["Moran's I"], dtype=np.float64)
+            scored = int(np.isfinite(I_h).sum())
+            tot = torch.tensor([scored], device="cuda")
+            if world > 1:
+                dist.all_reduce(tot)
+            same = float(np.abs(I_h[np.isfinite(I_h)] - I_res).max()) if scored == g_sc else None
+            return {"value": round(int(tot.item()) / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 2), "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(8 * scored + csr.shape[1]), "steps": n_timed, "path": path, "max_abs_diff_to_resident_run": same}
+
+        # headline: raw counts in the loader's compact format (u16 columns + u8 values, page-locked): 3 bytes per stored entry
+        Xc = compact_from_device(csr, torch, dv)
+        out["e2e"] = run_e2e(Xc, Xc.nbytes + xy.nbytes, 3, e_steps,
+                             "ch.detect_svgs(adata): adata.X = device.CompactCSR counts (uint16 columns, uint8 values + overflow list) in "
+                             "page-locked host arrays" + shard_note + tail)
         if core.SVG_TRACE:                                            # CHR_SVG_TRACE=1: host timeline of the last step
             sys.stderr.write(f"svg_stage trace (ms): {core.SVG_TRACE}\n")
-        I_h = np.asarray(ad.var["Moran's I"], dtype=np.float64)
-        scored = int(np.isfinite(I_h).sum())
-        tot = torch.tensor([scored], device="cuda")
-        if world > 1:
-            dist.all_reduce(tot)
-        h2d = int(Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes + xy.nbytes)
-        same = float(np.abs(I_h[np.isfinite(I_h)] - I_res).max()) if scored == g_sc else None
-        out["e2e"] = {"value": round(int(tot.item()) / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 2),
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * scored + csr.shape[1]), "steps": e_steps,
-                      "path": "ch.detect_svgs(adata): adata.X = scipy CSR counts in page-locked host arrays" +
-                              (" (this rank's gene shard, .uns['chr_gene_shard'])" if strong else "") +
-                              " -> H2D, filter/normalise/log1p/densify, kNN + W plan, Moran, D2H, pandas ranking + .var writes",
-                      "max_abs_diff_to_resident_run": same}
+        del Xc
+        # the same call on the scipy CSR an AnnData usually holds (float32 values, int32 indices: 8 bytes per entry)
+        Xh = pinned_scipy_csr(csr, torch, pin=True)
+        out["e2e_scipy_pinned"] = run_e2e(Xh, Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes + xy.nbytes, 2, e_steps,
+                                          "ch.detect_svgs(adata): adata.X = scipy CSR (float32, int32) in page-locked host arrays" + shard_note + tail)
+        del Xh
         if world == 1 and not args.no_pageable:
             Xp = pinned_scipy_csr(csr, torch, pin=False)
-            adp = ch.AnnDataLite(Xp, obsm={"spatial": xy}, var_names=var_names)
-            p_ms = timed_calls(lambda: e2e_step(adp), 1, 2, torch)
-            out["e2e_pageable"] = {"value": round(scored / (p_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(p_ms, 2),
-                                   "host_threads": int(_lib.query("chr_host_threads")),
-                                   "path": "same call, adata.X in ordinary (pageable) numpy arrays: multi-threaded pinned bounce ring"}
-            del Xp, adp
-        del Xh, ad
+            out["e2e_pageable"] = run_e2e(Xp, Xp.data.nbytes + Xp.indices.nbytes + Xp.indptr.nbytes + xy.nbytes, 1, 2,
+                                          "same call, adata.X = scipy CSR in ordinary (pageable) numpy arrays: multi-threaded pinned bounce ring")
+            out["e2e_pageable"]["host_threads"] = int(_lib.query("chr_host_threads"))
+            del Xp
 
     # ---- the rest of the path through the API on host data: detect_svgs -> pca -> aa ------------------------------------
     if rank == 0 and world == 1 and not args.no_pipeline:

@@ -126,6 +126,8 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     def upload_counts():
         if not split:
             return dv.upload_csr(X)
+        if isinstance(X, (dv.DeviceCSR, dv.PinnedCSR, dv.CompactCSR)):
+            return dv.csr_columns(dv.upload_csr(X), lo, hi)
         col_map = np.full(g_all, -1, dtype=np.int32)
         col_map[lo:hi] = np.arange(hi - lo, dtype=np.int32)
         return dv.upload_csr_selected(X, col_map)
@@ -270,9 +272,37 @@ def svg_stage_multi(samples, min_spots: float, neighbors: int, geary: bool):
     return [results[b] for b in range(B)]
 
 
-def _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary):
-    """The tail of ``detect_svgs`` (core.py:78-92) for one AnnData given the scored genes."""
-    names = _make_unique(pd.Index(adata.var_names)[keep])
+def _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary, all_names=None, offset=0):
+    """The tail of ``detect_svgs`` (core.py:78-92) for one AnnData given the scored genes.
+
+    ``keep`` / ``I`` / ``C`` may cover more genes than this AnnData holds (gene-sharded AnnData: the genes of all ranks
+    in rank order, ``all_names`` their names, this AnnData's genes starting at ``offset``).
+    With unique gene names the reference's pandas statements reduce to array arithmetic (a descending sort, a count above
+    the threshold, index-aligned writes) and are done that way; duplicate names take the statements themselves, so that
+    ``var_names_make_unique`` renames and index alignment behave exactly as in the reference."""
+    local = pd.Index(adata.var_names)
+    names_all = local if all_names is None else all_names
+    g_local = len(local)
+    if names_all.is_unique:
+        keep = np.asarray(keep, dtype=bool)
+        I = np.asarray(I, dtype=np.float64)
+        full = np.full(len(keep), np.nan)
+        full[keep] = I
+        adata.var["Moran's I"] = full[offset:offset + g_local]                     # core.py:80: NaN for filtered genes
+        if geary:
+            full_c = np.full(len(keep), np.nan)
+            full_c[keep] = np.asarray(C, dtype=np.float64)
+            adata.var["Geary's C"] = full_c[offset:offset + g_local]                # core.py:85
+        above = I > min_morans                                                     # strict, NaN is not above
+        chosen = np.zeros(len(keep), dtype=bool)
+        if min(top_svg, len(I)) < int(above.sum()):                                # core.py:88: len(df[:top_svg]) < len(df[df > min])
+            order = np.argsort(-I, kind="stable")                                  # descending, NaN last (core.py:79)
+            chosen[np.flatnonzero(keep)[order[:top_svg]]] = True
+        else:
+            chosen[np.flatnonzero(keep)[above]] = True
+        adata.var['spatially_variable'] = chosen[offset:offset + g_local]          # core.py:89,92
+        return
+    names = _make_unique(names_all[keep])
     moran_df = pd.DataFrame(data=I, index=names, columns=["Moran's I"])
     moran_df = moran_df.sort_values(ascending=False, by="Moran's I")
     adata.var["Moran's I"] = moran_df["Moran's I"]
@@ -284,7 +314,8 @@ def _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary):
         chosen = set(moran_df[:top_svg].index)
     else:
         chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
-    adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]
+    # membership of every var name in the chosen set (core.py:89,92 builds the same booleans with a list comprehension)
+    adata.var['spatially_variable'] = np.asarray(local.isin(list(chosen)), dtype=bool)
 
 
 def detect_svgs_multi(adatas, min_spots: float = 0.05, top_svg: int = 1000, min_morans: float = 0.20, neighbors: int = 6,
@@ -329,26 +360,12 @@ def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans:
                            already_log1p="log1p" in adata.uns_keys(), local_shard=local_shard)
 
     # names of the filtered copy after var_names_make_unique (core.py:53-54)
-    var_names = pd.Index(adata.var_names)
+    all_names, offset = None, 0
     if local_shard:
-        var_names = pd.Index([v for part in dd.allgather_objects(list(var_names)) for v in part])
-    names = _make_unique(var_names[keep])
-
-    moran_df = pd.DataFrame(data=I, index=names, columns=["Moran's I"])
-    moran_df = moran_df.sort_values(ascending=False, by="Moran's I")
-    adata.var["Moran's I"] = moran_df["Moran's I"]
-
-    if geary:
-        geary_df = pd.DataFrame(data=C, index=names, columns=["Geary's C"])
-        geary_df = geary_df.sort_values(ascending=False, by="Geary's C")
-        adata.var["Geary's C"] = geary_df["Geary's C"]
-
-    # select thresholds (core.py:88-92)
-    if len(moran_df[:top_svg]) < len(moran_df[moran_df["Moran's I"] > min_morans]):
-        chosen = set(moran_df[:top_svg].index)
-    else:
-        chosen = set(moran_df[moran_df["Moran's I"] > min_morans].index)
-    adata.var['spatially_variable'] = [x in chosen for x in adata.var_names]
+        parts = dd.allgather_objects(list(adata.var_names))
+        all_names = pd.Index([v for part in parts for v in part])
+        offset = sum(len(part) for part in parts[:dd.world()[0]])
+    _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary, all_names=all_names, offset=offset)
 
 
 def morans_i_permutation(adata, min_spots: float = 0.05, neighbors: int = 6, permutations: int = 999, seed: int | None = None):

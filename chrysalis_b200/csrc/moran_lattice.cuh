@@ -23,7 +23,7 @@ constexpr int kLatThreads = 32 * (kLatWarps + kLatProducers);
 constexpr int kLatFlushStages = 4;                                // level-1 sums cover 4 stages = 8 columns
 constexpr size_t kLatSmem = 128 + (size_t)kLatStages * kLatStageBytes + 16 * kLatStages;
 constexpr int kLatPilotMax = 512;
-constexpr int kCorrPerCta = 64;                                   // correction entries per CTA (2 batches of 4 per warp)
+constexpr int kCorrPerCta = 256;                                  // correction entries per CTA (8 batches of 4 per warp)
 constexpr int kCorrWarps = 8;
 
 static_assert(kLatBH == CHR_LATTICE_BAND_ROWS, "header and kernel disagree on the band height");

@@ -93,9 +93,48 @@ __global__ void csr_densify_kernel(const int64_t* __restrict__ indptr, const int
     }
 }
 
+// compact counts -> the int32 / float32 arrays the other kernels read: u16 column indices, u8 values (255 = escape)
+__global__ void csr_decode_compact_kernel(const uint16_t* __restrict__ cols, const uint8_t* __restrict__ vals, int64_t nnz,
+                                          int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; t < nnz; t += stride) {
+        if (t + 8 <= nnz) {                                           // 16 bytes of columns + 8 bytes of values per thread
+            const uint4 c = *reinterpret_cast<const uint4*>(cols + t);
+            const uint2 v = *reinterpret_cast<const uint2*>(vals + t);
+            int4 i0 = make_int4(c.x & 0xffff, c.x >> 16, c.y & 0xffff, c.y >> 16), i1 = make_int4(c.z & 0xffff, c.z >> 16, c.w & 0xffff, c.w >> 16);
+            float4 f0 = make_float4((float)(v.x & 0xff), (float)((v.x >> 8) & 0xff), (float)((v.x >> 16) & 0xff), (float)(v.x >> 24));
+            float4 f1 = make_float4((float)(v.y & 0xff), (float)((v.y >> 8) & 0xff), (float)((v.y >> 16) & 0xff), (float)(v.y >> 24));
+            *reinterpret_cast<int4*>(out_idx + t) = i0;
+            *reinterpret_cast<int4*>(out_idx + t + 4) = i1;
+            *reinterpret_cast<float4*>(out_val + t) = f0;
+            *reinterpret_cast<float4*>(out_val + t + 4) = f1;
+        } else {
+            for (int64_t u = t; u < nnz; ++u) { out_idx[u] = cols[u]; out_val[u] = (float)vals[u]; }
+        }
+    }
+}
+__global__ void csr_decode_overflow_kernel(const int64_t* __restrict__ pos, const float* __restrict__ val, int64_t m, float* __restrict__ out_val) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) out_val[pos[t]] = val[t];
+}
+
 }  // namespace chr
 
 extern "C" {
+
+int chr_csr_decode_compact(const uint16_t* cols, const uint8_t* vals, int64_t nnz, const int64_t* over_pos, const float* over_val,
+                           int64_t n_over, int32_t* out_indices, float* out_data, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(nnz >= 0 && n_over >= 0 && (nnz == 0 || (cols && vals && out_indices && out_data)) && (n_over == 0 || (over_pos && over_val)),
+                "chr_csr_decode_compact: bad arguments");
+    CHR_REQUIRE((((uintptr_t)cols | (uintptr_t)out_indices | (uintptr_t)out_data) & 15) == 0 && ((uintptr_t)vals & 7) == 0,
+                "chr_csr_decode_compact: arrays must be 16-byte aligned (values 8-byte)");
+    if (nnz > 0) csr_decode_compact_kernel<<<kNumSMs * 8, 256, 0, st>>>(cols, vals, nnz, out_indices, out_data);
+    if (n_over > 0) csr_decode_overflow_kernel<<<(unsigned)ceil_div<int64_t>(n_over, 256), 256, 0, st>>>(over_pos, over_val, n_over, out_data);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
 
 int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n, int64_t n_genes,
                      int32_t* gene_nnz, chr_stream_t stream) {

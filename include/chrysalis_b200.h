@@ -86,6 +86,12 @@ int chr_hilbert_keys(const double* xy, int64_t n, const double* bbox, int64_t* k
 int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
                      int64_t n_genes, int32_t* gene_nnz /* [n_genes], zeroed by callee */,
                      chr_stream_t stream);
+/* compact counts as a loader can deliver them (3 bytes per stored entry instead of 8 across PCIe): column indices as
+ * uint16 (n_genes <= 65536), values as uint8 with 255 = "look in the overflow list" (over_pos: positions into the value
+ * array, over_val: their values; counts >= 255 are rare).  Expands to the int32 / float32 arrays of the calls below. */
+int chr_csr_decode_compact(const uint16_t* cols, const uint8_t* vals, int64_t nnz, const int64_t* over_pos,
+                           const float* over_val, int64_t n_over, int32_t* out_indices, float* out_data,
+                           chr_stream_t stream);
 /* per-spot totals over the kept genes (gene_col[g] >= 0), double accumulation, one warp per spot */
 int chr_csr_spot_totals(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
                         const int32_t* gene_col, double* totals, chr_stream_t stream);

@@ -217,3 +217,26 @@ def test_lattice_plan_splits_the_knn_adjacency_exactly(shape):
     quad = corr[:, 3] == 0
     assert Q + (coef[quad] * xr[corr[quad, 0]] * xr[corr[quad, 1]]).sum() == pytest.approx(x @ A @ x, rel=1e-12, abs=1e-9)
     assert 8 * x.sum() + (coef[~quad] * xr[corr[~quad, 0]]).sum() == pytest.approx(A.sum(0) @ x, rel=1e-12, abs=1e-9)
+
+
+def test_compact_csr_round_trip_and_limits():
+    """device.CompactCSR (the 3-bytes-per-entry loader format of detect_svgs): exact round trip incl. counts >= 255."""
+    import scipy.sparse as sp
+    from chrysalis_b200 import device as dv
+    rng = np.random.default_rng(0)
+    dense = rng.poisson(0.3, (200, 700)).astype(np.float32)
+    dense[rng.integers(0, 200, 40), rng.integers(0, 700, 40)] = rng.integers(255, 70000, 40)
+    X = sp.csr_matrix(dense)
+    c = dv.CompactCSR.from_scipy(X, pin=False)
+    assert c.cols.dtype == torch_dtype("uint16") and c.vals.dtype == torch_dtype("uint8") and c.over_pos.numel() == int((X.data >= 255).sum())
+    assert (c.to_scipy() != X).nnz == 0 and c.shape == X.shape
+    assert c.nbytes < 0.5 * (X.data.nbytes + X.indices.nbytes + X.indptr.nbytes) + 8 * c.over_pos.numel() + X.indptr.nbytes
+    with pytest.raises(ValueError):
+        dv.CompactCSR.from_scipy(sp.csr_matrix(dense * 0.5), pin=False)            # not counts
+    with pytest.raises(ValueError):
+        dv.CompactCSR.from_scipy(sp.csr_matrix((3, 70000), dtype=np.float32), pin=False)   # too many genes for uint16
+
+
+def torch_dtype(name):
+    import torch
+    return getattr(torch, name)

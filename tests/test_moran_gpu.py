@@ -492,3 +492,22 @@ def test_local_morans_i_fields(golden_hex):
     for j in range(3):
         if dense[:, j].std() > 0:
             np.testing.assert_allclose(ad.obsm["local_morans_i"][:, j], om.local_moran(dense[:, j], w)["Is"], rtol=1e-4, atol=1e-5)
+
+
+def test_detect_svgs_on_compact_counts_and_uint8_scipy(golden_square):
+    """The loader formats of the counts: device.CompactCSR (u16 columns + u8 values + overflow list) and a scipy CSR with
+    uint8 data give bit-identical results to the float32 scipy matrix."""
+    z = golden_square
+    X = golden_csr(z).astype(np.float32)
+    X.data[::997] += 300.0                                              # a few counts beyond the u8 range
+    res = []
+    for form in ("f32", "compact", "u16"):
+        Xi = X if form == "f32" else (dv.CompactCSR.from_scipy(X) if form == "compact" else X.astype(np.uint16))
+        ad = ch.AnnDataLite(Xi, obsm={"spatial": z["xy"]})
+        ch.detect_svgs(ad, neighbors=8, top_svg=40, min_morans=0.05, geary=True)
+        res.append((ad.var["Moran's I"].to_numpy(), ad.var["Geary's C"].to_numpy(), ad.var["spatially_variable"].to_numpy()))
+    for r in res[1:]:
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(res[0], r))
+    ref = osvg.detect_svgs(X, z["xy"], neighbors=8, top_svg=40, min_morans=0.05)
+    m = ref["gene_mask"]
+    assert_close(res[1][0][m], ref["morans"][m])
