@@ -541,13 +541,17 @@ def lattice_layout(ix: torch.Tensor, iy: torch.Tensor, band_rows: int = LATTICE_
     """Bands / chunks / row map of the lattice layout for spots on nodes (ix, iy) (unique).  Device-agnostic tensor
     arithmetic; the per-band tables are tiny and assembled on the host (one round trip)."""
     n = ix.numel()
-    W, H = int(ix.max().item()) + 1, int(iy.max().item()) + 1
+    W, H = (int(v) + 1 for v in torch.stack([ix.max(), iy.max()]).cpu())
     n_bands = (H + band_rows - 1) // band_rows
     band = iy // band_rows
     big = torch.iinfo(torch.int64).max
     xmin = torch.full((n_bands,), big, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amin")
     xmax = torch.full((n_bands,), -1, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amax")
-    xmin_h, xmax_h = xmin.cpu().numpy(), xmax.cpu().numpy()
+    crowded = (torch.bincount(iy * W + ix, minlength=W * H) > 1).any().to(torch.int64)          # two spots on one node
+    packed = torch.cat([xmin, xmax, crowded[None]]).cpu().numpy()                                  # one round trip
+    if packed[-1]:
+        return None, 0, None, None, (W, H)
+    xmin_h, xmax_h = packed[:n_bands], packed[n_bands:2 * n_bands]
     bands_h = np.zeros((n_bands, 4), dtype=np.int64)
     chunks = []
     row = 0
@@ -566,11 +570,8 @@ def lattice_layout(ix: torch.Tensor, iy: torch.Tensor, band_rows: int = LATTICE_
         torch.tensor(chunks, dtype=torch.int32, device=ix.device).reshape(-1, 4).contiguous(), (W, H)
 
 
-def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, shape: tuple):
-    """D = A - B as a coalesced COO list (i, j, coefficient) plus the (indeg - k) weights of W's column sums.
-
-    A: kNN adjacency counts of ``nbr`` [n, k] (spot ids); B: 1 for every ordered pair of present nodes that are
-    8-neighbours on the lattice.  Any list is legal (duplicates, self loops): coefficients are exact integers."""
+def _lattice_corrections_general(ix, iy, nbr, shape):
+    """D = A - B by coalescing ALL ordered pairs (any list: duplicates, self loops): exact integer coefficients."""
     n, k = nbr.shape
     W, H = shape
     dev = ix.device
@@ -585,14 +586,49 @@ def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, s
             j = grid[(iy + 1 + dy) * (W + 2) + ix + 1 + dx]
             ok = j >= 0
             keys.append(me[ok] * n + j[ok])
-            vals.append(torch.full((int(ok.sum().item()),), -1, dtype=torch.int64, device=dev))
+            vals.append(torch.full((keys[-1].numel(),), -1, dtype=torch.int64, device=dev))
     key, inv = torch.unique(torch.cat(keys), return_inverse=True)
     coef = torch.zeros(key.numel(), dtype=torch.int64, device=dev).scatter_add_(0, inv, torch.cat(vals))
     nz = coef != 0
     key, coef = key[nz], coef[nz]
-    indeg = torch.bincount(nbr.reshape(-1).long(), minlength=n)
-    wj = torch.nonzero(indeg != k).squeeze(1)
-    return key // n, key % n, coef, wj, (indeg[wj] - k)
+    return key // n, key % n, coef
+
+
+def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, shape: tuple):
+    """D = A - B as a COO list (i, j, coefficient) plus the (indeg - k) weights of W's column sums.
+
+    A: kNN adjacency counts of ``nbr`` [n, k] (spot ids); B: 1 for every ordered pair of present nodes that are
+    8-neighbours on the lattice.  kNN lists (no repeats, no self) only differ from the stencil at tissue edges and holes:
+    list entries that are not stencil neighbours (+1) and stencil neighbours the list misses (-1) are found with dense
+    [n, k] / [n, 8] masks and two host round trips; lists with repeats or self loops take the general coalescing path."""
+    n, k = nbr.shape
+    W, H = shape
+    dev = ix.device
+    me = torch.arange(n, device=dev)
+    nb = nbr.long()
+    grid = torch.full(((H + 2) * (W + 2),), -1, dtype=torch.int64, device=dev)
+    grid[(iy + 1) * (W + 2) + ix + 1] = me
+    offs = torch.tensor([dy * (W + 2) + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1) if dx or dy], device=dev)
+    J = grid[((iy + 1) * (W + 2) + ix + 1)[:, None] + offs[None, :]]                          # [n, 8] stencil neighbours, -1 = absent
+    extra = ~(((ix[nb] - ix[:, None]).abs() <= 1) & ((iy[nb] - iy[:, None]).abs() <= 1)) | (nb == me[:, None])    # [n, k]
+    missing = (J >= 0) & ~(nb[:, None, :] == J[:, :, None]).any(2)                            # [n, 8]
+    srt = nb.sort(dim=1).values
+    irregular = (srt[:, 1:] == srt[:, :-1]).any() | (nb == me[:, None]).any()
+    indeg = torch.bincount(nb.reshape(-1), minlength=n)
+    wmask = indeg != k
+    counts = torch.stack([extra.sum(), missing.sum(), wmask.sum(), irregular.to(torch.int64)]).cpu()   # round trip 1
+    n_extra, n_missing, n_w, irr = (int(v) for v in counts)
+    hits = torch.nonzero(torch.cat([extra.reshape(-1), missing.reshape(-1), wmask]))[:, 0]               # round trip 2 (sizes known)
+    e, m, w = hits[:n_extra], hits[n_extra:n_extra + n_missing] - n * k, hits[n_extra + n_missing:] - n * (k + 8)
+    wj = w
+    if irr:
+        ci, cj, cc = _lattice_corrections_general(ix, iy, nbr, shape)
+    else:
+        ei, mi = e // k, m // 8
+        ci = torch.cat([ei, mi])
+        cj = torch.cat([nb.reshape(-1)[e], J.reshape(-1)[m]])
+        cc = torch.cat([torch.ones_like(ei), -torch.ones_like(mi)])
+    return ci, cj, cc, wj, (indeg[wj] - k)
 
 
 def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None = None, pitch: float | None = None,
@@ -604,14 +640,14 @@ def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None 
     if k != 8 or n < 64:
         return None
     bbox = spatial_bbox(xy) if bbox is None else bbox
-    pitch = square_lattice_pitch(xy, bbox) if pitch is None else pitch
+    if pitch is None:                                                   # the lists are sorted by distance: column 0 is the nearest neighbour
+        pitch = lattice_pitch_from_nn(xy, bbox, (xy[nbr[:, 0].long()] - xy).norm(dim=1))
     if pitch is None:
         return None
     ix, iy = lattice_nodes(xy, bbox, pitch)
-    W, H = int(ix.max().item()) + 1, int(iy.max().item()) + 1
-    if torch.unique(iy * W + ix).numel() != n:
-        return None
     row_of_spot, n_rows, bands, chunks, shape = lattice_layout(ix, iy)
+    if row_of_spot is None:                                             # two spots on one node
+        return None
     if n_rows > max_fill * n or n_rows >= 2 ** 31 or chunks.shape[0] >= 65536:
         return None
     ci, cj, cc, wj, ww = lattice_corrections(ix, iy, nbr, shape)
