@@ -156,7 +156,10 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
             nbr = rank_of.to(torch.int32)[nbr0[order].long()].contiguous()      # relabelled into the row order
             plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
             n_rows = n
-        if torch.cuda.is_available():
+        # on a lattice the kernel is fed from the CSR counts themselves (no dense matrix); permutation inference and every
+        # other W stream a dense matrix, whose zero fill runs here, under the upload
+        use_csr = lat is not None and not permutations and os.environ.get("CHR_MORAN_CSR", "1") != "0"
+        if torch.cuda.is_available() and not use_csr:
             dense_buf = torch.empty((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
             dense_buf.zero_()
     if csr is None:
@@ -164,7 +167,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         _mark(t0, "counts uploaded (bounce ring)")
     if side is not None:
         main.wait_stream(side)
-        keep_alive = [rank_of, dense_buf] + ([nbr, plan.buf] if plan is not None else []) + \
+        keep_alive = [rank_of] + ([dense_buf] if dense_buf is not None else []) + ([nbr, plan.buf] if plan is not None else []) + \
             ([lat.bands, lat.chunks, lat.corr, lat.absent, lat.pilot_rows] if lat is not None else [])
         for t in keep_alive:
             t.record_stream(main)
@@ -185,8 +188,19 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     scale = None
     if not already_log1p:
         scale = dv.median_scale(reduce_(dv.csr_spot_totals(csr, gene_col)))
-    if n_keep > 0:
-        # core.py:59  gene_matrix = ad.to_df()  (dense float32, here in Hilbert row order)
+    unsorted = None
+    if n_keep > 0 and use_csr and csr.indices.numel() < 2 ** 32 - 1:
+        # core.py:59 + 71-76 in one kernel: the producers of the stencil kernel build the tiles from the stored entries
+        I, C, _, unsorted = dv.moran_lattice_csr(csr, gene_col, n_keep, scale, lat, apply_log1p=not already_log1p, geary=geary, timing=timing)
+        sim = None
+        if int(unsorted.item()):                                        # columns not sorted inside a row: the dense path does not care
+            unsorted, use_csr = None, False
+    else:
+        use_csr = False
+    if n_keep > 0 and not use_csr:
+        # core.py:59  gene_matrix = ad.to_df()  (dense float32, in lattice layout / Hilbert row order)
+        if dense_buf is None and torch.cuda.is_available():
+            dense_buf = torch.zeros((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
         dense = dv.csr_densify(csr, gene_col, n_keep, scale, rank_of, apply_log1p=not already_log1p, out=dense_buf)
         # core.py:71-76  the gene loop
         if lat is not None:
@@ -195,7 +209,7 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
         else:
             I, C, _ = dv.moran_dense(dense, nbr, n_keep, geary=geary, timing=timing, plan=plan)
             sim = dv.moran_permutation_test(dense, nbr, n_keep, permutations, seed, plan) if permutations else None
-    else:
+    elif n_keep == 0:
         I = torch.empty(0, dtype=torch.float64, device=keep.device)
         C = torch.empty(0, dtype=torch.float64, device=keep.device) if geary else None
         sim = {k: torch.empty(0, dtype=torch.float64, device=keep.device)

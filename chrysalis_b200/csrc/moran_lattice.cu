@@ -101,10 +101,35 @@ __device__ __forceinline__ void lattice_step(uint32_t addr, bool accumulate, con
 
 // bands[b]  = {first matrix row, x of the first stored column, stored columns, lattice rows (<= 60)}
 // chunks[c] = {band, first column (relative to the band's first stored column), columns, 0}
-template <bool SHIFT>
-__global__ void __launch_bounds__(kLatThreads, 1)
-moran_lattice_kernel(const float* __restrict__ X, uint32_t row_bytes, int ncol, const int4* __restrict__ bands, int n_bands,
+//
+// Where the columns come from (LatSrc):
+//   dense  X [rows][ld] float32 in lattice layout: 4 producer warps copy rows with cp.async (HBM-bound: one read of X)
+//   CSR    the counts themselves, prepared once per call by lattice_csr_prepare_*: per stored entry the position inside
+//          its 128-gene slab (ecol, 0xFF = gene filtered out) and log1p(count * scale) (eval); per (slab, stored row) the
+//          range of the row's entries that fall into the slab (eoff).  6 producer warps, one staged column each, build the
+//          tiles in shared memory: rows are initialised (zeros for a present node, the pilot vector for an absent one) and
+//          the ~6 entries a row has inside the slab are scattered in (8 loads per lane in flight, the entry ranges of a warp's
+//          next column prefetched).  No dense matrix exists: HBM sees the entries once (5 bytes each) instead of 4 bytes
+//          per spot and gene.
+struct LatSrc {
+    const float* X;                 // dense
+    uint32_t row_bytes;
+    const uint32_t* eoff;           // CSR: [n_rows][n_slabs + 1] absolute entry offsets, 0xFFFFFFFF in every slot of an absent node
+    const uint8_t* ecol;
+    const float* eval;
+    int64_t n_slabs1;               // n_slabs + 1
+};
+
+constexpr int kLatCsrProducers = kLatStages * kLatStageCols;      // 6: one producer warp per staged column
+constexpr int kLatCsrThreads = 32 * (kLatWarps + kLatCsrProducers);
+
+template <bool SHIFT, bool CSR>
+__global__ void __launch_bounds__(CSR ? kLatCsrThreads : kLatThreads, 1)
+moran_lattice_kernel(const LatSrc src, int ncol, const int4* __restrict__ bands, int n_bands,
                      const int4* __restrict__ chunks, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
+    constexpr int kProducers = CSR ? kLatCsrProducers : kLatProducers;
+    const float* __restrict__ X = src.X;
+    const uint32_t row_bytes = src.row_bytes;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     uint32_t smem0 = (smem_u32(smem_dyn) + 127u) & ~127u;
     asm volatile("" : "+r"(smem0));
@@ -116,7 +141,8 @@ moran_lattice_kernel(const float* __restrict__ X, uint32_t row_bytes, int ncol, 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kLatStages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(32 * kLatProducers) : "memory");
+            // dense: every producer thread arrives through its cp.async group; CSR: the 2 warps that build the stage's columns arrive
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(CSR ? 32 * kLatStageCols : 32 * kProducers) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(kLatWarps) : "memory");
         }
         mbar_fence_init();
@@ -131,7 +157,104 @@ moran_lattice_kernel(const float* __restrict__ X, uint32_t row_bytes, int ncol, 
     const int n_steps = ch.z + 2;                                     // columns j = -1 .. ch.z of the chunk
     const int n_iters = (n_steps + kLatStageCols - 1) / kLatStageCols;
 
-    if (warp >= kLatWarps) {
+    if (CSR && warp >= kLatWarps) {
+        // ===== CSR producers: warp p owns the staged column slot (stage p / 2, column p % 2) for the whole chunk =====
+        const int pw = warp - kLatWarps;
+        const int my_stage = pw / kLatStageCols, cc = pw % kLatStageCols;
+        const bool has_next = ch.x + 1 < n_bands;
+        int4 nb = make_int4(0, 0, 0, 0);
+        if (has_next) nb = __ldg(bands + ch.x + 1);
+        const float4 pil4 = __ldg(reinterpret_cast<const float4*>(pilot + col));
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t* __restrict__ off = src.eoff + blockIdx.x;       // eoff[row][slab], eoff[row][slab + 1]
+        const int64_t off_ld = src.n_slabs1;
+        const uint32_t seg = smem0 + my_stage * kLatStageBytes + cc * kLatSegBytes;
+        // entry ranges of rows `lane` and `lane + 32` of column j (0xFFFFFFFF = absent node / nothing stored there)
+        auto resolve = [&](int j, uint2 (&rng)[2]) {
+            const int xc = ch.y + j;
+            const bool valid = xc >= 0 && xc < bd.z;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = lane + 32 * h;
+                int r = -1;
+                if (j <= ch.z) {
+                    if (t < bd.w) {
+                        if (valid) r = bd.x + xc * bd.w + t;
+                    } else if (t == bd.w && has_next) {
+                        const int xn = bd.y + xc - nb.y;
+                        if (xn >= 0 && xn < nb.z) r = nb.x + xn * nb.w;
+                    }
+                }
+                rng[h] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (r >= 0) rng[h] = make_uint2(__ldg(off + (int64_t)r * off_ld), __ldg(off + (int64_t)r * off_ld + 1));
+            }
+        };
+        uint2 cur[2], nxt[2];
+        resolve(my_stage * kLatStageCols + cc - 1, cur);
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int it = my_stage; it < n_iters; it += kLatStages, phase ^= 1u) {
+            const int j = it * kLatStageCols + cc - 1;
+            resolve((it + kLatStages) * kLatStageCols + cc - 1, nxt);   // the ranges of this warp's next column are in flight meanwhile
+            // first batch of entries of both rows of this lane: loaded into registers BEFORE the stage is waited for and the
+            // rows are initialised, so their latency hides behind both
+            constexpr int kB = 12;
+            unsigned c0[kB], c1[kB];
+            float v0[kB], v1[kB];
+            const uint32_t b0 = cur[0].x, b1 = cur[1].x;                 // absent node (0xFFFFFFFF): no entries
+            const uint32_t n0 = b0 == 0xFFFFFFFFu ? 0u : cur[0].y - b0, n1 = b1 == 0xFFFFFFFFu ? 0u : cur[1].y - b1;
+#pragma unroll
+            for (int q = 0; q < kB; ++q) {
+                const bool in0 = (uint32_t)q < n0, in1 = (uint32_t)q < n1;
+                c0[q] = in0 ? (unsigned)__ldg(src.ecol + b0 + q) : 0xFFu;
+                v0[q] = in0 ? __ldg(src.eval + b0 + q) : 0.f;
+                c1[q] = in1 ? (unsigned)__ldg(src.ecol + b1 + q) : 0xFFu;
+                v1[q] = in1 ? __ldg(src.eval + b1 + q) : 0.f;
+            }
+            if (it >= kLatStages) lat_mbar_wait(empty_bar + 8 * my_stage, phase ^ 1u);
+            if (j <= ch.z) {
+                const unsigned pm0 = __ballot_sync(0xffffffffu, cur[0].x != 0xFFFFFFFFu), pm1 = __ballot_sync(0xffffffffu, cur[1].x != 0xFFFFFFFFu);
+                // rows start as zeros (present node: no entry = no expression) or as the pilot vector (absent node: neutral)
+#pragma unroll 8
+                for (int t = 0; t < kLatSegRows; ++t) {
+                    const bool pres = ((t < 32 ? pm0 : pm1) >> (t & 31)) & 1u;
+                    const float4 v = pres ? zero4 : pil4;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(seg + t * kLatRowBytes + lane * 16), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                __syncwarp();
+                const uint32_t row0 = seg + (uint32_t)lane * kLatRowBytes, row1 = row0 + 32 * kLatRowBytes;
+#pragma unroll
+                for (int q = 0; q < kB; ++q) {
+                    if (c0[q] != 0xFFu) asm volatile("st.shared.f32 [%0], %1;" ::"r"(row0 + c0[q] * 4), "f"(v0[q]) : "memory");
+                    if (c1[q] != 0xFFu) asm volatile("st.shared.f32 [%0], %1;" ::"r"(row1 + c1[q] * 4), "f"(v1[q]) : "memory");
+                }
+                // rows with more than kB entries inside the slab (rare)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t row_addr = h ? row1 : row0, bb = h ? b1 : b0, nn = h ? n1 : n0;
+                    for (uint32_t o = kB; o < nn; o += 8) {
+                        unsigned c[8];
+                        float v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const bool in = o + q < nn;
+                            c[q] = in ? (unsigned)__ldg(src.ecol + bb + o + q) : 0xFFu;
+                            v[q] = in ? __ldg(src.eval + bb + o + q) : 0.f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (c[q] != 0xFFu) asm volatile("st.shared.f32 [%0], %1;" ::"r"(row_addr + c[q] * 4), "f"(v[q]) : "memory");
+                    }
+                }
+            }
+            __syncwarp();
+            lat_mbar_arrive(full_bar + 8 * my_stage);                 // release: the stores above are visible to the waiters
+            cur[0] = nxt[0];
+            cur[1] = nxt[1];
+        }
+    }
+
+    if (!CSR && warp >= kLatWarps) {
         // ===== producer warps: stream the chunk's columns, two stages ahead of the compute warps =====
         const int pw = warp - kLatWarps;
         const bool has_next = ch.x + 1 < n_bands;
@@ -324,6 +447,166 @@ moran_lattice_corr_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
     }
 }
 
+// ---- CSR-fed variant: preparation, pilot, corrections ---------------------------------------------------------------
+// per stored entry: position inside its 128-gene slab (0xFF: gene filtered out) and the value the dense matrix would hold
+// (same arithmetic as csr_densify_kernel: product in float64, rounded once, log1pf)
+__global__ void lattice_csr_entries_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                           int64_t n, const int32_t* __restrict__ gene_col, const double* __restrict__ scale, int apply_log1p,
+                                           uint8_t* __restrict__ ecol, float* __restrict__ eval, int32_t* __restrict__ unsorted) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t b = indptr[i], e = indptr[i + 1];
+        const double sc = scale ? scale[i] : 1.0;
+        for (int64_t t = b + lane; t < e; t += 32) {
+            const int32_t g = indices[t];
+            if (unsorted && t > b && indices[t - 1] >= g) *unsorted = 1;      // the slab ranges need strictly increasing columns per row
+            const int c = gene_col[g];
+            float v = scale ? (float)((double)data[t] * sc) : data[t];
+            if (apply_log1p) v = log1pf(v);
+            ecol[t] = c < 0 ? (uint8_t)0xFF : (uint8_t)(c & (kGeneTile - 1));
+            eval[t] = v;
+        }
+    }
+}
+
+// slab_first[s] = original column of the first kept gene of slab s; slab_first[n_slabs] = n_genes_all
+__global__ void lattice_csr_slab_first_kernel(const int32_t* __restrict__ gene_col, int64_t n_genes_all, int n_slabs, int32_t* __restrict__ slab_first) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) slab_first[n_slabs] = (int32_t)n_genes_all;
+    if (g >= n_genes_all) return;
+    const int c = gene_col[g];
+    if (c >= 0 && (c & (kGeneTile - 1)) == 0) slab_first[c / kGeneTile] = (int32_t)g;
+}
+
+// eoff[r][s] = absolute index of the first entry of the spot stored at row r whose (original, sorted) column is
+// >= slab_first[s]; every slot of an absent node is 0xFFFFFFFF.  One warp per row: the row's columns are staged in
+// shared memory and the lanes binary-search the slab boundaries there.
+constexpr int kOffWarps = 8, kOffStage = 1024;
+__global__ void __launch_bounds__(32 * kOffWarps)
+lattice_csr_offsets_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ spot_of_row,
+                           int64_t n_rows, const int32_t* __restrict__ slab_first, int n_slabs1, uint32_t* __restrict__ eoff) {
+    __shared__ int32_t cols_s[kOffWarps][kOffStage];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kOffWarps + warp;
+    if (r >= n_rows) return;
+    uint32_t* __restrict__ out = eoff + r * n_slabs1;
+    const int spot = spot_of_row[r];
+    if (spot < 0) {
+        for (int s = lane; s < n_slabs1; s += 32) out[s] = 0xFFFFFFFFu;
+        return;
+    }
+    const int64_t b = indptr[spot], e = indptr[spot + 1];
+    const int len = (int)(e - b);
+    const bool staged = len <= kOffStage;
+    if (staged) {
+        for (int t = lane; t < len; t += 32) cols_s[warp][t] = __ldg(indices + b + t);
+        __syncwarp();
+    }
+    for (int s = lane; s < n_slabs1; s += 32) {
+        const int32_t key = slab_first[s];
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int32_t c = staged ? cols_s[warp][mid] : __ldg(indices + b + mid);
+            if (c < key) lo = mid + 1; else hi = mid;
+        }
+        out[s] = (uint32_t)(b + lo);
+    }
+}
+
+// pilot shift from the CSR form: mean over the sample rows; one CTA per slab, warp w adds rows w, w + 16, ... into its own
+// accumulator, the accumulators are then added in warp order (fixed summation tree)
+constexpr int kPilotWarps = 16;
+__global__ void __launch_bounds__(32 * kPilotWarps)
+lattice_csr_pilot_kernel(const uint32_t* __restrict__ eoff, const uint8_t* __restrict__ ecol, const float* __restrict__ eval, int64_t n_slabs1,
+                         const int32_t* __restrict__ rows, int ns, float* __restrict__ pilot) {
+    __shared__ float acc[kPilotWarps][kGeneTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = lane; c < kGeneTile; c += 32) acc[warp][c] = 0.f;
+    __syncwarp();
+    for (int t = warp; t < ns; t += kPilotWarps) {
+        const uint32_t* __restrict__ o = eoff + (int64_t)rows[t] * n_slabs1 + blockIdx.x;
+        const uint32_t b = o[0], e = o[1];
+        for (uint32_t u = b + lane; u < e; u += 32) {
+            const unsigned c = ecol[u];
+            if (c != 0xFFu) acc[warp][c] += eval[u];                  // one entry per gene and row: no two lanes share a slot
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < kGeneTile) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPilotWarps; ++w) a += acc[w][threadIdx.x];
+        pilot[(int64_t)blockIdx.x * kGeneTile + threadIdx.x] = a / (float)ns;
+    }
+}
+
+// corrections from the CSR form: the two rows of an entry are rebuilt (128 genes of the slab) in per-warp shared memory
+__global__ void __launch_bounds__(32 * kCorrWarps)
+moran_lattice_csr_corr_kernel(const uint32_t* __restrict__ eoff, const uint8_t* __restrict__ ecol, const float* __restrict__ eval, int64_t n_slabs1,
+                              const int4* __restrict__ corr, int64_t n_corr, const float* __restrict__ pilot, double* __restrict__ part,
+                              int64_t gpad, int split0) {
+    __shared__ double red[kCorrWarps][kGeneTile];
+    __shared__ __align__(16) float rows_s[kCorrWarps][2][kGeneTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_col = blockIdx.x * kGeneTile;
+    const float4 pf = __ldg(reinterpret_cast<const float4*>(pilot + tile_col + lane * 4));
+    const int64_t e0 = (int64_t)blockIdx.y * kCorrPerCta, e1 = e0 + kCorrPerCta < n_corr ? e0 + kCorrPerCta : n_corr;
+    double acc[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[s][c] = 0.0;
+    for (int64_t e = e0 + warp; e < e1; e += kCorrWarps) {
+        const int4 en = __ldg(corr + e);
+        const int nrow = en.w == 0 ? 2 : 1;
+        for (int h = 0; h < nrow; ++h) {
+            const int r = h == 0 ? en.x : en.y;
+            *reinterpret_cast<float4*>(&rows_s[warp][h][lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            const uint32_t* __restrict__ o = eoff + (int64_t)r * n_slabs1 + blockIdx.x;
+            for (uint32_t u = o[0] + lane; u < o[1]; u += 32) {
+                const unsigned c = ecol[u];
+                if (c != 0xFFu) rows_s[warp][h][c] = eval[u];
+            }
+        }
+        __syncwarp();
+        const float c = __int_as_float(en.z);
+        const float4 xi = *reinterpret_cast<const float4*>(&rows_s[warp][0][lane * 4]);
+        const float a[4] = {xi.x - pf.x, xi.y - pf.y, xi.z - pf.z, xi.w - pf.w};
+        if (en.w == 0) {
+            const float4 xj = *reinterpret_cast<const float4*>(&rows_s[warp][1][lane * 4]);
+            const float b[4] = {xj.x - pf.x, xj.y - pf.y, xj.z - pf.z, xj.w - pf.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[0][q] += (double)c * (double)a[q] * (double)b[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[1][q] += (double)c * (double)a[q];
+                acc[2][q] += (double)c * (double)a[q] * (double)a[q];
+            }
+        }
+        __syncwarp();
+    }
+    for (int st = 0; st < kNStat; ++st) {
+        if (st >= 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = acc[st - 2][q];
+        }
+        __syncthreads();
+        if (threadIdx.x < kGeneTile) {
+            double t = 0.0;
+            if (st >= 2)
+                for (int w = 0; w < kCorrWarps; ++w) t += red[w][threadIdx.x];
+            part[((int64_t)(split0 + blockIdx.y) * kNStat + st) * gpad + tile_col + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
 struct LatWs {
     int64_t gpad;
     int ntile, nsplit, ncorr_split;
@@ -344,9 +627,98 @@ static LatWs lattice_ws(int64_t ncol, int n_chunks, int64_t n_corr) {
     return p;
 }
 
+struct LatCsrWs {
+    LatWs lat;
+    int n_slabs;
+    size_t lat_off, ecol_off, eval_off, eoff_off, first_off, total;
+};
+
+static LatCsrWs lattice_csr_ws(int64_t nnz, int64_t n_rows, int64_t n_keep, int n_chunks, int64_t n_corr) {
+    LatCsrWs p;
+    const int64_t ncol = round_up<int64_t>(n_keep, 4);
+    p.lat = lattice_ws(ncol, n_chunks, n_corr);
+    p.n_slabs = p.lat.ntile;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += round_up<size_t>(b, 256); return r; };
+    p.lat_off = take(p.lat.total);
+    p.ecol_off = take((size_t)(nnz > 0 ? nnz : 1));
+    p.eval_off = take((size_t)(nnz > 0 ? nnz : 1) * 4);
+    p.eoff_off = take((size_t)(p.n_slabs + 1) * (size_t)n_rows * 4);
+    p.first_off = take((size_t)(p.n_slabs + 1) * 4);
+    p.total = o;
+    return p;
+}
+
 }  // namespace chr
 
 extern "C" {
+
+size_t chr_moran_lattice_csr_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_keep, int n_chunks, int64_t n_corr) {
+    if (nnz < 0 || n_rows <= 0 || n_keep <= 0 || n_chunks <= 0 || n_corr < 0) return 256;
+    return chr::lattice_csr_ws(nnz, n_rows, n_keep, n_chunks, n_corr).total + 512;
+}
+
+int chr_moran_lattice_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t nnz, int64_t n_spots,
+                              int64_t n_genes_all, const int32_t* gene_col, int64_t n_keep, const double* scale, int apply_log1p,
+                              int64_t n_rows, int k, const int32_t* bands, int n_bands, const int32_t* chunks, int n_chunks,
+                              const int32_t* corr, int64_t n_corr, const int32_t* spot_of_row, const int32_t* pilot_rows, int n_pilot,
+                              unsigned flags, double* out_I, double* out_C, double* out_stats, int32_t* unsorted_flag, void* workspace,
+                              size_t workspace_bytes, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(indptr && indices && data && gene_col && bands && chunks && spot_of_row && pilot_rows && out_I && workspace,
+                "chr_moran_lattice_csr_f32: null pointer argument");
+    CHR_REQUIRE(n_rows >= n_spots && n_spots > 1 && n_keep > 0 && n_genes_all >= n_keep, "chr_moran_lattice_csr_f32: bad sizes");
+    CHR_REQUIRE(nnz >= 0 && nnz < 0xFFFFFFFFLL, "chr_moran_lattice_csr_f32: needs fewer than 2^32 - 1 stored entries (got %lld)", (long long)nnz);
+    CHR_REQUIRE(k == 8, "chr_moran_lattice_csr_f32: the stencil path is the 8-neighbour square lattice (k=%d)", k);
+    CHR_REQUIRE(n_rows < (1LL << 31) && n_bands > 0 && n_chunks > 0 && n_chunks < 65536 && n_pilot > 0 && n_pilot <= kLatPilotMax,
+                "chr_moran_lattice_csr_f32: bad plan sizes");
+    CHR_REQUIRE((n_corr == 0 || corr) && n_corr >= 0, "chr_moran_lattice_csr_f32: bad correction list");
+    const bool geary = flags & CHR_FLAG_GEARY, timing = flags & CHR_FLAG_TIMING;
+    CHR_REQUIRE(!geary || out_C, "chr_moran_lattice_csr_f32: CHR_FLAG_GEARY needs out_C");
+    CHR_REQUIRE(!(flags & CHR_FLAG_PRESHIFTED), "chr_moran_lattice_csr_f32: CHR_FLAG_PRESHIFTED has no meaning for sparse input");
+    LatCsrWs p = lattice_csr_ws(nnz, n_rows, n_keep, n_chunks, n_corr);
+    CHR_REQUIRE(p.lat.ncorr_split < 65536 && p.n_slabs + 1 < 65536, "chr_moran_lattice_csr_f32: too many corrections / gene slabs");
+    CHR_REQUIRE(workspace_bytes >= p.total + 256, "chr_moran_lattice_csr_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total + 256);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    char* lws = ws + p.lat_off;
+    float* pilot = (float*)(lws + p.lat.pilot_off);
+    double* part = (double*)(lws + p.lat.part_off);
+    uint8_t* ecol = (uint8_t*)(ws + p.ecol_off);
+    float* eval = (float*)(ws + p.eval_off);
+    uint32_t* eoff = (uint32_t*)(ws + p.eoff_off);
+    int32_t* slab_first = (int32_t*)(ws + p.first_off);
+
+    // preparation: entries -> (position in slab, value); per (slab, stored row) entry ranges
+    if (unsorted_flag) CHR_CUDA(cudaMemsetAsync(unsorted_flag, 0, sizeof(int32_t), st));
+    lattice_csr_entries_kernel<<<kNumSMs * 8, 256, 0, st>>>(indptr, indices, data, n_spots, gene_col, scale, apply_log1p, ecol, eval, unsorted_flag);
+    lattice_csr_slab_first_kernel<<<(unsigned)ceil_div<int64_t>(n_genes_all, 256), 256, 0, st>>>(gene_col, n_genes_all, p.n_slabs, slab_first);
+    lattice_csr_offsets_kernel<<<(unsigned)ceil_div<int64_t>(n_rows, kOffWarps), 32 * kOffWarps, 0, st>>>(indptr, indices, spot_of_row, n_rows,
+                                                                                                     slab_first, p.n_slabs + 1, eoff);
+    lattice_csr_pilot_kernel<<<p.n_slabs, 32 * kPilotWarps, 0, st>>>(eoff, ecol, eval, p.n_slabs + 1, pilot_rows, n_pilot, pilot);
+    CHR_LAUNCH_CHECK();
+
+    const int64_t ncol = round_up<int64_t>(n_keep, 4);
+    LatSrc src{};
+    src.eoff = eoff;
+    src.ecol = ecol;
+    src.eval = eval;
+    src.n_slabs1 = p.n_slabs + 1;
+    dim3 grid((unsigned)p.lat.ntile, (unsigned)n_chunks);
+    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+    timer_begin(CHR_FAMILY_MORAN, timing, st);
+    moran_lattice_kernel<true, true><<<grid, kLatCsrThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot,
+                                                                           part, p.lat.gpad);
+    timer_end(CHR_FAMILY_MORAN, timing, st);
+    CHR_LAUNCH_CHECK();
+    if (p.lat.ncorr_split > 0) {
+        dim3 gc((unsigned)p.lat.ntile, (unsigned)p.lat.ncorr_split);
+        moran_lattice_csr_corr_kernel<<<gc, 32 * kCorrWarps, 0, st>>>(eoff, ecol, eval, p.n_slabs + 1, (const int4*)corr, n_corr, pilot, part,
+                                                                      p.lat.gpad, n_chunks);
+        CHR_LAUNCH_CHECK();
+    }
+    return launch_moran_finalize(part, p.lat.nsplit, p.lat.gpad, n_keep, n_spots, k, pilot, geary, out_I, out_C, out_stats, st);
+}
 
 size_t chr_moran_lattice_workspace_bytes(int64_t n_genes, int n_chunks, int64_t n_corr) {
     if (n_genes <= 0 || n_chunks <= 0 || n_corr < 0) return 256;
@@ -391,13 +763,16 @@ int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld,
     }
     const uint32_t rb = (uint32_t)(ld * 4);
     dim3 grid((unsigned)p.ntile, (unsigned)n_chunks);
+    LatSrc src{};
+    src.X = X;
+    src.row_bytes = rb;
     timer_begin(CHR_FAMILY_MORAN, timing, st);
     if (preshifted) {
-        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
-        moran_lattice_kernel<false><<<grid, kLatThreads, kLatSmem, st>>>(X, rb, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+        moran_lattice_kernel<false, false><<<grid, kLatThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
     } else {
-        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
-        moran_lattice_kernel<true><<<grid, kLatThreads, kLatSmem, st>>>(X, rb, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+        moran_lattice_kernel<true, false><<<grid, kLatThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
     }
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();

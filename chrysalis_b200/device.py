@@ -687,6 +687,32 @@ def moran_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None
     return out_I, out_C, stats
 
 
+def moran_lattice_csr(csr: DeviceCSR, gene_col: torch.Tensor, n_keep: int, scale: torch.Tensor | None, plan: LatticePlan,
+                      apply_log1p: bool, geary: bool = False, timing: bool = False, want_stats: bool = False):
+    """Moran's I (and Geary's C) of the kept genes straight from the device CSR counts (``chr_moran_lattice_csr_f32``): the
+    column map of the gene filter, the per-spot scale, log1p and the densification are fused into the stencil kernel's
+    producers; no dense matrix is built.  ``csr`` in spot order (the order ``plan`` was built for), columns sorted inside
+    every row.  Returns ``(I, C, stats, unsorted)``: ``unsorted`` is a device int32 that is 1 when a row was not sorted -
+    the caller must then discard the results and take the dense path."""
+    n, g_all = csr.shape
+    assert n == plan.n and gene_col.dtype == torch.int32 and gene_col.numel() == g_all
+    nnz = csr.indices.numel()
+    n_chunks, n_corr = plan.chunks.shape[0], plan.corr.shape[0]
+    sor, _ = plan.maps()
+    flags = (_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0)
+    ws_bytes = _lib.query("chr_moran_lattice_csr_workspace_bytes", nnz, plan.n_rows, n_keep, n_chunks, n_corr)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=csr.data.device)
+    out_I = torch.empty(n_keep, dtype=torch.float64, device=csr.data.device)
+    out_C = torch.empty(n_keep, dtype=torch.float64, device=csr.data.device) if geary else None
+    stats = torch.empty((4, n_keep), dtype=torch.float64, device=csr.data.device) if want_stats else None
+    unsorted = torch.zeros(1, dtype=torch.int32, device=csr.data.device)
+    _lib.call("chr_moran_lattice_csr_f32", _ptr(csr.indptr), _ptr(csr.indices), _ptr(csr.data), nnz, n, g_all, _ptr(gene_col), n_keep,
+              _ptr(scale), int(apply_log1p), plan.n_rows, plan.k, _ptr(plan.bands), plan.bands.shape[0], _ptr(plan.chunks), n_chunks,
+              _ptr(plan.corr) if n_corr else 0, n_corr, _ptr(sor), _ptr(plan.pilot_rows), plan.pilot_rows.numel(), flags, _ptr(out_I),
+              _ptr(out_C), _ptr(stats), _ptr(unsorted), _ptr(ws), ws_bytes, _stream())
+    return out_I, out_C, stats, unsorted
+
+
 def perm_seed(seed: int | None) -> int:
     """64-bit key of the device's counter-based permutations (``csrc/perm.cuh``); ``None`` draws fresh entropy.  torch's and
     numpy's global RNG states are never touched."""

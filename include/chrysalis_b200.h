@@ -179,6 +179,24 @@ int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld,
                           const int32_t* pilot_rows, int n_pilot, unsigned flags, double* out_I, double* out_C,
                           double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream);
 
+/* The same statistic fed from the CSR COUNTS instead of a dense matrix (north_star: "streams the spots x genes expression
+ * matrix (CSR counts or dense log1p)"): fuses filter_genes' column map, normalize_total's per-spot scale, log1p and
+ * ad.to_df() (core.py:53-59) into the Moran kernel's producer - the tiles are built in shared memory from the stored
+ * entries, no dense matrix exists, HBM sees ~5 bytes per stored entry instead of 4 bytes per spot and gene.
+ * indptr / indices / data: device CSR in SPOT order with sorted column indices inside every row, nnz < 2^32;
+ * gene_col [n_genes_all]: new column of a kept gene or -1; scale [n_spots] float64 or NULL; apply_log1p as in
+ * chr_csr_densify_log1p.  Lattice tables as chr_moran_lattice_f32 plus spot_of_row [n_rows] (-1 = absent node).
+ * unsorted_flag (device int32, may be NULL): set to 1 when a row's columns are not strictly increasing - the results are
+ * then meaningless and the caller must take the dense path (checked while the entries are prepared, no extra pass). */
+size_t chr_moran_lattice_csr_workspace_bytes(int64_t nnz, int64_t n_rows, int64_t n_keep, int n_chunks, int64_t n_corr);
+int chr_moran_lattice_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t nnz,
+                              int64_t n_spots, int64_t n_genes_all, const int32_t* gene_col, int64_t n_keep,
+                              const double* scale, int apply_log1p, int64_t n_rows, int k, const int32_t* bands,
+                              int n_bands, const int32_t* chunks, int n_chunks, const int32_t* corr, int64_t n_corr,
+                              const int32_t* spot_of_row, const int32_t* pilot_rows, int n_pilot, unsigned flags,
+                              double* out_I, double* out_C, double* out_stats, int32_t* unsorted_flag,
+                              void* workspace, size_t workspace_bytes, chr_stream_t stream);
+
 /* ---- K3p: permutation inference ------------------------------------------------------------
  * replaces  esda.moran.Moran(y, w, permutations=P)'s simulation (np.random.permutation(z), P times per gene;
  *           /root/reference/article/A2_human_lymph_node/morans_i.ipynb:186; core.py:72 hard-codes permutations=0)

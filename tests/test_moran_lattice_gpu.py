@@ -163,14 +163,122 @@ def test_detect_svgs_takes_the_lattice_path_and_matches_the_oracle(monkeypatch):
     X, _ = synth.make_counts_csr(xy, 260, n_zones=5, seed=11)
     ref = osvg.detect_svgs(X, xy, neighbors=8, top_svg=50, min_morans=0.05, geary=True)
     calls = []
-    real = dv.moran_lattice
-    monkeypatch.setattr(dv, "moran_lattice", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    real, real_csr = dv.moran_lattice, dv.moran_lattice_csr
+    monkeypatch.setattr(dv, "moran_lattice", lambda *a, **k: (calls.append("dense"), real(*a, **k))[1])
+    monkeypatch.setattr(dv, "moran_lattice_csr", lambda *a, **k: (calls.append("csr"), real_csr(*a, **k))[1])
+    monkeypatch.setenv("CHR_MORAN_CSR", "0")                              # the dense-matrix flavour of the stencil kernel
     ad = ch.AnnDataLite(X, obsm={"spatial": xy})
     ch.detect_svgs(ad, neighbors=8, top_svg=50, min_morans=0.05, geary=True)
-    assert calls, "the stencil kernel was not used"
+    assert calls == ["dense"], "the stencil kernel was not used"
     m = ref["gene_mask"]
     got = ad.var["Moran's I"].to_numpy()
     assert np.array_equal(np.isnan(got), ~m)
     assert_close(got[m], ref["morans"][m])
     assert_close(ad.var["Geary's C"].to_numpy()[m], ref["geary"][m], what="C")
     assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+
+
+# ---- the same kernel fed from the CSR counts (chr_moran_lattice_csr_f32): no dense matrix ------------------------------
+
+def _csr_case(xy, g, seed, density=0.08):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = len(xy)
+    lam = density * (1.0 + 2.0 * (np.sin(xy[:, :1] / 600.0) > 0) * (rng.uniform(0, 1, g)[None] > 0.6))
+    counts = rng.poisson(lam * rng.gamma(2.0, 1.0, (1, g))).astype(np.float32)
+    counts[:, ::17] = 0                                                   # genes the filter drops
+    counts[rng.integers(0, n, 30), rng.integers(0, g, 30)] += 400          # a few large counts
+    return sp.csr_matrix(counts)
+
+
+@pytest.mark.parametrize("shape", ["rect", "blob"])
+@pytest.mark.parametrize("logged", [False, True])
+def test_csr_fed_kernel_matches_oracle_and_dense_path(shape, logged):
+    xy = square_blob(110, 4) if shape == "blob" else synth.make_coords("square", 75 * 131, seed=2)      # 131 rows: 3 bands, last short
+    n, g = len(xy), 300
+    X = _csr_case(xy, g, 5)
+    nbr = ow.knn_neighbors(xy, 8)
+    plan, _ = lattice_case(xy, nbr)
+    csr = dv.upload_csr(X)
+    min_cells = int(0.03 * n)
+    gene_nnz = dv.csr_gene_nnz(csr)
+    keep = gene_nnz >= min_cells
+    gene_col = torch.where(keep, torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(gene_nnz, -1))
+    n_keep = int(keep.sum())
+    assert 0 < n_keep < g
+    scale = None if logged else dv.median_scale(dv.csr_spot_totals(csr, gene_col))
+    if logged:                                                           # the caller already normalised: values are used as they are
+        Xl = osvg.normalize_total_log1p(X[:, keep.cpu().numpy()])
+        Xfull = X.copy().astype(np.float32)
+        csr = dv.upload_csr(osvg.normalize_total_log1p(X))
+        dense_ref = np.asarray(osvg.normalize_total_log1p(X)[:, keep.cpu().numpy()].todense(), dtype=np.float32)
+    else:
+        dense_ref = np.asarray(osvg.normalize_total_log1p(X[:, keep.cpu().numpy()]).todense(), dtype=np.float32)
+    I, C, st, unsorted = dv.moran_lattice_csr(csr, gene_col, n_keep, scale, plan, apply_log1p=not logged, geary=True, want_stats=True)
+    assert int(unsorted.item()) == 0
+    I, C = I.cpu().numpy(), C.cpu().numpy()
+    assert_close(I, om.morans_I_batched(dense_ref, nbr))
+    assert_close(C, om.gearys_C_batched(dense_ref, nbr), what="C")
+    assert np.allclose(st[0].cpu().numpy(), dense_ref.astype(np.float64).mean(0), rtol=1e-6, atol=1e-9)
+    # the dense path on the same counts: the two differ only in the pilot sample's summation order
+    dense = torch.zeros((plan.n_rows, dv.dense_ld(n_keep)), dtype=torch.float32, device="cuda")
+    dv.csr_densify(csr, gene_col, n_keep, scale, plan.row_of_spot, apply_log1p=not logged, out=dense)
+    I2, C2, _ = dv.moran_lattice(dense, plan, n_keep, geary=True)
+    assert_close(I, I2.cpu().numpy())                                     # two float32 evaluations with different shift vectors
+    assert_close(C, C2.cpu().numpy(), what="C")
+    again = dv.moran_lattice_csr(csr, gene_col, n_keep, scale, plan, apply_log1p=not logged, geary=True)
+    assert np.array_equal(again[0].cpu().numpy(), I)                      # run-to-run bit reproducible
+
+
+def test_csr_fed_kernel_many_slabs_ragged_and_gene_shards():
+    """More than one gene slab, a ragged last slab, and gene shards of the same matrix give the same bits."""
+    xy = synth.make_coords("square", 64 * 70, seed=6)
+    n, g = len(xy), 450
+    X = _csr_case(xy, g, 9, density=0.12)
+    nbr = ow.knn_neighbors(xy, 8)
+    plan, _ = lattice_case(xy, nbr)
+    dense_all = np.asarray(X.todense(), dtype=np.float32)
+
+    def run(lo, hi):
+        csr = dv.upload_csr(X[:, lo:hi].tocsr())
+        gene_col = torch.arange(hi - lo, dtype=torch.int32, device="cuda")
+        I, _, _, uns = dv.moran_lattice_csr(csr, gene_col, hi - lo, None, plan, apply_log1p=True)
+        assert int(uns.item()) == 0
+        return I.cpu().numpy()
+
+    keep = np.flatnonzero(np.log1p(dense_all).std(0) > 0)
+    I = run(0, g)
+    assert_close(I[keep], om.morans_I_batched(np.log1p(dense_all[:, keep]), nbr))
+    for lo, hi in ((0, 128), (128, 450), (200, 333)):
+        assert np.array_equal(run(lo, hi), I[lo:hi], equal_nan=True), f"gene shard [{lo}, {hi}) differs bitwise"
+
+
+def test_detect_svgs_is_fed_from_csr_on_lattices_and_falls_back_when_unsorted(monkeypatch):
+    import chrysalis_b200 as ch
+    import scipy.sparse as sp
+    xy = square_blob(70, 11)
+    X, _ = synth.make_counts_csr(xy, 260, n_zones=5, seed=11)
+    ref = osvg.detect_svgs(X, xy, neighbors=8, top_svg=50, min_morans=0.05, geary=True)
+    calls = {"csr": 0, "dense": 0}
+    real_csr, real_dense = dv.moran_lattice_csr, dv.moran_lattice
+    monkeypatch.setattr(dv, "moran_lattice_csr", lambda *a, **k: (calls.__setitem__("csr", calls["csr"] + 1), real_csr(*a, **k))[1])
+    monkeypatch.setattr(dv, "moran_lattice", lambda *a, **k: (calls.__setitem__("dense", calls["dense"] + 1), real_dense(*a, **k))[1])
+
+    def check(Xin, expect):
+        before = dict(calls)
+        ad = ch.AnnDataLite(Xin, obsm={"spatial": xy})
+        ch.detect_svgs(ad, neighbors=8, top_svg=50, min_morans=0.05, geary=True)
+        assert {k: calls[k] - before[k] for k in calls} == expect
+        m = ref["gene_mask"]
+        got = ad.var["Moran's I"].to_numpy()
+        assert np.array_equal(np.isnan(got), ~m)
+        assert_close(got[m], ref["morans"][m])
+        assert_close(ad.var["Geary's C"].to_numpy()[m], ref["geary"][m], what="C")
+        assert np.array_equal(ad.var["spatially_variable"].to_numpy(), ref["spatially_variable"])
+
+    check(X, {"csr": 1, "dense": 0})
+    # the same matrix with the entries of every row reversed: a legal CSR, not sorted -> flagged on the device, dense path
+    rev = np.concatenate([np.arange(X.indptr[i + 1] - 1, X.indptr[i] - 1, -1) for i in range(X.shape[0])])
+    Xu = sp.csr_matrix((X.data[rev], X.indices[rev], X.indptr), shape=X.shape)
+    assert not Xu.has_sorted_indices
+    check(Xu, {"csr": 1, "dense": 1})
