@@ -489,6 +489,8 @@ def run_native(args):
             return dv.moran_lattice(X, lat, g_sc, timing=timing)
         return dv.moran_dense(X, nbr_rows, g_sc, timing=timing, variant=variant, plan=plan)
 
+    state = {}
+
     def measure(X, g_sc):
         """Device-timed resident throughput: K steps bracketed by barrier + synchronize, max over ranks."""
         counts = torch.tensor([g_sc], device="cuda")
@@ -501,10 +503,21 @@ def run_native(args):
         g_max, g_tot = max(sizes), sum(sizes)
         padded = torch.zeros(g_max, dtype=torch.float64, device="cuda")
         gathered = [torch.empty(g_max, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+        # the one exchange of the path (per-gene statistics): written into the peers' buffers over NVLink by one kernel
+        # (chr_p2p_allgather_f64) when symmetric memory is available, NCCL all-gather otherwise (CHR_BENCH_NCCL=1 forces it)
+        peer = dd.PeerGather.create(g_max) if (world > 1 and os.environ.get("CHR_BENCH_NCCL", "0") != "1") else None
+        ok = torch.tensor([1 if peer is not None else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)                  # every rank or none
+            if not int(ok.item()):
+                peer = None
+        state["collective"] = "none" if world == 1 else ("peer-memory writes (chr_p2p_allgather_f64)" if peer is not None else "nccl all_gather")
 
         def step(timing=False):
             I, _, _ = moran(X, g_sc, timing)
-            if world > 1:                                             # the one exchange of the path: per-gene statistics
+            if peer is not None:
+                state["gathered"] = peer.gather(I, g_sc)
+            elif world > 1:
                 padded[:g_sc] = I
                 dist.all_gather(gathered, padded)
             return I
@@ -537,7 +550,11 @@ def run_native(args):
         for _ in range(min(args.steps, 10)):
             moran(X, g_sc, True)
             kms.append(dv.last_kernel_ms(_lib.FAMILY_MORAN))
-        return dict(I=I, g_tot=g_tot, ms_per_step=total_ms / args.steps, kernel_ms=float(np.mean(kms)), clocks=clocks)
+        if peer is not None:                                          # what arrived from the peers is what they computed
+            got = state["gathered"][rank, :g_sc]
+            assert torch.equal(got, I), "peer-memory all-gather returned other values than this rank computed"
+        return dict(I=I, g_tot=g_tot, ms_per_step=total_ms / args.steps, kernel_ms=float(np.mean(kms)), clocks=clocks,
+                    collective=state["collective"])
 
     weak_rec = None
     if strong and not args.no_weak:
@@ -604,7 +621,7 @@ def run_native(args):
         "scaling": scaling if world > 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(n, g, k), "n_spots": n, "genes": m["g_tot"], "genes_per_gpu": g_sc, "neighbors": k,
                    "ld": ld, "rows_resident": int(X.shape[0]), "counts_density": round(density, 4),
-                   "parallelism": f"gene-shard x{world}" + ("" if world == 1 else f" ({scaling} scaling; all-gather of per-gene statistics timed)"),
+                   "parallelism": f"gene-shard x{world}" + ("" if world == 1 else f" ({scaling} scaling; all-gather of per-gene statistics timed: {m['collective']})"),
                    "layout": "lattice layout (60-row bands), stencil kernel" if lat is not None else "Hilbert row order, quad plan of W",
                    "l2_policy": "inputs_exceed_l2 (X = %.1f GB per GPU >> 126 MB L2)" % (4.0 * X.shape[0] * ld / 1e9),
                    "variant": args.variant, "setup_s": round(setup_s, 1)},

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "chr_moran_blockdiag_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "chr_moran_blockdiag_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, c_int, _P, _P, c_int, _P, c_int64, c_uint, _P, _P, _P,
                                         c_size_t, _P]),
+    "chr_p2p_allgather_f64": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int64, c_int, c_uint, _P]),
     "chr_perm_row_map": (c_int, [c_int64, ctypes.c_uint64, c_int, _P, _P]),
     "chr_moran_perm_lattice_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int64, c_int]),
     "chr_moran_perm_lattice_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int, _P, c_int, _P, c_int64, _P, c_int64, _P,

@@ -219,6 +219,17 @@ int chr_moran_perm_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_
                                double* out_I, int64_t* out_larger, double* out_sum, double* out_sumsq,
                                void* workspace, size_t workspace_bytes, chr_stream_t stream);
 
+/* ---- multi-GPU: all-gather of the per-gene statistics through peer memory -----------------------
+ * The one exchange of the gene-sharded Moran path ("a small all-gather of per-gene statistics over NVLink").
+ * peer_bufs_dev / signal_pads_dev: device arrays [world] of the peers' receive buffers / uint32 signal pads (a symmetric
+ * allocation mapped into every process, e.g. torch.distributed._symmetric_memory).  Every rank writes `count` doubles of
+ * `local` to element offset dst_elem0 of EVERY peer's buffer, raises slot signal_slot0 + rank of every peer's pad to
+ * `epoch` (non-zero, increasing per call) and waits until its own pad shows `epoch` from every peer.  One launch; ranks must
+ * sit on different GPUs. */
+int chr_p2p_allgather_f64(const double* local, int64_t count, void* const* peer_bufs_dev, void* const* signal_pads_dev,
+                          int rank, int world, int64_t dst_elem0, int signal_slot0, uint32_t epoch,
+                          chr_stream_t stream);
+
 /* ---- Local Moran's I (LISA) ---------------------------------------------------------------
  * replaces  esda.moran.Moran_Local(y, w, transformation='r', permutations=P)
  *           (/root/reference/article/A2_human_lymph_node/morans_i.ipynb:150; not called by core.py)
