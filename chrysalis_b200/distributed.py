@@ -107,7 +107,6 @@ class PeerGather:
             import torch.distributed._symmetric_memory as symm
 
             group = dist.group.WORLD
-            symm.enable_symm_mem_for_group(group.group_name)
             buf = symm.empty(2 * size * int(max_elems), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
             handle = symm.rendezvous(buf, group)
             if handle.signal_pad_size < 4 * (PeerGather.SIGNAL_SLOT0 + 2 * size):
