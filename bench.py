@@ -377,11 +377,16 @@ def gram_sharded(args, rank, world, torch, dist, dv, dd, _lib):
     Device-timed per part with CUDA events, max over ranks."""
     n, S, r = args.n, min(args.svgs, args.g - 1), args.pcs
     lo, hi = dd.shard_range(n, rank, world)
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    P = torch.empty((hi - lo, dv.dense_ld(S)), dtype=torch.float32, device="cuda")
-    P.uniform_(0.0, 1.0, generator=gen)
-    P = torch.where(P > 0.8, torch.log1p(8.0 * (P - 0.8)), torch.zeros_like(P))      # sparse log1p-like values
-    P[:, :64] += torch.linspace(0, 1, hi - lo, device="cuda")[:, None] * (rank + 1) / world
+    # synthetic SVG matrix with the structure of the real one: a dozen smooth factors + sparse log1p-like noise (a flat
+    # spectrum would make the Lanczos solver run to its depth cap, which real data never does)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    V = torch.rand((12, dv.dense_ld(S)), device="cuda", generator=gen)
+    gen.manual_seed(5678 + rank)
+    t = torch.linspace(lo / n, hi / n, hi - lo, device="cuda")[:, None] * torch.arange(1, 13, device="cuda")[None, :]
+    U = torch.sin(6.28318 * t) ** 2
+    P = torch.rand((hi - lo, dv.dense_ld(S)), device="cuda", generator=gen)
+    P = torch.where(P > 0.8, torch.log1p(8.0 * (P - 0.8)), torch.zeros_like(P)) + 0.05 * (U @ V)
+    del U, V, t
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
