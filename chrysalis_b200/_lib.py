@@ -75,7 +75,7 @@ _SIGNATURES = {
     "chr_moran_lattice_csr_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int, c_int64, c_int, _P, c_int, _P, c_int,
                                           _P, c_int64, _P, _P, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
     "chr_moran_lattice_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
-    "chr_moran_lattice_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int, _P, c_int, _P, c_int64, _P, c_int64, _P,
+    "chr_moran_lattice_f32": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int, _P, c_int, c_int, _P, c_int, _P, c_int64, _P, c_int64, _P,
                                       c_int, c_uint, _P, _P, _P, _P, c_size_t, _P]),
     "chr_moran_dense_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_int, _P, c_uint, _P, _P, _P, _P, c_size_t, _P]),
 }

@@ -122,12 +122,22 @@ struct LatSrc {
 
 constexpr int kLatCsrProducers = kLatStages * kLatStageCols;      // 6: one producer warp per staged column
 constexpr int kLatCsrThreads = 32 * (kLatWarps + kLatCsrProducers);
+constexpr int kLatTmaThreads = 32 * (kLatWarps + 1);              // one producer warp: TMA boxes need no per-row instructions
 
-template <bool SHIFT, bool CSR>
-__global__ void __launch_bounds__(CSR ? kLatCsrThreads : kLatThreads, 1)
-moran_lattice_kernel(const LatSrc src, int ncol, const int4* __restrict__ bands, int n_bands,
+// the three boxes of the TMA producer over X [rows][ld]: a whole column of a full band (60 rows x 512 B), a column of the
+// short last band, a single row (the row below a band)
+struct LatMaps {
+    CUtensorMap full, last, row;
+};
+
+enum { kProdCpAsync = 0, kProdCsr = 1, kProdTma = 2 };
+
+template <bool SHIFT, int PROD>
+__global__ void __launch_bounds__(PROD == kProdCsr ? kLatCsrThreads : (PROD == kProdTma ? kLatTmaThreads : kLatThreads), 1)
+moran_lattice_kernel(const LatSrc src, const __grid_constant__ LatMaps maps, int ncol, const int4* __restrict__ bands, int n_bands,
                      const int4* __restrict__ chunks, const float* __restrict__ pilot, double* __restrict__ part, int64_t gpad) {
-    constexpr int kProducers = CSR ? kLatCsrProducers : kLatProducers;
+    constexpr bool CSR = PROD == kProdCsr, TMA = PROD == kProdTma;
+    constexpr int kProducers = CSR ? kLatCsrProducers : (TMA ? 1 : kLatProducers);
     const float* __restrict__ X = src.X;
     const uint32_t row_bytes = src.row_bytes;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -141,8 +151,9 @@ moran_lattice_kernel(const LatSrc src, int ncol, const int4* __restrict__ bands,
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kLatStages; ++s) {
-            // dense: every producer thread arrives through its cp.async group; CSR: the 2 warps that build the stage's columns arrive
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(CSR ? 32 * kLatStageCols : 32 * kProducers) : "memory");
+            // cp.async: every producer thread arrives through its cp.async group; CSR: the 2 warps that build the stage's columns
+            // arrive; TMA: one expect_tx arrival + the producer warp's 32 cp.async arrivals (rows the boxes cannot deliver)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(CSR ? 32 * kLatStageCols : (TMA ? 33 : 32 * kProducers)) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(kLatWarps) : "memory");
         }
         mbar_fence_init();
@@ -254,7 +265,70 @@ moran_lattice_kernel(const LatSrc src, int ncol, const int4* __restrict__ bands,
         }
     }
 
-    if (!CSR && warp >= kLatWarps) {
+    if (TMA && warp >= kLatWarps) {
+        // ===== TMA producer: one box per column (cp.async.bulk.tensor.2d, 60 rows x 512 B), one box for the row below =====
+        // Rows no box can deliver - the pilot vector for columns / halo rows outside the stored range and for the rows past the
+        // end of a short band - are copied by the same warp with cp.async; both kinds of completion land on the stage's barrier.
+        const bool has_next = ch.x + 1 < n_bands;
+        int4 nb = make_int4(0, 0, 0, 0);
+        if (has_next) nb = __ldg(bands + ch.x + 1);
+        const char* pil = reinterpret_cast<const char*>(pilot + col);
+        const CUtensorMap* col_map = bd.w == kLatBH ? &maps.full : &maps.last;
+        if (lane == 0) { prefetch_tensormap(col_map); prefetch_tensormap(&maps.row); }
+        int sidx = 0;
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_iters; ++it) {
+            if (it >= kLatStages) lat_mbar_wait(empty_bar + 8 * sidx, phase ^ 1u);
+            const uint32_t st = smem0 + sidx * kLatStageBytes;
+            const uint32_t bar = full_bar + 8 * sidx;
+            // bytes the boxes of this stage will deliver
+            uint32_t tx = 0;
+#pragma unroll
+            for (int cc = 0; cc < kLatStageCols; ++cc) {
+                const int j = it * kLatStageCols + cc - 1;
+                if (j > ch.z) break;
+                const int xc = ch.y + j;
+                if (xc >= 0 && xc < bd.z) tx += (uint32_t)bd.w * kLatRowBytes;
+                if (has_next) {
+                    const int xn = bd.y + xc - nb.y;
+                    if (xn >= 0 && xn < nb.z) tx += kLatRowBytes;
+                }
+            }
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+#pragma unroll
+            for (int cc = 0; cc < kLatStageCols; ++cc) {
+                const int j = it * kLatStageCols + cc - 1;
+                if (j > ch.z) break;
+                const int xc = ch.y + j;
+                const bool valid = xc >= 0 && xc < bd.z;
+                const uint32_t dst = st + cc * kLatSegBytes;
+                int halo_row = -1;
+                if (has_next) {
+                    const int xn = bd.y + xc - nb.y;
+                    if (xn >= 0 && xn < nb.z) halo_row = nb.x + xn * nb.w;
+                }
+                if (lane == 0) {
+                    if (valid)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                                     "l"(col_map), "r"(bar), "r"(tile_col), "r"(bd.x + xc * bd.w) : "memory");
+                    if (halo_row >= 0)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst + bd.w * kLatRowBytes),
+                                     "l"(&maps.row), "r"(bar), "r"(tile_col), "r"(halo_row) : "memory");
+                }
+                // the rest of the column from the pilot vector
+                const int first_pilot = valid ? (halo_row >= 0 ? bd.w + 1 : bd.w) : 0;
+                for (int t = first_pilot; t < kLatSegRows; ++t) {
+                    if (!valid && t == bd.w && halo_row >= 0) continue;   // delivered by the row box
+                    lat_cp_async_16(dst + t * kLatRowBytes + lane * 16, pil, col_bytes);
+                }
+            }
+            lat_cp_async_mbar_arrive(bar);
+            if (++sidx == kLatStages) { sidx = 0; phase ^= 1u; }
+        }
+    }
+
+    if (PROD == kProdCpAsync && warp >= kLatWarps) {
         // ===== producer warps: stream the chunk's columns, two stages ahead of the compute warps =====
         const int pw = warp - kLatWarps;
         const bool has_next = ch.x + 1 < n_bands;
@@ -445,6 +519,22 @@ moran_lattice_corr_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
         }
         __syncthreads();
     }
+}
+
+// tensor map over X [rows][ld] float32 with a box of 128 genes x box_rows rows (no swizzle: a row of the box is the 512-byte
+// segment a warp reads with one ld.shared)
+static int make_lattice_map(CUtensorMap* m, const float* X, int64_t n_rows, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    CHR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not found");
+    CHR_REQUIRE(box_rows >= 1 && box_rows <= 256, "lattice tensor map: bad box height %d", box_rows);
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kGeneTile, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CHR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the lattice matrix", (int)r);
+    return 0;
 }
 
 // ---- CSR-fed variant: preparation, pilot, corrections ---------------------------------------------------------------
@@ -705,10 +795,11 @@ int chr_moran_lattice_csr_f32(const int64_t* indptr, const int32_t* indices, con
     src.eval = eval;
     src.n_slabs1 = p.n_slabs + 1;
     dim3 grid((unsigned)p.lat.ntile, (unsigned)n_chunks);
-    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, kProdCsr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+    LatMaps maps{};
     timer_begin(CHR_FAMILY_MORAN, timing, st);
-    moran_lattice_kernel<true, true><<<grid, kLatCsrThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot,
-                                                                           part, p.lat.gpad);
+    moran_lattice_kernel<true, kProdCsr><<<grid, kLatCsrThreads, kLatSmem, st>>>(src, maps, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks,
+                                                                               pilot, part, p.lat.gpad);
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();
     if (p.lat.ncorr_split > 0) {
@@ -726,7 +817,7 @@ size_t chr_moran_lattice_workspace_bytes(int64_t n_genes, int n_chunks, int64_t 
 }
 
 int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int64_t n_spots, int k, const int32_t* bands,
-                          int n_bands, const int32_t* chunks, int n_chunks, const int32_t* corr, int64_t n_corr,
+                          int n_bands, int last_band_rows, const int32_t* chunks, int n_chunks, const int32_t* corr, int64_t n_corr,
                           const int32_t* absent_rows, int64_t n_absent, const int32_t* pilot_rows, int n_pilot, unsigned flags,
                           double* out_I, double* out_C, double* out_stats, void* workspace, size_t workspace_bytes,
                           chr_stream_t stream) {
@@ -766,13 +857,28 @@ int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld,
     LatSrc src{};
     src.X = X;
     src.row_bytes = rb;
+    // default: TMA producer (one tensor-map box per staged column; needs the height of the last band, the only one that may
+    // be shorter than 60 rows); kernel variant 2 or last_band_rows == 0: the cp.async producer warps
+    CHR_REQUIRE(last_band_rows >= 0 && last_band_rows <= kLatBH, "chr_moran_lattice_f32: last_band_rows out of range (%d)", last_band_rows);
+    const bool use_tma = last_band_rows > 0 && ((flags >> CHR_VARIANT_SHIFT) & 0xffu) != 2u && !preshifted;
+    LatMaps maps{};
+    if (use_tma) {
+        if (int rc = make_lattice_map(&maps.full, X, n_rows, ld, kLatBH)) return rc;
+        if (int rc = make_lattice_map(&maps.last, X, n_rows, ld, last_band_rows)) return rc;
+        if (int rc = make_lattice_map(&maps.row, X, n_rows, ld, 1)) return rc;
+    }
     timer_begin(CHR_FAMILY_MORAN, timing, st);
     if (preshifted) {
-        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
-        moran_lattice_kernel<false, false><<<grid, kLatThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<false, kProdCpAsync>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+        moran_lattice_kernel<false, kProdCpAsync><<<grid, kLatThreads, kLatSmem, st>>>(src, maps, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
     } else {
-        CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
-        moran_lattice_kernel<true, false><<<grid, kLatThreads, kLatSmem, st>>>(src, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        if (use_tma) {
+            CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, kProdTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+            moran_lattice_kernel<true, kProdTma><<<grid, kLatTmaThreads, kLatSmem, st>>>(src, maps, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        } else {
+            CHR_CUDA(cudaFuncSetAttribute(moran_lattice_kernel<true, kProdCpAsync>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+            moran_lattice_kernel<true, kProdCpAsync><<<grid, kLatThreads, kLatSmem, st>>>(src, maps, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, pilot, part, p.gpad);
+        }
     }
     timer_end(CHR_FAMILY_MORAN, timing, st);
     CHR_LAUNCH_CHECK();

@@ -371,7 +371,7 @@ int chr_moran_perm_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_
     double* part = (double*)(ws + p.part_off);
     int32_t* maps = (int32_t*)(ws + p.maps_off);
     // the observed statistic (validates the arguments as well) + per-gene mean and z'z
-    const int rc = chr_moran_lattice_f32(X, n_rows, n_genes, ld, n_spots, k, bands, n_bands, chunks, n_chunks, corr, n_corr, absent_rows, n_absent,
+    const int rc = chr_moran_lattice_f32(X, n_rows, n_genes, ld, n_spots, k, bands, n_bands, 0, chunks, n_chunks, corr, n_corr, absent_rows, n_absent,
                                          pilot_rows, n_pilot, flags & ~(CHR_FLAG_GEARY | CHR_FLAG_TIMING), out_I, nullptr, stats, ws + p.lat_off,
                                          chr_moran_lattice_workspace_bytes(n_genes, n_chunks, n_corr), stream);
     if (rc) return rc;

@@ -518,6 +518,7 @@ class LatticePlan:
     absent: torch.Tensor       # int32 [n_absent]
     pilot_rows: torch.Tensor   # int32 [<= 512]
     lattice_shape: tuple       # (W, H) nodes
+    last_band_rows: int = 0    # lattice rows of the last band (the others have LATTICE_BAND_ROWS)
     _maps: tuple | None = None
 
     def maps(self):
@@ -663,24 +664,28 @@ def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None 
     absent = torch.nonzero(~present).squeeze(1).to(torch.int32).contiguous()
     ns = min(n, 512)
     pilot_rows = row_of_spot[(torch.arange(ns, device=xy.device) * n) // ns].to(torch.int32).contiguous()
-    return LatticePlan(row_of_spot, n_rows, n, k, bands, chunks, corr, absent, pilot_rows, shape)
+    last_rows = shape[1] - (bands.shape[0] - 1) * LATTICE_BAND_ROWS
+    return LatticePlan(row_of_spot, n_rows, n, k, bands, chunks, corr, absent, pilot_rows, shape, int(last_rows))
 
 
 def moran_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None, geary: bool = False, timing: bool = False,
-                  want_stats: bool = False, preshifted: bool = False):
+                  want_stats: bool = False, preshifted: bool = False, variant: int | None = None):
     """Moran's I (and Geary's C) of every column of ``X`` [plan.n_rows, ld] float32 in lattice layout.
     Returns ``(I, C, stats)`` like ``moran_dense``.  The filler rows of ``X`` (absent nodes) are overwritten."""
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1 and X.shape[0] == plan.n_rows
     ld = X.stride(0)
     g = X.shape[1] if n_genes is None else n_genes
-    flags = ((_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PRESHIFTED if preshifted else 0))
+    if variant is None:                                              # 0: TMA producer (default), 2: cp.async producer warps
+        variant = int(os.environ.get("CHR_LATTICE_VARIANT", "0"))
+    flags = ((_lib.FLAG_GEARY if geary else 0) | (_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PRESHIFTED if preshifted else 0) |
+             (variant << _lib.VARIANT_SHIFT))
     n_chunks, n_corr = plan.chunks.shape[0], plan.corr.shape[0]
     ws_bytes = _lib.query("chr_moran_lattice_workspace_bytes", g, n_chunks, n_corr)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
     out_I = torch.empty(g, dtype=torch.float64, device=X.device)
     out_C = torch.empty(g, dtype=torch.float64, device=X.device) if geary else None
     stats = torch.empty((4, g), dtype=torch.float64, device=X.device) if want_stats else None
-    _lib.call("chr_moran_lattice_f32", _ptr(X), plan.n_rows, g, ld, plan.n, plan.k, _ptr(plan.bands), plan.bands.shape[0],
+    _lib.call("chr_moran_lattice_f32", _ptr(X), plan.n_rows, g, ld, plan.n, plan.k, _ptr(plan.bands), plan.bands.shape[0], plan.last_band_rows,
               _ptr(plan.chunks), n_chunks, _ptr(plan.corr) if n_corr else 0, n_corr, _ptr(plan.absent) if plan.absent.numel() else 0,
               plan.absent.numel(), _ptr(plan.pilot_rows), plan.pilot_rows.numel(), flags, _ptr(out_I), _ptr(out_C), _ptr(stats),
               _ptr(ws), ws_bytes, _stream())

@@ -169,12 +169,15 @@ int chr_moran_blockdiag_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t l
  * chunks: int32 [n_chunks][4] = {band, first column relative to the band's first stored column, columns, 0} (one CTA each)
  * corr:   int32 [n_corr][4]   = {row_i, row_j, coefficient as float bits, kind}; kind 0: x'Ax' += c x_i x_j,
  *                                kind 1: sum_j (indeg_j - k) x_j += c x_i  (column sums of A differ from k at the edges)
+ * last_band_rows: lattice rows of the last band (every other band has CHR_LATTICE_BAND_ROWS); with it the columns are
+ *   fetched by TMA (cp.async.bulk.tensor, one box per staged column); 0 = unknown: cp.async producer warps instead
+ *   (also selected by kernel variant 2 in `flags`).  Both give bit-identical results.
  * pilot_rows: int32 [n_pilot <= 512] matrix rows of present spots whose mean is the per-gene shift.
  * n_spots = number of present spots (the n of the statistic).  Outputs as chr_moran_dense_f32. */
 #define CHR_LATTICE_BAND_ROWS 60
 size_t chr_moran_lattice_workspace_bytes(int64_t n_genes, int n_chunks, int64_t n_corr);
 int chr_moran_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_t ld, int64_t n_spots, int k,
-                          const int32_t* bands, int n_bands, const int32_t* chunks, int n_chunks,
+                          const int32_t* bands, int n_bands, int last_band_rows, const int32_t* chunks, int n_chunks,
                           const int32_t* corr, int64_t n_corr, const int32_t* absent_rows, int64_t n_absent,
                           const int32_t* pilot_rows, int n_pilot, unsigned flags, double* out_I, double* out_C,
                           double* out_stats, void* workspace, size_t workspace_bytes, chr_stream_t stream);

@@ -282,3 +282,26 @@ def test_detect_svgs_is_fed_from_csr_on_lattices_and_falls_back_when_unsorted(mo
     Xu = sp.csr_matrix((X.data[rev], X.indices[rev], X.indptr), shape=X.shape)
     assert not Xu.has_sorted_indices
     check(Xu, {"csr": 1, "dense": 1})
+
+
+@pytest.mark.parametrize("shape", ["rect_short_last_band", "blob", "tiny_single_band"])
+def test_tma_producer_variant_is_bit_identical_to_the_cp_async_producers(shape):
+    """The default TMA producer (one cp.async.bulk.tensor box per staged column) and kernel variant 2 (cp.async producer
+    warps) deliver the same tiles: identical bits."""
+    if shape == "blob":
+        xy = square_blob(130, 8)
+    elif shape == "tiny_single_band":
+        xy = synth.make_coords("square", 30 * 30, seed=1)
+    else:
+        xy = synth.make_coords("square", 300 * 131, seed=2)[: 300 * 131]
+    n = len(xy)
+    rng = np.random.default_rng(5)
+    g = 200
+    dense = (np.log1p(rng.poisson(0.7, (n, g))) + np.sin(xy[:, :1] / 800.0) * rng.uniform(0, 1, g)[None]).astype(np.float32)
+    nbr = ow.knn_neighbors(xy, 8)
+    plan, _ = lattice_case(xy, nbr)
+    I0, C0, _ = gpu_lattice(dense, plan, geary=True, variant=2)
+    for ld in (dv.dense_ld(g), dv.dense_ld(g) + 96):
+        I1, C1, _ = gpu_lattice(dense, plan, geary=True, ld=ld, variant=0)
+        assert np.array_equal(I0, I1) and np.array_equal(C0, C1)
+    assert_close(I0, om.morans_I_batched(dense, nbr))
