@@ -104,10 +104,21 @@ def load():
     return lib
 
 
+_NVTX = os.environ.get("CHR_NVTX", "0") == "1"     # NVTX range around every C-ABI call (timeline tools)
+
+
 def call(name: str, *args):
     """Call a status-returning entry point; raise with the library's message on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(lib, name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.chr_last_error().decode("utf-8", "replace")
         raise ChrysalisNativeError(f"{name} failed (status {rc}): {msg}")

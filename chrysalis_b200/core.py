@@ -18,6 +18,32 @@ from . import device as dv
 from . import distributed as dd
 
 
+class _perf:
+    """``CHR_PERF=1``: wall seconds of a public call (device synchronised on both sides) stashed under
+    ``adata.uns['chr_perf'][stage]`` together with what the stage reports about itself."""
+
+    def __init__(self, adata, stage):
+        self.adata, self.stage, self.on = adata, stage, os.environ.get("CHR_PERF", "0") == "1"
+
+    def __enter__(self):
+        if self.on:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if self.on and exc_type is None:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            rec = {"seconds": time.perf_counter() - self.t0, "n_obs": int(self.adata.X.shape[0]), "n_vars": int(self.adata.X.shape[1])}
+            if torch.cuda.is_available():
+                rec["device"] = torch.cuda.get_device_name()
+                rec["peak_device_bytes"] = int(torch.cuda.max_memory_allocated())
+            self.adata.uns.setdefault("chr_perf", {})[self.stage] = rec
+        return False
+
+
 def _make_unique(names) -> pd.Index:
     """``AnnData.var_names_make_unique()`` (core.py:54): 2nd+ duplicates get '-1', '-2', ..."""
     names = pd.Index(names)
@@ -365,7 +391,11 @@ def detect_svgs(adata, min_spots: float = 0.05, top_svg: int = 1000, min_morans:
     :return: None; updates ``.var["Moran's I"]`` and ``.var["spatially_variable"]``.
     """
     assert 0 < min_spots < 1
+    with _perf(adata, "detect_svgs"):
+        _detect_svgs(adata, min_spots, top_svg, min_morans, neighbors, geary)
 
+
+def _detect_svgs(adata, min_spots, top_svg, min_morans, neighbors, geary):
     # Multi-GPU extension (no counterpart in the reference): under torch.distributed an AnnData flagged with
     # .uns['chr_gene_shard'] holds this rank's GENES only (all spots) - a loader that reads column ranges per rank.
     # Scores and the top_svg / min_morans rule are then global over the genes of all ranks; every rank writes its own .var.
@@ -502,7 +532,8 @@ def pca(adata, n_pcs: int = 50):
         'loadings' and 'features'.
     """
     sel = np.asarray(adata.var['spatially_variable'] == True)  # noqa: E712  (same test as core.py:126)
-    scores, components, ratio = pca_stage(adata.X, sel, n_pcs)
+    with _perf(adata, "pca"):
+        scores, components, ratio = pca_stage(adata.X, sel, n_pcs)
     adata.obsm['chr_X_pca'] = scores
 
     features = list(np.asarray(adata.var_names)[sel])
@@ -662,7 +693,8 @@ def aa(adata, n_archetypes: int = 8, pca_key: str = None, n_pcs: int = None, max
         emb = adata.obsm['chr_X_pca'][:, :pcs]
     else:
         emb = adata.obsm[pca_key][:, :pcs]
-    fit = aa_stage(np.asarray(emb), n_archetypes, max_iter=max_iter)
+    with _perf(adata, "aa"):
+        fit = aa_stage(np.asarray(emb), n_archetypes, max_iter=max_iter)
 
     adata.obsm['chr_aa'] = fit["alphas"]
 

@@ -78,7 +78,7 @@ class _FakeDevice:
         from oracle import moran as om, weights as ow
         self.om, self.ow = om, ow
 
-    from chrysalis_b200.device import DeviceCSR, PinnedCSR      # svg_stage only asks "is the input already pinned?"
+    from chrysalis_b200.device import CompactCSR, DeviceCSR, PinnedCSR      # svg_stage only asks "is the input already resident / pinned?"
 
     def upload_csr(self, X):
         import scipy.sparse as sp
