@@ -377,15 +377,17 @@ def gram_sharded(args, rank, world, torch, dist, dv, dd, _lib):
     Device-timed per part with CUDA events, max over ranks."""
     n, S, r = args.n, min(args.svgs, args.g - 1), args.pcs
     lo, hi = dd.shard_range(n, rank, world)
-    # synthetic SVG matrix with the structure of the real one: a dozen smooth factors + sparse log1p-like noise (a flat
-    # spectrum would make the Lanczos solver run to its depth cap, which real data never does)
+    # synthetic SVG matrix with the structure of the real one: smooth factors with a decaying spectrum (more of them than
+    # components asked for) + sparse log1p-like noise; a flat spectrum below the 12th component would make the Lanczos solver
+    # run to its depth cap, which real data never does
+    n_fac = max(2 * r, 40)
     gen = torch.Generator(device="cuda").manual_seed(1234)
-    V = torch.rand((12, dv.dense_ld(S)), device="cuda", generator=gen)
+    V = torch.randn((n_fac, dv.dense_ld(S)), device="cuda", generator=gen) * (0.85 ** torch.arange(n_fac, device="cuda"))[:, None]
     gen.manual_seed(5678 + rank)
-    t = torch.linspace(lo / n, hi / n, hi - lo, device="cuda")[:, None] * torch.arange(1, 13, device="cuda")[None, :]
-    U = torch.sin(6.28318 * t) ** 2
+    t = torch.linspace(lo / n, hi / n, hi - lo, device="cuda")[:, None] * torch.arange(1, n_fac + 1, device="cuda")[None, :]
+    U = torch.sin(6.28318 * t + torch.arange(n_fac, device="cuda")[None, :])
     P = torch.rand((hi - lo, dv.dense_ld(S)), device="cuda", generator=gen)
-    P = torch.where(P > 0.8, torch.log1p(8.0 * (P - 0.8)), torch.zeros_like(P)) + 0.05 * (U @ V)
+    P = torch.where(P > 0.8, torch.log1p(8.0 * (P - 0.8)), torch.zeros_like(P)) + 0.3 * (U @ V)
     del U, V, t
 
     def ev():
@@ -394,6 +396,8 @@ def gram_sharded(args, rank, world, torch, dist, dv, dd, _lib):
         return e
 
     def run():
+        dist.barrier()                                                # ranks start together: the first all-reduce measures the exchange, not skew
+        torch.cuda.synchronize()
         e0 = ev()
         sums = dv.column_sums(P, S)
         e1 = ev()
