@@ -586,8 +586,13 @@ def _aa_upload(X: np.ndarray) -> torch.Tensor:
     return dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
 
 
-def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: int, tol: float, random_state: int, init_rows=None):
-    """``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit`` on a device-resident embedding."""
+def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: int, tol: float, random_state: int, init_rows=None,
+                   restart_workers: int = None):
+    """``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit`` on a device-resident embedding.
+
+    The restarts are independent fits (their initial rows are drawn up front, so the RNG stream does not depend on them);
+    ``restart_workers`` host threads drive one CUDA stream each, so the launch gaps and the convergence read-backs of one
+    restart are covered by the kernels of the others.  Each restart is the same deterministic chain of launches either way."""
     n, d = Xd.shape
     if n_archetypes > MAX_ARCHETYPES or d > MAX_AA_DIMS:
         raise ValueError(f"aa: this implementation supports n_archetypes <= {MAX_ARCHETYPES} and <= {MAX_AA_DIMS} embedding "
@@ -617,9 +622,29 @@ def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: i
             rss_prev = rss
         return {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
 
+    workers = n_init if restart_workers is None else int(restart_workers)
+    if workers > 1 and len(used) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        device = Xd.device
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(device))          # Xd (and the seeding kernels) precede every restart
+
+        def on_own_stream(rows):
+            torch.cuda.set_device(device)
+            stream = torch.cuda.Stream(device=device)
+            stream.wait_event(ready)
+            with torch.cuda.stream(stream):
+                f = fit_restart(rows)
+            stream.synchronize()
+            return f
+
+        with ThreadPoolExecutor(max_workers=min(workers, len(used))) as pool:
+            fits = list(pool.map(on_own_stream, used))
+    else:
+        fits = [fit_restart(rows) for rows in used]
     best = None
-    for rows in used:                                           # first restart with the smallest RSS, as a sequential loop keeps it
-        f = fit_restart(rows)
+    for f in fits:                                              # first restart with the smallest RSS, as a sequential loop keeps it
         if best is None or f["rss"] < best["rss"]:
             best = f
     best["init_rows"] = used
@@ -653,7 +678,7 @@ def aa_sweep(X: np.ndarray, archetype_counts, max_iter: int = 10, n_init: int = 
         torch.cuda.set_device(device)
         stream = torch.cuda.Stream(device=device)
         with torch.cuda.stream(stream):
-            f = _aa_fit_device(Xd, a, max_iter, n_init, tol, random_state)
+            f = _aa_fit_device(Xd, a, max_iter, n_init, tol, random_state, restart_workers=1)
             p = f["alphas"] / f["alphas"].sum(1, keepdim=True)          # scipy.stats.entropy normalises, then -sum p log p
             ent = -(torch.where(p > 0, p * torch.log(p), torch.zeros_like(p))).sum(1)
             out = {"rss": f["rss"], "entropy": ent.cpu().numpy(), "n_iter": f["n_iter"]}

@@ -91,6 +91,9 @@ __device__ __forceinline__ void perm_step(uint32_t addr, bool accumulate, const 
 }
 
 // blockIdx.x = chunk + n_chunks * (draw inside the batch), blockIdx.y = gene slab (slowest: L2 reuse across the draws)
+// BULK: every gathered row travels as ONE 512-byte bulk copy (cp.async.bulk, the TMA engine's 1-D form: a lane issues the row it
+// resolved, completion is counted in bytes on the stage's mbarrier) instead of 32 lanes x 16-byte cp.async.
+template <bool BULK>
 __global__ void __launch_bounds__(kLatThreads, 1)
 moran_lattice_perm_kernel(const float* __restrict__ X, uint32_t row_bytes, int ncol, const int4* __restrict__ bands, int n_bands,
                           const int4* __restrict__ chunks, int n_chunks, const int32_t* __restrict__ maps, int64_t n_rows,
@@ -107,7 +110,7 @@ moran_lattice_perm_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kLatStages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(32 * kLatProducers) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s), "r"(BULK ? kLatProducers : 32 * kLatProducers) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_bar + 8 * s), "r"(kLatWarps) : "memory");
         }
         mbar_fence_init();
@@ -130,6 +133,10 @@ moran_lattice_perm_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
         int4 nb = make_int4(0, 0, 0, 0);
         if (has_next) nb = __ldg(bands + ch.x + 1);
         const char* pil = reinterpret_cast<const char*>(shift + col);
+        // BULK: whole-tile sources (the last slab of a matrix whose row stride is not a multiple of 128 floats is narrower)
+        const char* __restrict__ tile_base = reinterpret_cast<const char*>(X + tile_col);
+        const char* tile_pil = reinterpret_cast<const char*>(shift + tile_col);
+        const uint32_t tile_bytes = row_bytes - (uint32_t)tile_col * 4u < (uint32_t)kLatRowBytes ? row_bytes - (uint32_t)tile_col * 4u : (uint32_t)kLatRowBytes;
         constexpr int kRowsPerProducer = (kLatSegRows + kLatProducers - 1) / kLatProducers;
         static_assert(kRowsPerProducer <= 32, "one lane resolves one row of the column");
         // source row of the node this lane resolves (row pw + 4 * lane of column j of the chunk), -1 = neutral (shift vector)
@@ -157,6 +164,33 @@ moran_lattice_perm_kernel(const float* __restrict__ X, uint32_t row_bytes, int n
 #pragma unroll
             for (int cc = 0; cc < kLatStageCols; ++cc) src_nxt[cc] = resolve((it + 1) * kLatStageCols + cc - 1);
             if (it >= kLatStages) lat_mbar_wait(empty_bar + 8 * sidx, phase ^ 1u);
+            if constexpr (BULK) {
+                // lane l copies row t = pw + kLatProducers * l of every column of the stage: the row it resolved itself
+                const int t = pw + kLatProducers * lane;
+                const int my_rows = (kLatSegRows - pw + kLatProducers - 1) / kLatProducers;
+                const int j_first = it * kLatStageCols - 1;
+                const int ncols = ch.z - j_first + 1 < kLatStageCols ? ch.z - j_first + 1 : kLatStageCols;
+                const uint32_t bar = full_bar + 8 * sidx;
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(my_rows * ncols) * tile_bytes) : "memory");
+                __syncwarp();
+                if (t < kLatSegRows) {
+                    const uint32_t dst = smem0 + sidx * kLatStageBytes + t * kLatRowBytes;
+#pragma unroll
+                    for (int cc = 0; cc < kLatStageCols; ++cc) {
+                        if (cc >= ncols) break;
+                        const int srow = src_cur[cc];
+                        const char* q = srow >= 0 ? tile_base + (uint64_t)(uint32_t)srow * row_bytes : tile_pil;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + cc * kLatSegBytes),
+                                     "l"(q), "r"(tile_bytes), "r"(bar)
+                                     : "memory");
+                    }
+                }
+                if (++sidx == kLatStages) { sidx = 0; phase ^= 1u; }
+#pragma unroll
+                for (int cc = 0; cc < kLatStageCols; ++cc) src_cur[cc] = src_nxt[cc];
+                continue;
+            }
             const uint32_t st = smem0 + sidx * kLatStageBytes + lane * 16;
 #pragma unroll
             for (int cc = 0; cc < kLatStageCols; ++cc) {
@@ -380,7 +414,10 @@ int chr_moran_perm_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_
     CHR_LAUNCH_CHECK();
     const int64_t ncol = round_up<int64_t>(n_genes, 4);
     const uint32_t rb = (uint32_t)(ld * 4);
-    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+    // variant 2: 16-byte cp.async producers (the first design); default: one bulk copy per gathered row
+    const bool bulk = ((flags >> CHR_VARIANT_SHIFT) & 0xffu) != 2u && ld % 4 == 0;
+    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_perm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
+    CHR_CUDA(cudaFuncSetAttribute(moran_lattice_perm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatSmem));
     const bool timing = flags & CHR_FLAG_TIMING;
     timer_begin(CHR_FAMILY_MORAN, timing, st);
     for (int d0 = 0; d0 < permutations; d0 += p.batch) {
@@ -388,8 +425,12 @@ int chr_moran_perm_lattice_f32(float* X, int64_t n_rows, int64_t n_genes, int64_
         perm_maps_kernel<<<dim3((unsigned)ceil_div<int64_t>(n_rows, 256), (unsigned)nd), 256, 0, st>>>(spot_of_row, row_of_spot, n_rows,
                                                                                                       (uint32_t)n_spots, seed, (uint32_t)d0, maps);
         dim3 grid((unsigned)(n_chunks * nd), (unsigned)p.ntile);
-        moran_lattice_perm_kernel<<<grid, kLatThreads, kLatSmem, st>>>(X, rb, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks, n_chunks,
-                                                                       maps, n_rows, shift, part, p.nsplit, p.gpad);
+        if (bulk)
+            moran_lattice_perm_kernel<true><<<grid, kLatThreads, kLatSmem, st>>>(X, rb, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks,
+                                                                                 n_chunks, maps, n_rows, shift, part, p.nsplit, p.gpad);
+        else
+            moran_lattice_perm_kernel<false><<<grid, kLatThreads, kLatSmem, st>>>(X, rb, (int)ncol, (const int4*)bands, n_bands, (const int4*)chunks,
+                                                                                  n_chunks, maps, n_rows, shift, part, p.nsplit, p.gpad);
         if (p.ncorr_split > 0) {
             dim3 gc((unsigned)p.ntile, (unsigned)p.ncorr_split, (unsigned)nd);
             moran_lattice_perm_corr_kernel<<<gc, 32 * kCorrWarps, 0, st>>>(X, rb, (int)ncol, (const int4*)corr, n_corr, maps, n_rows, shift, part,

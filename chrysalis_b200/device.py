@@ -773,14 +773,18 @@ def moran_permutation_test(X: torch.Tensor, nbr: torch.Tensor, n_genes: int | No
 
 
 def moran_perm_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None = None, permutations: int = 999,
-                       seed: int | None = None, timing: bool = False):
+                       seed: int | None = None, timing: bool = False, variant: int | None = None):
     """The same inference on a square lattice (``chr_moran_perm_lattice_f32``): all P draws inside the library, batches of
-    draws per launch, the gene slab reused from L2 across the draws of a batch.  ``X`` in lattice layout."""
+    draws per launch, the gene slab reused from L2 across the draws of a batch.  ``X`` in lattice layout.
+    ``variant`` (env CHR_PERM_VARIANT): 0 = one bulk copy per gathered row (default), 2 = 16-byte cp.async producers."""
     assert X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1 and X.shape[0] == plan.n_rows
     ld = X.stride(0)
     g = X.shape[1] if n_genes is None else n_genes
     n_chunks, n_corr = plan.chunks.shape[0], plan.corr.shape[0]
     sor, ros = plan.maps()
+    if variant is None:
+        variant = int(os.environ.get("CHR_PERM_VARIANT", "0"))
+    flags = (_lib.FLAG_TIMING if timing else 0) | (variant << _lib.VARIANT_SHIFT)
     ws_bytes = _lib.query("chr_moran_perm_lattice_workspace_bytes", plan.n_rows, g, n_chunks, n_corr, int(permutations))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
     I = torch.empty(g, dtype=torch.float64, device=X.device)
@@ -790,7 +794,7 @@ def moran_perm_lattice(X: torch.Tensor, plan: LatticePlan, n_genes: int | None =
     _lib.call("chr_moran_perm_lattice_f32", _ptr(X), plan.n_rows, g, ld, plan.n, plan.k, _ptr(plan.bands), plan.bands.shape[0],
               _ptr(plan.chunks), n_chunks, _ptr(plan.corr) if n_corr else 0, n_corr, _ptr(plan.absent) if plan.absent.numel() else 0,
               plan.absent.numel(), _ptr(plan.pilot_rows), plan.pilot_rows.numel(), _ptr(sor), _ptr(ros), int(permutations),
-              perm_seed(seed) & (2 ** 64 - 1), _lib.FLAG_TIMING if timing else 0, _ptr(I), _ptr(larger), _ptr(s1), _ptr(s2), _ptr(ws), ws_bytes,
+              perm_seed(seed) & (2 ** 64 - 1), flags, _ptr(I), _ptr(larger), _ptr(s1), _ptr(s2), _ptr(ws), ws_bytes,
               _stream())
     return _perm_summary(I, larger, s1, s2, permutations)
 

@@ -170,3 +170,14 @@ def test_aa_properties_at_large_n():
     assert abs(rss2[-1] - rss[-1]) < 1e-6 * rss[-1]
     assert np.abs(st2.Z.cpu().numpy() - Z).max() < 1e-6 * np.abs(Z).max()
     assert np.abs(st2.alphas.cpu().numpy() - al[perm]).max() < 1e-6
+
+
+def test_concurrent_restarts_equal_sequential_restarts():
+    """The restarts of a fit run on their own streams; every one of them must be the launch chain a sequential loop makes."""
+    X = simplex_data(30_000, 12, 6, seed=5).astype(np.float64)
+    Xd = dv.to_device(X, torch.float64)
+    seq = core._aa_fit_device(Xd, 6, 25, 3, 0.001, 42, restart_workers=1)
+    par = core._aa_fit_device(Xd, 6, 25, 3, 0.001, 42)
+    assert all(np.array_equal(a, b) for a, b in zip(seq["init_rows"], par["init_rows"]))
+    assert seq["rss"] == par["rss"] and seq["n_iter"] == par["n_iter"]
+    assert torch.equal(seq["alphas"], par["alphas"]) and torch.equal(seq["archetypes"], par["archetypes"])

@@ -78,6 +78,23 @@ def test_lattice_permutation_kernel_is_exact_draw_by_draw(shape):
     assert np.array_equal(res["p_sim"], (larger + 1.0) / (P + 1.0))
 
 
+@pytest.mark.parametrize("g", [40, 200, 256])
+def test_bulk_copy_producer_is_bit_identical_to_the_cp_async_producers(g):
+    """Default producer (one 512-byte bulk copy per gathered row) against kernel variant 2 (16-byte cp.async): same staged
+    tiles, hence the same sums bit for bit; 200 genes leave a last slab narrower than 128 columns."""
+    xy = _blob(120, 9)
+    n = len(xy)
+    nbr = ow.knn_neighbors(xy, 8)
+    plan = dv.lattice_plan(torch.from_numpy(xy).cuda(), torch.from_numpy(nbr.astype(np.int32)).cuda())
+    assert plan is not None
+    Xd = torch.zeros((plan.n_rows, dv.dense_ld(g)), dtype=torch.float32, device="cuda")
+    Xd[plan.row_of_spot, :g] = torch.from_numpy(np.log1p(np.random.default_rng(2).poisson(1.1, (n, g))).astype(np.float32)).cuda()
+    a = dv.moran_perm_lattice(Xd.clone(), plan, g, permutations=19, seed=5, variant=0)
+    b = dv.moran_perm_lattice(Xd.clone(), plan, g, permutations=19, seed=5, variant=2)
+    for key in ("I", "p_sim", "EI_sim", "VI_sim", "z_sim"):
+        assert torch.equal(a[key], b[key]), key
+
+
 def test_general_path_uses_the_same_draws():
     """Hex lattice, k = 6 (quad-plan kernel + chr_perm_row_map): the same exact draw-by-draw parity."""
     xy = synth.make_coords("hex", 1300, seed=8)
