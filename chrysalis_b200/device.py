@@ -838,15 +838,18 @@ def column_sums(P: torch.Tensor, s: int) -> torch.Tensor:
     return out
 
 
-def gram_centered(P: torch.Tensor, s: int, mean: torch.Tensor, timing: bool = False) -> torch.Tensor:
-    """(P - mean)^T (P - mean) as float64 [s, s] (tcgen05, split-bf16 operands)."""
+def gram_centered(P: torch.Tensor, s: int, mean: torch.Tensor, timing: bool = False, variant: int | None = None) -> torch.Tensor:
+    """(P - mean)^T (P - mean) as float64 [s, s] (tcgen05, split-bf16 operands).  ``variant`` (env CHR_GRAM_VARIANT): 0 = 256 x 256
+    super-tile kernel (default), 2 = 128 x 128 tile kernel; both produce the same bits."""
     n, ld = P.shape[0], P.stride(0)
+    if variant is None:
+        variant = int(os.environ.get("CHR_GRAM_VARIANT", "0"))
     assert mean.dtype == torch.float64 and mean.numel() == s
     ws_bytes = _lib.query("chr_gram_workspace_bytes", n, s)
     ws = _workspace(ws_bytes, P.device)
     C = torch.empty((s, s), dtype=torch.float64, device=P.device)
-    _lib.call("chr_gram_centered_bf16x3", _ptr(P), n, s, ld, _ptr(mean), _ptr(C), _lib.FLAG_TIMING if timing else 0,
-              _ptr(ws), ws_bytes, _stream())
+    _lib.call("chr_gram_centered_bf16x3", _ptr(P), n, s, ld, _ptr(mean), _ptr(C),
+              (_lib.FLAG_TIMING if timing else 0) | (variant << _lib.VARIANT_SHIFT), _ptr(ws), ws_bytes, _stream())
     return C
 
 

@@ -47,6 +47,18 @@ def test_gram_matches_float64(n, s):
     assert np.abs(C - ref).max() / scale.max() > 0             # and it is not the fp64 reference itself
 
 
+@pytest.mark.parametrize("n,s", [(900, 64), (2000, 130), (9000, 300), (20000, 640), (4035, 1000)])
+def test_super_tile_gram_kernel_equals_the_tile_kernel_bit_for_bit(n, s):
+    """The 256 x 256 super-tile kernel (default) issues, per 128 x 128 tile, the same 16-spot MMA slices in the same order as
+    the tile kernel (variant 2): identical fp32 partials, identical fp64 sums.  300 columns = an odd number of 128-blocks
+    (half-empty last super-tile), 640 = several diagonal and off-diagonal super-tiles."""
+    X = to_dense_dev(synthetic_svg_matrix(n, s, seed=s))
+    mean = dv.column_sums(X, s) / n
+    a = dv.gram_centered(X, s, mean, variant=0)
+    b = dv.gram_centered(X, s, mean, variant=2)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("s,r", [(64, 12), (300, 20), (1000, 50)])
 def test_eigensolver_matches_lapack(s, r):
     rng = np.random.default_rng(s)
