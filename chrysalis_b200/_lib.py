@@ -34,6 +34,7 @@ _SIGNATURES = {
     "chr_last_kernel_ms": (c_float, [c_int]),
     "chr_host_threads": (c_int, []),
     "chr_host_upload": (c_int, [_P, _P, c_size_t, _P]),
+    "chr_host_download": (c_int, [_P, _P, c_size_t, _P]),
     "chr_host_csr_select_count": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "chr_host_csr_select_upload": (c_int, [_P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P]),
     "chr_knn_workspace_bytes": (c_size_t, [c_int64, c_int]),

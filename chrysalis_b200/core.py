@@ -138,9 +138,12 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     dense_buf = None
     # core.py:61-62  coordinates (x, -y): uploaded BEFORE the counts, otherwise this small copy queues behind the
     # multi-GB transfer on the copy engine and the side-stream work below cannot start until the upload has finished
-    pts = np.array(spatial, dtype=np.float64, copy=True)
-    pts[:, 1] = pts[:, 1] * -1
-    xy = dv.to_device(pts, torch.float64)
+    # (the sign flip of y happens on the device: the host makes no copy of the coordinates)
+    pts = np.asarray(spatial)
+    if pts.dtype.kind not in "fiu":
+        pts = pts.astype(np.float64)
+    xy = dv.upload_array(pts, torch.float64)
+    xy[:, 1].neg_()
     if side is not None:
         side.wait_stream(main)
     _mark(t0, "coords uploaded")
@@ -312,6 +315,17 @@ def svg_stage_multi(samples, min_spots: float, neighbors: int, geary: bool):
     return [results[b] for b in range(B)]
 
 
+class _UniqueNames:
+    """Stand-in for the names of all ranks when they are known to be distinct (only their count and uniqueness are used)."""
+    is_unique = True
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
 def _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary, all_names=None, offset=0):
     """The tail of ``detect_svgs`` (core.py:78-92) for one AnnData given the scored genes.
 
@@ -406,9 +420,20 @@ def _detect_svgs(adata, min_spots, top_svg, min_morans, neighbors, geary):
     # names of the filtered copy after var_names_make_unique (core.py:53-54)
     all_names, offset = None, 0
     if local_shard:
-        parts = dd.allgather_objects(list(adata.var_names))
-        all_names = pd.Index([v for part in parts for v in part])
-        offset = sum(len(part) for part in parts[:dd.world()[0]])
+        # the names themselves only matter when some are duplicated (var_names_make_unique renames): exchange one 64-bit
+        # hash per name (a fixed-size tensor all-gather) and fall back to the names when two hashes coincide
+        rank = dd.world()[0]
+        local = pd.Index(adata.var_names)
+        h = pd.util.hash_array(local.to_numpy(), categorize=False).view(np.int64)     # siphash of every name, same key on every rank
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        hashes, lens = dd.allgather_ragged(torch.from_numpy(h.copy()).to(dev), return_lens=True)
+        offset = int(sum(lens[:rank]))
+        hashes = hashes.cpu().numpy()
+        if np.unique(hashes).size != hashes.size:
+            parts = dd.allgather_objects(list(local))
+            all_names = pd.Index([v for part in parts for v in part])
+        else:
+            all_names = _UniqueNames(int(hashes.size))
     _write_svg_fields(adata, keep, I, C, top_svg, min_morans, geary, all_names=all_names, offset=offset)
 
 
@@ -582,8 +607,8 @@ def _aa_upload(X: np.ndarray) -> torch.Tensor:
     widening happens on the device, so half the bytes cross PCIe and the host never builds the float64 copy."""
     X = np.asarray(X)
     if X.dtype == np.float32:
-        return dv.to_device(np.ascontiguousarray(X), torch.float32).to(torch.float64)
-    return dv.to_device(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
+        return dv.upload_array(np.ascontiguousarray(X), torch.float64)
+    return dv.upload_array(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
 
 
 def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: int, tol: float, random_state: int, init_rows=None,

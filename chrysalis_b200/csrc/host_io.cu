@@ -6,6 +6,8 @@
 // points fill a ring of pinned bounce buffers with a pool of host threads and overlap the fill of chunk c + 1 with
 // the DMA of chunk c:
 //   chr_host_upload            any buffer, as is
+//   chr_host_download          the way back for the 10-100 MB results (PCA scores, AA proportions): DMA into the ring,
+//                              pool threads copy (and first-touch) the caller's fresh pageable array
 //   chr_host_csr_select_*      only the entries of selected columns (pca densifies the SVG columns, core.py:126):
 //                              count pass + pack pass, both multi-threaded; ~1/9 of the bytes cross PCIe at cfg4
 // The ring (4 x 32 MB, cudaHostAlloc'd once per process) and the thread pool are the only library-level state.
@@ -148,6 +150,44 @@ int chr_host_upload(void* dst_device, const void* src_host, size_t bytes, chr_st
             if (e > b) memcpy(buf + b, src + b, e - b);
         });
         if (int rc = ring_submit(s, (char*)dst_device + off, len, st)) return rc;
+    }
+    return 0;
+}
+
+// dst (pageable or pinned host) <- src (device).  Synchronous: returns when dst holds the data.  The copy of chunk c out of its
+// bounce buffer (all pool threads; a fresh numpy array is first-touched here, in parallel) overlaps the DMA of chunk c + 1.
+int chr_host_download(void* dst_host, const void* src_device, size_t bytes, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(bytes == 0 || (dst_host && src_device), "chr_host_download: null pointer argument");
+    std::lock_guard<std::mutex> lock(g_io.mu);
+    if (int rc = host_io_ready()) return rc;
+    const int nt = g_io.pool->size();
+    const size_t n_chunks = (bytes + kRingSlotBytes - 1) / kRingSlotBytes;
+    auto issue = [&](size_t c) -> int {
+        const int s = (int)(c % kRingSlots);
+        const size_t off = c * kRingSlotBytes, len = std::min(kRingSlotBytes, bytes - off);
+        if (int rc = ring_acquire(s)) return rc;                        // a pending upload out of this slot
+        CHR_CUDA(cudaMemcpyAsync(g_io.slot[s], (const char*)src_device + off, len, cudaMemcpyDeviceToHost, st));
+        CHR_CUDA(cudaEventRecord(g_io.ev[s], st));
+        g_io.busy[s] = true;
+        return 0;
+    };
+    for (size_t c = 0; c < n_chunks && c < (size_t)kRingSlots - 1; ++c)
+        if (int rc = issue(c)) return rc;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        if (c + kRingSlots - 1 < n_chunks)
+            if (int rc = issue(c + kRingSlots - 1)) return rc;          // its slot was drained in iteration c - 1
+        const int s = (int)(c % kRingSlots);
+        const size_t off = c * kRingSlotBytes, len = std::min(kRingSlotBytes, bytes - off);
+        if (int rc = ring_acquire(s)) return rc;                        // the DMA of this chunk has landed
+        const char* buf = g_io.slot[s];
+        char* dst = (char*)dst_host + off;
+        g_io.pool->run([&](int t) {
+            const size_t per = ((len + nt - 1) / nt + 4095) & ~(size_t)4095;
+            const size_t b = std::min(len, per * t), e = std::min(len, b + per);
+            if (e > b) memcpy(dst + b, buf + b, e - b);
+        });
     }
     return 0;
 }

@@ -29,6 +29,9 @@ def _ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+_BOUNCE_MIN_BYTES = 8 << 20
+
+
 def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
     """Host ndarray -> device tensor: a plain copy from pageable memory (about 11 GB/s on this box).  Pinning a fresh
     buffer first only pays when the pinned pool is already warm (the first cudaHostAlloc of a size costs 100-200 ms,
@@ -41,13 +44,18 @@ def to_device(a: np.ndarray, dtype=None) -> torch.Tensor:
 
 
 def to_host(t: torch.Tensor) -> np.ndarray:
-    """Device tensor -> fresh ndarray.  Copying into a numpy buffer is about twice as fast as ``t.cpu().numpy()`` for
-    the 10-100 MB results of this path (14 ms instead of 31 ms for the 67 MB alphas of cfg4)."""
+    """Device tensor -> fresh ndarray.  Results of 8 MB and more (67 MB of proportions, 84 MB of scores at cfg4) come back through
+    the library's pinned ring with all host threads copying out of it (``chr_host_download``): ``t.cpu().numpy()`` takes 31 ms for
+    the 67 MB, a copy into a numpy buffer 14 ms - most of it one thread first-touching the pages of the new array."""
     t = t.contiguous()
-    if t.numel() * t.element_size() < (1 << 20):
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 20):
         return t.cpu().numpy()
     out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
-    torch.from_numpy(out).copy_(t)
+    if nbytes >= _BOUNCE_MIN_BYTES and t.is_cuda:
+        _lib.call("chr_host_download", out.ctypes.data, t.data_ptr(), nbytes, _stream())
+    else:
+        torch.from_numpy(out).copy_(t)
     return out
 
 
@@ -77,7 +85,6 @@ class PinnedCSR:
         return sum(t.numel() * t.element_size() for t in (self.indptr, self.indices, self.data))
 
 
-_BOUNCE_MIN_BYTES = 8 << 20
 
 
 def upload_array(a: np.ndarray, dtype=None) -> torch.Tensor:

@@ -48,7 +48,7 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def allgather_ragged(t: torch.Tensor, n_total: int | None = None) -> torch.Tensor:
+def allgather_ragged(t: torch.Tensor, n_total: int | None = None, return_lens: bool = False):
     """Concatenate the 1-D / 2-D (rows) shards of every rank in rank order.
 
     Shards may differ in length (a gene count that does not divide by the world size, or a gene
@@ -56,13 +56,14 @@ def allgather_ragged(t: torch.Tensor, n_total: int | None = None) -> torch.Tenso
     to the longest one for the fixed-size all-gather."""
     rank, size = world()
     if size == 1:
-        return t
+        return (t, [int(t.shape[0])]) if return_lens else t
     if _host_backend(t):
-        return allgather_ragged(t.cpu(), n_total).to(t.device)
+        out = allgather_ragged(t.cpu(), n_total, return_lens)
+        return (out[0].to(t.device), out[1]) if return_lens else out.to(t.device)
     n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    lens = [torch.zeros_like(n_local) for _ in range(size)]
-    dist.all_gather(lens, n_local)
-    lens = [int(x.item()) for x in lens]
+    lens_t = torch.zeros(size, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(lens_t, n_local)
+    lens = [int(x) for x in lens_t.cpu()]                    # one read-back for all ranks' lengths
     m = max(lens)
     pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
@@ -71,7 +72,7 @@ def allgather_ragged(t: torch.Tensor, n_total: int | None = None) -> torch.Tenso
     out = torch.cat([p[:n] for p, n in zip(parts, lens)], dim=0)
     if n_total is not None and out.shape[0] != n_total:
         raise RuntimeError(f"all-gathered {out.shape[0]} items, expected {n_total}")
-    return out
+    return (out, lens) if return_lens else out
 
 
 def allgather_objects(obj) -> list:

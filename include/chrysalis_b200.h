@@ -51,6 +51,9 @@ float chr_last_kernel_ms(int family);
  * pointers; the calls return once the last chunk has been queued on `stream`. */
 int chr_host_threads(void);
 int chr_host_upload(void* dst_device, const void* src_host, size_t bytes, chr_stream_t stream);
+/* the way back for the large results (.obsm['chr_X_pca'], .obsm['chr_aa']; core.py:128,193): device -> host array through the
+ * same ring; synchronous (returns when dst_host holds the data), the pool threads first-touch a fresh destination in parallel */
+int chr_host_download(void* dst_host, const void* src_device, size_t bytes, chr_stream_t stream);
 /* column selection while uploading (pca densifies the SVG columns only, core.py:126; a rank's gene shard under
  * multi-GPU detect_svgs): col_map_host[c] = new column index or -1.  count: sel_indptr_host [n + 1] int64 and the
  * selected nnz; upload: new column indices (int32) and values (float32) of the selected entries, row by row, into

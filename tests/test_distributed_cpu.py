@@ -115,6 +115,10 @@ class _FakeDevice:
     def to_device(self, a, dtype=None):
         return torch.from_numpy(np.ascontiguousarray(a))
 
+    def upload_array(self, a, dtype=None):
+        t = torch.from_numpy(np.array(a, copy=True))
+        return t if dtype is None else t.to(dtype)
+
     def spatial_bbox(self, xy):
         return None
 
