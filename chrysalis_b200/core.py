@@ -8,6 +8,7 @@ hand-written sm_100a kernels reached through the C ABI (``include/chrysalis_b200
 from __future__ import annotations
 
 import os
+import threading
 import time
 
 import numpy as np
@@ -611,6 +612,23 @@ def _aa_upload(X: np.ndarray) -> torch.Tensor:
     return dv.upload_array(np.ascontiguousarray(X, dtype=np.float64), torch.float64)
 
 
+_RESTART_WORKERS = {}
+_RESTART_LOCK = threading.Lock()
+
+
+def _restart_workers(device, n: int):
+    """Host threads and CUDA streams that drive concurrent restarts: created once per device and kept (a fresh stream per
+    call would make the caching allocator open a new small-block pool each time)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+    with _RESTART_LOCK:
+        if key not in _RESTART_WORKERS:
+            _RESTART_WORKERS[key] = (ThreadPoolExecutor(max_workers=n, thread_name_prefix="chr-aa"),
+                                     [torch.cuda.Stream(device=device) for _ in range(n)])
+        return _RESTART_WORKERS[key]
+
+
 def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: int, tol: float, random_state: int, init_rows=None,
                    restart_workers: int = None):
     """``archetypes.AA(n_archetypes, n_init, max_iter, tol, random_state).fit`` on a device-resident embedding.
@@ -636,8 +654,8 @@ def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: i
             rs.choice(n_archetypes, n, replace=True)            # alphas0 draw: unused by the updates, keeps the RNG stream
         used.append(rows)
 
-    def fit_restart(rows):
-        st = dv.AAState(Xd, n_archetypes)
+    def fit_restart(rows, st=None):
+        st = dv.AAState(Xd, n_archetypes) if st is None else st
         st.init_from_rows(rows)
         rss_prev, rss, it = np.inf, np.inf, 0
         for it in range(max_iter):
@@ -647,25 +665,27 @@ def _aa_fit_device(Xd: torch.Tensor, n_archetypes: int, max_iter: int, n_init: i
             rss_prev = rss
         return {"alphas": st.alphas, "archetypes": st.Z, "rss": rss, "n_iter": it + 1 if max_iter else 0}
 
-    workers = n_init if restart_workers is None else int(restart_workers)
+    workers = int(os.environ.get("CHR_AA_RESTART_WORKERS", n_init)) if restart_workers is None else int(restart_workers)
     if workers > 1 and len(used) > 1:
-        from concurrent.futures import ThreadPoolExecutor
-
         device = Xd.device
+        # the restarts' buffers come from the caller's stream (the caching allocator cannot hand blocks cached for one stream
+        # to another: allocating 150 MB per restart on fresh streams would go to cudaMalloc, or to a cache flush on a full device)
+        states = [dv.AAState(Xd, n_archetypes) for _ in used]
+        pool, streams = _restart_workers(device, min(workers, len(used)))
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(device))          # Xd (and the seeding kernels) precede every restart
 
-        def on_own_stream(rows):
+        def on_own_stream(job):
+            i, rows, st = job
             torch.cuda.set_device(device)
-            stream = torch.cuda.Stream(device=device)
+            stream = streams[i % len(streams)]
             stream.wait_event(ready)
             with torch.cuda.stream(stream):
-                f = fit_restart(rows)
-            stream.synchronize()
+                f = fit_restart(rows, st)
+            stream.synchronize()                                 # the caller's stream may reuse the buffers afterwards
             return f
 
-        with ThreadPoolExecutor(max_workers=min(workers, len(used))) as pool:
-            fits = list(pool.map(on_own_stream, used))
+        fits = list(pool.map(on_own_stream, [(i, rows, st) for i, (rows, st) in enumerate(zip(used, states))]))
     else:
         fits = [fit_restart(rows) for rows in used]
     best = None
