@@ -13,8 +13,8 @@ gene range, W is replicated, the only exchange is the all-gather of the per-gene
 region.  ``--scaling weak`` gives every rank its own 18,000 genes instead (reported under "weak" at N > 1 by default).
 
 `e2e` is the same metric through the public API with HOST buffers: ``ch.detect_svgs(adata)`` on an AnnData-like object
-whose ``X`` holds the raw counts in page-locked host memory in the loader's compact format (``device.CompactCSR``: uint16
-columns + uint8 values, 3 bytes per stored entry; at N > 1: this rank's gene shard, flagged with ``.uns['chr_gene_shard']``):
+whose ``X`` holds the raw counts in page-locked host memory in the loader's compact format (``device.CompactCSR``: uint8 column deltas or uint16
+columns + uint8 values, 2 - 3 bytes per stored entry; at N > 1: this rank's gene shard, flagged with ``.uns['chr_gene_shard']``):
 H2D + decode + filter/normalise/log1p/densify + kNN + lattice plan + Moran + D2H + ranking and ``.var`` writes.
 `e2e_scipy_pinned` is the same call on the float32/int32 scipy CSR an AnnData usually holds (8 bytes per entry),
 `e2e_pageable` on ordinary (pageable) numpy arrays.  `pipeline` times ch.detect_svgs -> ch.pca -> ch.aa
@@ -179,12 +179,25 @@ def pinned_scipy_csr(csr, torch, pin=True):
 
 
 def compact_from_device(csr, torch, dv):
-    """device.CompactCSR (u16 columns, u8 values, overflow list) in page-locked host memory with the device CSR's content:
-    the 3-bytes-per-entry format a loader stages raw counts in."""
+    """device.CompactCSR in page-locked host memory with the device CSR's content: the format a loader stages raw counts in -
+    u8 values + overflow list, columns delta-coded in u8 (gaps >= 255 in a list) when that is the smaller form, else u16."""
     big = csr.data >= 255
     pin = lambda t: t.cpu().pin_memory()
-    return dv.CompactCSR(pin(csr.indptr), pin(csr.indices.to(torch.uint16)), pin(torch.where(big, torch.full_like(csr.data, 255.0), csr.data).to(torch.uint8)),
-                         pin(torch.nonzero(big).squeeze(1)), pin(csr.data[big]), tuple(csr.shape))
+    vals = pin(torch.where(big, torch.full_like(csr.data, 255.0), csr.data).to(torch.uint8))
+    over_pos, over_val = pin(torch.nonzero(big).squeeze(1)), pin(csr.data[big])
+    idx = csr.indices.to(torch.int64)
+    d = idx.clone()
+    d[1:] -= idx[:-1]
+    starts = csr.indptr[:-1][(csr.indptr[1:] - csr.indptr[:-1]) > 0]
+    d[starts] = idx[starts]
+    esc = d >= 255
+    n_esc = int(esc.sum().item())
+    sorted_rows = bool((d >= 0).all().item())
+    if sorted_rows and (12 * n_esc <= idx.numel() or csr.shape[1] > 65536):
+        return dv.CompactCSR(pin(csr.indptr), pin(torch.empty(0, dtype=torch.uint16)), vals, over_pos, over_val, tuple(csr.shape),
+                             pin(torch.where(esc, torch.full_like(d, 255), d).to(torch.uint8)), pin(torch.nonzero(esc).squeeze(1)),
+                             pin(d[esc].to(torch.int32)))
+    return dv.CompactCSR(pin(csr.indptr), pin(csr.indices.to(torch.uint16)), vals, over_pos, over_val, tuple(csr.shape))
 
 
 def timed_calls(fn, n_warm, n_timed, torch, dist=None):
@@ -715,7 +728,7 @@ def run_native(args):
         # headline: raw counts in the loader's compact format (u16 columns + u8 values, page-locked): 3 bytes per stored entry
         Xc = compact_from_device(csr, torch, dv)
         out["e2e"] = run_e2e(Xc, Xc.nbytes + xy.nbytes, 3, e_steps,
-                             "ch.detect_svgs(adata): adata.X = device.CompactCSR counts (uint16 columns, uint8 values + overflow list) in "
+                             "ch.detect_svgs(adata): adata.X = device.CompactCSR counts (" + ("uint8 column deltas" if Xc.deltas is not None else "uint16 columns") + ", uint8 values + overflow lists) in "
                              "page-locked host arrays" + shard_note + tail)
         if core.SVG_TRACE:                                            # CHR_SVG_TRACE=1: host timeline of the last step
             sys.stderr.write(f"svg_stage trace (ms): {core.SVG_TRACE}\n")

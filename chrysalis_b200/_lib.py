@@ -43,6 +43,7 @@ _SIGNATURES = {
     "chr_hilbert_keys": (c_int, [_P, c_int64, _P, _P, _P]),
     "chr_csr_gene_nnz": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "chr_csr_decode_compact": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
+    "chr_csr_decode_compact_delta": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P]),
     "chr_csr_spot_totals": (c_int, [_P, _P, _P, c_int64, _P, _P, _P]),
     "chr_csr_densify_log1p": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int, _P]),
     "chr_moran_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_uint]),

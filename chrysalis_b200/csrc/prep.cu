@@ -118,9 +118,66 @@ __global__ void csr_decode_overflow_kernel(const int64_t* __restrict__ pos, cons
     if (t < m) out_val[pos[t]] = val[t];
 }
 
+// delta-coded columns: a stored entry's column = the previous entry's column of the same row + delta (the first entry of a row
+// counts from 0); delta 255 = "look up the true delta" (gap_pos sorted positions, gap_val).  One warp per row: 32 deltas per
+// step, warp-inclusive scan, running base.
+__global__ void __launch_bounds__(256)
+csr_decode_delta_kernel(const int64_t* __restrict__ indptr, const uint8_t* __restrict__ deltas, const uint8_t* __restrict__ vals, int64_t n_rows,
+                        const int64_t* __restrict__ gap_pos, const int32_t* __restrict__ gap_val, int64_t n_gap,
+                        int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rows; r += n_warps) {
+        const int64_t p0 = indptr[r], p1 = indptr[r + 1];
+        int base = 0;
+        for (int64_t q = p0; q < p1; q += 32) {
+            const int64_t p = q + lane;
+            int dlt = 0;
+            float v = 0.f;
+            if (p < p1) {
+                dlt = deltas[p];
+                v = (float)vals[p];
+                if (dlt == 255) {                                     // rare: binary search of the position
+                    int64_t lo = 0, hi = n_gap - 1;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (gap_pos[mid] < p) lo = mid + 1; else hi = mid;
+                    }
+                    dlt = gap_val[lo];
+                }
+            }
+            int incl = dlt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (p < p1) {
+                out_idx[p] = base + incl;
+                out_val[p] = v;
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
 }  // namespace chr
 
 extern "C" {
+
+int chr_csr_decode_compact_delta(const int64_t* indptr, const uint8_t* deltas, const uint8_t* vals, int64_t n_rows, int64_t nnz,
+                                 const int64_t* gap_pos, const int32_t* gap_val, int64_t n_gap, const int64_t* over_pos,
+                                 const float* over_val, int64_t n_over, int32_t* out_indices, float* out_data, chr_stream_t stream) {
+    using namespace chr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CHR_REQUIRE(n_rows > 0 && nnz >= 0 && n_gap >= 0 && n_over >= 0 && indptr && (nnz == 0 || (deltas && vals && out_indices && out_data)) &&
+                    (n_gap == 0 || (gap_pos && gap_val)) && (n_over == 0 || (over_pos && over_val)),
+                "chr_csr_decode_compact_delta: bad arguments");
+    if (nnz > 0) csr_decode_delta_kernel<<<kNumSMs * 16, 256, 0, st>>>(indptr, deltas, vals, n_rows, gap_pos, gap_val, n_gap, out_indices, out_data);
+    if (n_over > 0) csr_decode_overflow_kernel<<<(unsigned)ceil_div<int64_t>(n_over, 256), 256, 0, st>>>(over_pos, over_val, n_over, out_data);
+    CHR_LAUNCH_CHECK();
+    return 0;
+}
 
 int chr_csr_decode_compact(const uint16_t* cols, const uint8_t* vals, int64_t nnz, const int64_t* over_pos, const float* over_val,
                            int64_t n_over, int32_t* out_indices, float* out_data, chr_stream_t stream) {

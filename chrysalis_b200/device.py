@@ -117,28 +117,51 @@ def _as_csr(X):
 
 @dataclass
 class CompactCSR:
-    """Raw counts as a loader can stage them for the device: 3 bytes per stored entry instead of scipy's 8 (PCIe is the floor of
-    ``detect_svgs`` end to end).  ``cols`` uint16 (needs n_genes <= 65536), ``vals`` uint8 with 255 = escape to the overflow
-    list (``over_pos`` positions into ``vals``, ``over_val`` float32).  Host tensors, page-locked when ``pin``.
-    ``detect_svgs`` accepts it as ``adata.X`` (expanded on the device by ``chr_csr_decode_compact``); ``to_scipy()`` gives the
-    ordinary matrix back."""
+    """Raw counts as a loader can stage them for the device: 2 - 3 bytes per stored entry instead of scipy's 8 (PCIe is the floor
+    of ``detect_svgs`` end to end).  Values: ``vals`` uint8 with 255 = escape to the overflow list (``over_pos`` positions into
+    ``vals``, ``over_val`` float32).  Columns, either
+      * ``cols`` uint16 absolute indices (needs n_genes <= 65536), or
+      * ``deltas`` uint8: column minus the previous column of the row (first entry of a row: from 0), columns sorted inside
+        every row, 255 = escape to the gap list (``gap_pos`` sorted positions, ``gap_val`` int32 true deltas) - at a few per cent
+        density a delta >= 255 occurs about once in a million entries.
+    Host tensors, page-locked when ``pin``.  ``detect_svgs`` accepts it as ``adata.X`` (expanded on the device by
+    ``chr_csr_decode_compact[_delta]``); ``to_scipy()`` gives the ordinary matrix back."""
     indptr: torch.Tensor
     cols: torch.Tensor
     vals: torch.Tensor
     over_pos: torch.Tensor
     over_val: torch.Tensor
     shape: tuple
+    deltas: torch.Tensor | None = None
+    gap_pos: torch.Tensor | None = None
+    gap_val: torch.Tensor | None = None
+
+    def _arrays(self):
+        return [t for t in (self.indptr, self.cols, self.vals, self.over_pos, self.over_val, self.deltas, self.gap_pos, self.gap_val)
+                if t is not None]
 
     @property
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.indptr, self.cols, self.vals, self.over_pos, self.over_val))
+        return sum(t.numel() * t.element_size() for t in self._arrays())
 
     @staticmethod
-    def from_scipy(X, pin: bool = True) -> "CompactCSR":
+    def encode_deltas(indptr: np.ndarray, indices: np.ndarray):
+        """(deltas uint8, gap_pos int64, gap_val int32) of CSR column indices that are sorted inside every row."""
+        idx = np.asarray(indices, dtype=np.int64)
+        d = idx.copy()
+        d[1:] -= idx[:-1]
+        starts = np.asarray(indptr[:-1])[np.diff(indptr) > 0]
+        d[starts] = idx[starts]
+        if d.size and d.min() < 0:
+            raise ValueError("CompactCSR: column indices must be sorted inside every row for the delta coding")
+        esc = d >= 255
+        return np.where(esc, 255, d).astype(np.uint8), np.flatnonzero(esc).astype(np.int64), d[esc].astype(np.int32)
+
+    @staticmethod
+    def from_scipy(X, pin: bool = True, delta: bool | None = None) -> "CompactCSR":
+        """``delta``: None = delta-code the columns when that is the smaller form (few escapes), True / False = force."""
         X = _as_csr(X)
         n, g = X.shape
-        if g > 65536:
-            raise ValueError("CompactCSR needs n_genes <= 65536 (uint16 column indices)")
         data = np.asarray(X.data)
         if data.size and (data.min() < 0 or not np.array_equal(data, np.floor(data))):
             raise ValueError("CompactCSR holds raw counts: non-negative integers")
@@ -150,26 +173,61 @@ class CompactCSR:
             t = torch.from_numpy(np.ascontiguousarray(a))
             return t.pin_memory() if pin and torch.cuda.is_available() else t
 
-        return CompactCSR(host(X.indptr.astype(np.int64)), host(X.indices.astype(np.uint16)), host(vals), host(over_pos),
-                          host(data[big].astype(np.float32)), (n, g))
+        enc = None
+        if delta is not False:
+            if not X.has_sorted_indices:
+                X = X.sorted_indices()
+                data = np.asarray(X.data)
+                big = data >= 255
+                over_pos = np.flatnonzero(big).astype(np.int64)
+                vals = np.where(big, 255, data).astype(np.uint8)
+            enc = CompactCSR.encode_deltas(X.indptr, X.indices)
+            if delta is None and g <= 65536 and enc[1].size * 12 > X.nnz:      # an escape costs 12 bytes: the uint16 form is smaller
+                enc = None
+        if enc is None:
+            if g > 65536:
+                raise ValueError("CompactCSR needs n_genes <= 65536 for uint16 column indices (or sorted rows for the delta coding)")
+            return CompactCSR(host(X.indptr.astype(np.int64)), host(X.indices.astype(np.uint16)), host(vals), host(over_pos),
+                              host(data[big].astype(np.float32)), (n, g))
+        return CompactCSR(host(X.indptr.astype(np.int64)), host(np.empty(0, dtype=np.uint16)), host(vals), host(over_pos),
+                          host(data[big].astype(np.float32)), (n, g), host(enc[0]), host(enc[1]), host(enc[2]))
+
+    def columns(self) -> np.ndarray:
+        """Absolute int32 column indices (host)."""
+        if self.deltas is None:
+            return self.cols.numpy().astype(np.int32)
+        d = self.deltas.numpy().astype(np.int64)
+        d[self.gap_pos.numpy()] = self.gap_val.numpy()
+        run = np.cumsum(d)
+        indptr = self.indptr.numpy()
+        counts = np.diff(indptr)
+        before = np.concatenate([[0], run])[indptr[:-1]]                 # running sum in front of every row
+        return (run - np.repeat(before, counts)).astype(np.int32)
 
     def to_scipy(self):
         import scipy.sparse as sp
 
         data = self.vals.numpy().astype(np.float32)
         data[self.over_pos.numpy()] = self.over_val.numpy()
-        return sp.csr_matrix((data, self.cols.numpy().astype(np.int32), self.indptr.numpy()), shape=self.shape)
+        return sp.csr_matrix((data, self.columns(), self.indptr.numpy()), shape=self.shape)
 
 
 def _upload_compact(X: CompactCSR) -> DeviceCSR:
     dev = _require_cuda()
     up = lambda t: t.to(dev, non_blocking=True)
-    indptr, cols, vals, opos, oval = up(X.indptr), up(X.cols), up(X.vals), up(X.over_pos), up(X.over_val)
-    nnz = cols.numel()
+    indptr, vals, opos, oval = up(X.indptr), up(X.vals), up(X.over_pos), up(X.over_val)
+    nnz = vals.numel()
     idx = torch.empty(nnz, dtype=torch.int32, device=dev)
     val = torch.empty(nnz, dtype=torch.float32, device=dev)
-    _lib.call("chr_csr_decode_compact", _ptr(cols), _ptr(vals), nnz, _ptr(opos) if opos.numel() else 0, _ptr(oval) if oval.numel() else 0,
-              opos.numel(), _ptr(idx), _ptr(val), _stream())
+    if X.deltas is not None:
+        deltas, gpos, gval = up(X.deltas), up(X.gap_pos), up(X.gap_val)
+        _lib.call("chr_csr_decode_compact_delta", _ptr(indptr), _ptr(deltas), _ptr(vals), X.shape[0], nnz, _ptr(gpos) if gpos.numel() else 0,
+                  _ptr(gval) if gval.numel() else 0, gpos.numel(), _ptr(opos) if opos.numel() else 0, _ptr(oval) if oval.numel() else 0,
+                  opos.numel(), _ptr(idx), _ptr(val), _stream())
+    else:
+        cols = up(X.cols)
+        _lib.call("chr_csr_decode_compact", _ptr(cols), _ptr(vals), nnz, _ptr(opos) if opos.numel() else 0, _ptr(oval) if oval.numel() else 0,
+                  opos.numel(), _ptr(idx), _ptr(val), _stream())
     return DeviceCSR(indptr, idx, val, tuple(X.shape))
 
 
@@ -214,7 +272,7 @@ def host_arrays_pinned(X) -> bool:
     if isinstance(X, (PinnedCSR, DeviceCSR)):
         return True
     if isinstance(X, CompactCSR):
-        return X.cols.is_pinned()
+        return X.vals.is_pinned() and (X.deltas if X.deltas is not None else X.cols).is_pinned()
     import scipy.sparse as sp
 
     if not (sp.issparse(X) and X.format == "csr") or not torch.cuda.is_available():

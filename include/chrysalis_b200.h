@@ -95,6 +95,13 @@ int chr_csr_gene_nnz(const int64_t* indptr, const int32_t* indices, const float*
 int chr_csr_decode_compact(const uint16_t* cols, const uint8_t* vals, int64_t nnz, const int64_t* over_pos,
                            const float* over_val, int64_t n_over, int32_t* out_indices, float* out_data,
                            chr_stream_t stream);
+/* the same with delta-coded columns (2 bytes per stored entry): columns sorted inside a row, deltas[p] = column - previous
+ * column of the row (the first entry of a row counts from 0), 255 = "look in the gap list" (gap_pos: sorted positions,
+ * gap_val: the true deltas; at ~5 % density deltas >= 255 occur once in a million entries).  indptr: device, [n_rows + 1]. */
+int chr_csr_decode_compact_delta(const int64_t* indptr, const uint8_t* deltas, const uint8_t* vals, int64_t n_rows,
+                                 int64_t nnz, const int64_t* gap_pos, const int32_t* gap_val, int64_t n_gap,
+                                 const int64_t* over_pos, const float* over_val, int64_t n_over, int32_t* out_indices,
+                                 float* out_data, chr_stream_t stream);
 /* per-spot totals over the kept genes (gene_col[g] >= 0), double accumulation, one warp per spot */
 int chr_csr_spot_totals(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
                         const int32_t* gene_col, double* totals, chr_stream_t stream);

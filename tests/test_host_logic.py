@@ -220,21 +220,35 @@ def test_lattice_plan_splits_the_knn_adjacency_exactly(shape):
 
 
 def test_compact_csr_round_trip_and_limits():
-    """device.CompactCSR (the 3-bytes-per-entry loader format of detect_svgs): exact round trip incl. counts >= 255."""
+    """device.CompactCSR (the 2-3-bytes-per-entry loader format of detect_svgs): exact round trip incl. counts >= 255, uint16
+    columns and delta-coded columns (with and without escapes), automatic choice of the smaller form."""
     import scipy.sparse as sp
     from chrysalis_b200 import device as dv
     rng = np.random.default_rng(0)
     dense = rng.poisson(0.3, (200, 700)).astype(np.float32)
     dense[rng.integers(0, 200, 40), rng.integers(0, 700, 40)] = rng.integers(255, 70000, 40)
+    dense[7] = 0                                                                   # an empty row
     X = sp.csr_matrix(dense)
-    c = dv.CompactCSR.from_scipy(X, pin=False)
+    c = dv.CompactCSR.from_scipy(X, pin=False, delta=False)
     assert c.cols.dtype == torch_dtype("uint16") and c.vals.dtype == torch_dtype("uint8") and c.over_pos.numel() == int((X.data >= 255).sum())
     assert (c.to_scipy() != X).nnz == 0 and c.shape == X.shape
     assert c.nbytes < 0.5 * (X.data.nbytes + X.indices.nbytes + X.indptr.nbytes) + 8 * c.over_pos.numel() + X.indptr.nbytes
+    d = dv.CompactCSR.from_scipy(X, pin=False)                                     # dense rows: deltas, no escapes
+    assert d.deltas is not None and d.deltas.dtype == torch_dtype("uint8") and d.gap_pos.numel() == 0 and d.nbytes < c.nbytes
+    assert (d.to_scipy() != X).nnz == 0 and np.array_equal(d.columns(), X.indices)
+    # sparse rows over many genes: gaps >= 255 are escaped; forced deltas still round-trip, the automatic choice is uint16
+    S = sp.random(300, 60000, density=0.002, format="csr", random_state=3, data_rvs=lambda k: rng.integers(1, 9, k)).astype(np.float32)
+    e = dv.CompactCSR.from_scipy(S, pin=False, delta=True)
+    assert e.gap_pos.numel() > 0 and (e.to_scipy() != S).nnz == 0 and np.array_equal(e.columns(), S.indices)
+    assert dv.CompactCSR.from_scipy(S, pin=False).deltas is None
+    # unsorted rows are sorted for the delta coding; more genes than uint16 holds need it
+    U = sp.csr_matrix((np.array([1, 2, 3], dtype=np.float32), np.array([5, 1, 3]), np.array([0, 3])), shape=(1, 70000))
+    u = dv.CompactCSR.from_scipy(U, pin=False)
+    assert u.deltas is not None and (u.to_scipy() != U).nnz == 0
     with pytest.raises(ValueError):
         dv.CompactCSR.from_scipy(sp.csr_matrix(dense * 0.5), pin=False)            # not counts
     with pytest.raises(ValueError):
-        dv.CompactCSR.from_scipy(sp.csr_matrix((3, 70000), dtype=np.float32), pin=False)   # too many genes for uint16
+        dv.CompactCSR.from_scipy(sp.csr_matrix((3, 70000), dtype=np.float32), pin=False, delta=False)   # too many genes for uint16
 
 
 def torch_dtype(name):

@@ -494,15 +494,29 @@ def test_local_morans_i_fields(golden_hex):
             np.testing.assert_allclose(ad.obsm["local_morans_i"][:, j], om.local_moran(dense[:, j], w)["Is"], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,g,density", [(300, 700, 0.2), (500, 60000, 0.002), (64, 70000, 0.01), (2000, 3000, 0.05)])
+def test_delta_coded_columns_decode_to_the_scipy_arrays(n, g, density):
+    """chr_csr_decode_compact_delta: device CSR arrays of a delta-coded CompactCSR (escapes for gaps >= 255 and counts >= 255,
+    empty rows) against the scipy matrix it was made from."""
+    rng = np.random.default_rng(n + g)
+    X = sp.random(n, g, density=density, format="csr", random_state=n, data_rvs=lambda k: rng.integers(1, 300, k)).astype(np.float32)
+    X.sort_indices()
+    c = dv.CompactCSR.from_scipy(X, delta=True)
+    d = dv.upload_csr(c)
+    assert np.array_equal(d.indptr.cpu().numpy(), X.indptr) and np.array_equal(d.indices.cpu().numpy(), X.indices)
+    assert np.array_equal(d.data.cpu().numpy(), X.data)
+
+
 def test_detect_svgs_on_compact_counts_and_uint8_scipy(golden_square):
-    """The loader formats of the counts: device.CompactCSR (u16 columns + u8 values + overflow list) and a scipy CSR with
-    uint8 data give bit-identical results to the float32 scipy matrix."""
+    """The loader formats of the counts: device.CompactCSR (u16 or delta-coded u8 columns + u8 values + overflow lists) and a
+    scipy CSR with uint8 / uint16 data give bit-identical results to the float32 scipy matrix."""
     z = golden_square
     X = golden_csr(z).astype(np.float32)
     X.data[::997] += 300.0                                              # a few counts beyond the u8 range
     res = []
-    for form in ("f32", "compact", "u16"):
-        Xi = X if form == "f32" else (dv.CompactCSR.from_scipy(X) if form == "compact" else X.astype(np.uint16))
+    for form in ("f32", "compact", "compact_delta", "u16"):
+        Xi = {"f32": lambda: X, "compact": lambda: dv.CompactCSR.from_scipy(X, delta=False),
+              "compact_delta": lambda: dv.CompactCSR.from_scipy(X, delta=True), "u16": lambda: X.astype(np.uint16)}[form]()
         ad = ch.AnnDataLite(Xi, obsm={"spatial": z["xy"]})
         ch.detect_svgs(ad, neighbors=8, top_svg=40, min_morans=0.05, geary=True)
         res.append((ad.var["Moran's I"].to_numpy(), ad.var["Geary's C"].to_numpy(), ad.var["spatially_variable"].to_numpy()))
