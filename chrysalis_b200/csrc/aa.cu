@@ -635,7 +635,8 @@ __global__ void aa_partial_reduce_kernel(const double* __restrict__ part, int np
 }
 
 // ---- pinv step (single CTA): Zhat = pinv(alphas) X via eigen-decomposition of A^T A ---------------------
-__global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int na, int d, int64_t n, double* __restrict__ Zhat) {
+__global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int na, int d, int64_t n, double* __restrict__ Zhat,
+                               double* __restrict__ gram_out /* [na*na + na*d]: A^T A | A^T X, for the RSS identity */) {
     extern __shared__ double sh[];
     const int nacc = na * na + na * d;
     double* S = sh;                 // na x na  (A^T A, becomes diagonal)
@@ -646,6 +647,7 @@ __global__ void aa_pinv_kernel(const double* __restrict__ part, int nparts, int 
 #pragma unroll 16
         for (int p = 0; p < nparts; ++p) a += part[(size_t)p * nacc + e];          // loads issue ahead, the sum stays in order
         if (e < na * na) S[e] = a; else B[e - na * na] = a;
+        gram_out[e] = a;
     }
     for (int e = threadIdx.x; e < na * na; e += blockDim.x) Vv[e] = (e / na == e % na) ? 1.0 : 0.0;
     __syncthreads();
@@ -1209,6 +1211,46 @@ aa_rss_kernel(const double* __restrict__ X, int64_t n, int d, const double* __re
     }
 }
 
+// ||X||_F^2 partials (once per restart): 256 rows per CTA, fixed order
+__global__ void __launch_bounds__(256) aa_xnorm_kernel(const double* __restrict__ X, int64_t n, int d, double* __restrict__ part) {
+    __shared__ double red[8];
+    const int64_t e0 = (int64_t)blockIdx.x * 256 * d, e1 = e0 + (int64_t)256 * d < n * d ? e0 + (int64_t)256 * d : n * d;
+    double t = 0.0;
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) t += X[e] * X[e];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double u = 0.0;
+        for (int w = 0; w < 8; ++w) u += red[w];
+        part[blockIdx.x] = u;
+    }
+}
+// rss = ||X - A Z||_F^2 = ||X||^2 - 2 <A^T X, Z> + <A^T A, Z Z^T>  from the Gram sums the alpha step leaves behind (one CTA, fixed
+// order).  The three terms are 10 - 100 times the result: absolute error ~1e-15 ||X||^2, five orders below the 1e-3 stop rule.
+__global__ void __launch_bounds__(256)
+aa_rss_gram_kernel(const double* __restrict__ gram, const double* __restrict__ Z, int na, int d, const double* __restrict__ xnorm2,
+                   double* __restrict__ rss_out) {
+    __shared__ double red[256];
+    const double* __restrict__ S = gram;                 // A^T A  [na][na]
+    const double* __restrict__ B = gram + na * na;       // A^T X  [na][d]
+    double t = 0.0;
+    for (int e = threadIdx.x; e < na * d; e += 256) t -= 2.0 * B[e] * Z[e];
+    for (int e = threadIdx.x; e < na * na; e += 256) {
+        const int a = e / na, b = e - a * na;
+        double zz = 0.0;
+        for (int q = 0; q < d; ++q) zz += Z[a * d + q] * Z[b * d + q];
+        t += S[e] * zz;
+    }
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *rss_out = *xnorm2 + red[0];
+}
+
 __global__ void __launch_bounds__(256) aa_sum_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
     // fixed order: every thread sums a contiguous chunk, thread 0 adds the 256 chunk sums in order
     __shared__ double red[256];
@@ -1295,6 +1337,7 @@ __global__ void aa_fs_argmax_final_kernel(const double* __restrict__ cand_w, con
 struct AaPlan {
     int alpha_blocks, grad_blocks, rss_blocks, nacc;
     size_t off_part, off_part2, off_zhat, off_R, off_state, off_pidx, off_bcoef, off_candw, off_candi, off_scr, off_rsspart, total;
+    size_t off_gram, off_xnorm;     // reduced A^T A | A^T X of the iteration, ||X||_F^2 of the restart
 };
 
 static AaPlan aa_plan(int64_t n, int d, int na) {
@@ -1319,6 +1362,8 @@ static AaPlan aa_plan(int64_t n, int d, int na) {
     p.off_candi = take((size_t)cand_rows * na * 8);
     p.off_scr = take(256);                  // (unused: the beta refits keep their scratch in shared memory)
     p.off_rsspart = take((size_t)p.rss_blocks * 8);
+    p.off_gram = take((size_t)p.nacc * 8);
+    p.off_xnorm = take(8);
     p.total = o;
     return p;
 }
@@ -1452,7 +1497,9 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     if (sm_pinv > 48 * 1024) CHR_CUDA(cudaFuncSetAttribute(aa_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pinv));
     const int nred = ceil_div(p.alpha_blocks, kAaRedChunk);
     aa_partial_reduce_kernel<<<dim3((unsigned)ceil_div(p.nacc, 128), (unsigned)nred), 128, 0, st>>>(part, p.alpha_blocks, p.nacc, part2);
-    aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part2, nred, na, d, n, Zhat);
+    double* gram = (double*)(ws + p.off_gram);
+    double* xnorm2 = (double*)(ws + p.off_xnorm);
+    aa_pinv_kernel<<<1, 256, sm_pinv, st>>>(part2, nred, na, d, n, Zhat, gram);
     CHR_LAUNCH_CHECK();
     // ---- betas: active-set passes, every archetype advances one step per pass
     aa_beta_init_kernel<<<1, 256, 0, st>>>(bst, Zhat, na, d, penalty_M, warm, R);
@@ -1497,7 +1544,17 @@ int chr_aa_iterate(const double* X, int64_t n, int d, int n_archetypes, double p
     }
     if (beta_passes_out) *beta_passes_out = passes;
     aa_beta_finish_kernel<<<na, 64, 0, st>>>(X, d, na, bst, pidx, bcoef, Z);
-    // ---- rss
+    // ---- rss: from the iteration's Gram sums (no pass over X); CHR_AA_RSS_DIRECT=1 keeps the per-spot residual pass
+    if (!getenv("CHR_AA_RSS_DIRECT")) {
+        if (!warm) {                       // first iteration of a restart: ||X||_F^2 into the workspace
+            aa_xnorm_kernel<<<p.rss_blocks, 256, 0, st>>>(X, n, d, rsspart);
+            aa_sum_kernel<<<1, 256, 0, st>>>(rsspart, p.rss_blocks, xnorm2);
+        }
+        aa_rss_gram_kernel<<<1, 256, 0, st>>>(gram, Z, na, d, xnorm2, rss_out);
+        timer_end(CHR_FAMILY_AA, timing_env(), st);
+        CHR_LAUNCH_CHECK();
+        return 0;
+    }
     const size_t sm_rss = ((size_t)na * d + 256 * (size_t)(d | 1) + 256 * (size_t)(na | 1)) * 8;
     const int NAr = (na + 3) & ~3;
     const size_t sm_rssf = ((size_t)NAr * d + 256 * (size_t)(d | 1) + 256 * (size_t)(na | 1)) * 8;

@@ -305,7 +305,9 @@ int chr_aa_furthest_sum(const double* X, int64_t n, int d, int n_archetypes, int
                         int64_t* rows_out, void* workspace, size_t workspace_bytes,
                         chr_stream_t stream);
 /* one iteration, in place:  alphas <- NNLS(X | Z);  Z <- pinv(alphas) X;  betas <- NNLS(Z | X);
- * Z <- betas X;  *rss_out (device) = ||X - alphas Z||_F^2.  beta_passes_out: HOST int (may be
+ * Z <- betas X;  *rss_out (device) = ||X - alphas Z||_F^2, evaluated as ||X||^2 - 2 <A^T X, Z> + <A^T A, Z Z^T> from the sums
+ * the alpha step accumulates anyway (absolute error ~1e-15 ||X||^2, far below the 1e-3 stop rule of the fit; the
+ * environment variable CHR_AA_RSS_DIRECT=1 selects the per-spot residual pass instead).  beta_passes_out: HOST int (may be
  * NULL), number of active-set passes of the beta step.  Synchronises the stream (the beta
  * step's termination flag is read back).  warm != 0: `alphas` and the workspace still hold the
  * previous iteration of the same restart; their supports seed the active sets (the NNLS

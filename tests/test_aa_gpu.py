@@ -172,6 +172,27 @@ def test_aa_properties_at_large_n():
     assert np.abs(st2.alphas.cpu().numpy() - al[perm]).max() < 1e-6
 
 
+@pytest.mark.parametrize("n,d,a", [(777, 30, 12), (40_000, 20, 8), (1300, 11, 3), (300, 64, 16), (2049, 16, 20)])
+def test_rss_from_the_gram_sums_equals_the_residual_pass(n, d, a, monkeypatch):
+    """||X - A Z||^2 as ||X||^2 - 2 <A^T X, Z> + <A^T A, Z Z^T> (default: no pass over X) against the per-spot residual sum
+    (CHR_AA_RSS_DIRECT=1): the same state, RSS equal to 1e-14 ||X||^2 - five orders below the fit's 1e-3 stop rule."""
+    X = blob_data(n, d, seed=n + a) if n < 20_000 else simplex_data(n, d, a, seed=n).astype(np.float64)
+    rows = np.random.default_rng(2).choice(n, a, replace=False)
+    Xd = dv.to_device(X, torch.float64)
+    runs = {}
+    for variant in ("gram", "direct"):
+        monkeypatch.delenv("CHR_AA_RSS_DIRECT", raising=False)
+        if variant == "direct":
+            monkeypatch.setenv("CHR_AA_RSS_DIRECT", "1")
+        st = dv.AAState(Xd, a)
+        st.init_from_rows(rows)
+        rss = [st.iterate() for _ in range(10)]
+        runs[variant] = (st.alphas.clone(), st.Z.clone(), np.array(rss))
+    monkeypatch.delenv("CHR_AA_RSS_DIRECT", raising=False)
+    assert torch.equal(runs["gram"][0], runs["direct"][0]) and torch.equal(runs["gram"][1], runs["direct"][1])
+    assert np.abs(runs["gram"][2] - runs["direct"][2]).max() <= 1e-14 * float((X ** 2).sum())
+
+
 def test_concurrent_restarts_equal_sequential_restarts():
     """The restarts of a fit run on their own streams; every one of them must be the launch chain a sequential loop makes."""
     X = simplex_data(30_000, 12, 6, seed=5).astype(np.float64)
