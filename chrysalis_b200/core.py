@@ -75,6 +75,7 @@ MAX_ARCHETYPES = 64      # aa.cu kAaMaxA
 MAX_AA_DIMS = 64         # aa.cu kAaMaxD
 
 _SIDE_STREAMS = {}
+_POOL_LOCK = threading.Lock()
 SVG_TRACE = []     # CHR_SVG_TRACE=1: (label, host seconds since the call started) of the last svg_stage call
 
 
@@ -82,6 +83,19 @@ def _mark(t0, label):
     if t0 is not None:
         SVG_TRACE.append((label, round((time.perf_counter() - t0) * 1e3, 3)))
 
+
+
+_W_BUILDER = []
+
+
+def _w_builder():
+    """The host thread that assembles W next to the calling thread (one per process, kept)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with _POOL_LOCK:
+        if not _W_BUILDER:
+            _W_BUILDER.append(ThreadPoolExecutor(max_workers=1, thread_name_prefix="chr-w"))
+        return _W_BUILDER[0]
 
 
 def _side_stream():
@@ -167,41 +181,65 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     if async_upload:
         csr = upload_counts()
         _mark(t0, "counts upload enqueued")
-    with _stream_ctx(side):
+    def build_w():
         # core.py:64-65  kNN weights, row-standardised.  kNN on the spots as given: distance ties go to the lower ORIGINAL
         # spot id (knn.cu), so W does not depend on the internal row order and is the W local_morans_i builds
-        bbox = dv.spatial_bbox(xy)
-        nbr0 = dv.knn_build(xy, neighbors, bbox)
-        # square lattice with k = 8 (Visium HD / Stereo-seq bins): lattice layout + stencil kernel; otherwise rows in
-        # Hilbert order + the quad plan of W
-        lat = None
-        if neighbors == 8 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0":
-            lat = dv.lattice_plan(xy, nbr0, bbox)
-        if lat is not None:
-            rank_of, nbr, plan, n_rows = lat.row_of_spot, None, None, lat.n_rows
-        else:
-            order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
-            rank_of = torch.empty_like(order)
-            rank_of[order] = torch.arange(n, device=order.device)
-            nbr = rank_of.to(torch.int32)[nbr0[order].long()].contiguous()      # relabelled into the row order
-            plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
-            n_rows = n
-        # on a lattice the kernel is fed from the CSR counts themselves (no dense matrix); permutation inference and every
-        # other W stream a dense matrix, whose zero fill runs here, under the upload
-        use_csr = lat is not None and not permutations and os.environ.get("CHR_MORAN_CSR", "1") != "0"
-        if torch.cuda.is_available() and not use_csr:
-            dense_buf = torch.empty((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
-            dense_buf.zero_()
+        with _stream_ctx(side):
+            bbox = dv.spatial_bbox(xy)
+            nbr0 = dv.knn_build(xy, neighbors, bbox)
+            # square lattice with k = 8 (Visium HD / Stereo-seq bins): lattice layout + stencil kernel; otherwise rows in
+            # Hilbert order + the quad plan of W
+            lat = None
+            if neighbors == 8 and os.environ.get("CHR_MORAN_LATTICE", "1") != "0":
+                lat = dv.lattice_plan(xy, nbr0, bbox, simple_lists=n > neighbors)     # knn_build: k distinct others per spot
+            if lat is not None:
+                rank_of, nbr, plan, n_rows = lat.row_of_spot, None, None, lat.n_rows
+            else:
+                order = dv.spatial_order(xy, bbox)          # spatially coherent row order of the dense matrix
+                rank_of = torch.empty_like(order)
+                rank_of[order] = torch.arange(n, device=order.device)
+                nbr = rank_of.to(torch.int32)[nbr0[order].long()].contiguous()      # relabelled into the row order
+                plan = dv.moran_plan(nbr)                    # W as the device plan the Moran kernel streams against
+                n_rows = n
+            # on a lattice the kernel is fed from the CSR counts themselves (no dense matrix); permutation inference and every
+            # other W stream a dense matrix, whose zero fill runs here, under the upload
+            use_csr = lat is not None and not permutations and os.environ.get("CHR_MORAN_CSR", "1") != "0"
+            dense_buf = None
+            if torch.cuda.is_available() and not use_csr:
+                dense_buf = torch.empty((n_rows, dv.dense_ld(hi - lo)), dtype=torch.float32, device="cuda")
+                dense_buf.zero_()
+        return lat, rank_of, nbr, plan, n_rows, use_csr, dense_buf
+
+    # The W build is a chain of ~100 short launches with a few read-backs: host-bound (6 - 9 ms at 700k spots).  It runs on a
+    # second host thread (and the side stream) while this thread moves the counts and applies the gene filter; on one GPU it
+    # hides under the upload, on a gene shard of a multi-GPU run it is the longest item of the call.
+    w_job = None
+    if side is not None:
+        device_index = torch.cuda.current_device()
+
+        def build_w_on_worker():
+            torch.cuda.set_device(device_index)
+            return build_w()
+
+        w_job = _w_builder().submit(build_w_on_worker)
+    else:
+        w_built = build_w()
     if csr is None:
         csr = upload_counts()
         _mark(t0, "counts uploaded (bounce ring)")
-    if side is not None:
-        main.wait_stream(side)
-        keep_alive = [rank_of] + ([dense_buf] if dense_buf is not None else []) + ([nbr, plan.buf] if plan is not None else []) + \
-            ([lat.bands, lat.chunks, lat.corr, lat.absent, lat.pilot_rows] if lat is not None else [])
-        for t in keep_alive:
-            t.record_stream(main)
-    _mark(t0, "W build + zero fill enqueued (side stream)")
+
+    def join_w():
+        built = w_job.result() if w_job is not None else w_built
+        lat, rank_of, nbr, plan, n_rows, use_csr, dense_buf = built
+        if side is not None:
+            main.wait_stream(side)
+            keep_alive = [rank_of] + ([dense_buf] if dense_buf is not None else []) + ([nbr, plan.buf] if plan is not None else []) + \
+                ([lat.bands, lat.chunks, lat.corr, lat.absent, lat.pilot_rows] if lat is not None else [])
+            for t in keep_alive:
+                t.record_stream(main)
+        _mark(t0, "W build joined (side stream, second host thread)")
+        return built
+
     # core.py:53  sc.pp.filter_genes(min_cells=int(len(adata) * min_spots))
     gene_nnz = dv.csr_gene_nnz(csr)
     keep = gene_nnz >= int(n * min_spots)
@@ -213,11 +251,13 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     reduce_ = dd.allreduce_sum_ if size > 1 else (lambda t: t)
     keep_all = gather(keep, None if local_shard else g_all)
     if int(keep_all.sum().item()) == 0:
+        join_w()
         return keep_all.cpu().numpy(), np.empty(0), (np.empty(0) if geary else None)
     # core.py:55-57  normalize_total + log1p on the filtered copy unless the caller already did
     scale = None
     if not already_log1p:
         scale = dv.median_scale(reduce_(dv.csr_spot_totals(csr, gene_col)))
+    lat, rank_of, nbr, plan, n_rows, use_csr, dense_buf = join_w()
     unsorted = None
     if n_keep > 0 and use_csr and csr.indices.numel() < 2 ** 32 - 1:
         # core.py:59 + 71-76 in one kernel: the producers of the stencil kernel build the tiles from the stored entries

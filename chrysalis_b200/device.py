@@ -610,10 +610,16 @@ def lattice_layout(ix: torch.Tensor, iy: torch.Tensor, band_rows: int = LATTICE_
     W, H = (int(v) + 1 for v in torch.stack([ix.max(), iy.max()]).cpu())
     n_bands = (H + band_rows - 1) // band_rows
     band = iy // band_rows
-    big = torch.iinfo(torch.int64).max
-    xmin = torch.full((n_bands,), big, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amin")
-    xmax = torch.full((n_bands,), -1, dtype=torch.int64, device=ix.device).scatter_reduce(0, band, ix, "amax")
-    crowded = (torch.bincount(iy * W + ix, minlength=W * H) > 1).any().to(torch.int64)          # two spots on one node
+    # occupancy of the node grid (padded to whole bands): two spots on one node, and per band the first / last occupied column.
+    # (Dense reductions over the grid: a scatter-min / max of 700k spots into a dozen band slots serialises on the atomics.)
+    occ = torch.bincount(iy * W + ix, minlength=n_bands * band_rows * W)
+    crowded = (occ > 1).any().to(torch.int64)
+    col_used = (occ.view(n_bands, band_rows, W) > 0).any(1)                                        # [n_bands, W]
+    first = col_used.to(torch.int8).argmax(1)
+    last = W - 1 - col_used.flip(1).to(torch.int8).argmax(1)
+    used = col_used.any(1)
+    xmin = torch.where(used, first, torch.full_like(first, torch.iinfo(torch.int64).max))
+    xmax = torch.where(used, last, torch.full_like(last, -1))
     packed = torch.cat([xmin, xmax, crowded[None]]).cpu().numpy()                                  # one round trip
     if packed[-1]:
         return None, 0, None, None, (W, H)
@@ -660,7 +666,7 @@ def _lattice_corrections_general(ix, iy, nbr, shape):
     return key // n, key % n, coef
 
 
-def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, shape: tuple):
+def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, shape: tuple, simple_lists: bool = False):
     """D = A - B as a COO list (i, j, coefficient) plus the (indeg - k) weights of W's column sums.
 
     A: kNN adjacency counts of ``nbr`` [n, k] (spot ids); B: 1 for every ordered pair of present nodes that are
@@ -678,8 +684,11 @@ def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, s
     J = grid[((iy + 1) * (W + 2) + ix + 1)[:, None] + offs[None, :]]                          # [n, 8] stencil neighbours, -1 = absent
     extra = ~(((ix[nb] - ix[:, None]).abs() <= 1) & ((iy[nb] - iy[:, None]).abs() <= 1)) | (nb == me[:, None])    # [n, k]
     missing = (J >= 0) & ~(nb[:, None, :] == J[:, :, None]).any(2)                            # [n, 8]
-    srt = nb.sort(dim=1).values
-    irregular = (srt[:, 1:] == srt[:, :-1]).any() | (nb == me[:, None]).any()
+    if simple_lists:                                            # lists of the kNN builder: k distinct neighbours, never the spot itself
+        irregular = torch.zeros((), dtype=torch.bool, device=dev)
+    else:
+        srt = nb.sort(dim=1).values
+        irregular = (srt[:, 1:] == srt[:, :-1]).any() | (nb == me[:, None]).any()
     indeg = torch.bincount(nb.reshape(-1), minlength=n)
     wmask = indeg != k
     counts = torch.stack([extra.sum(), missing.sum(), wmask.sum(), irregular.to(torch.int64)]).cpu()   # round trip 1
@@ -698,7 +707,7 @@ def lattice_corrections(ix: torch.Tensor, iy: torch.Tensor, nbr: torch.Tensor, s
 
 
 def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None = None, pitch: float | None = None,
-                 max_fill: float = 1.6, max_corr_frac: float = 0.2) -> LatticePlan | None:
+                 max_fill: float = 1.6, max_corr_frac: float = 0.2, simple_lists: bool = False) -> LatticePlan | None:
     """Lattice layout + corrections for the kNN lists ``nbr`` [n, 8] of spots on a square lattice, or None when the
     stencil kernel does not apply (k != 8, no lattice, two spots on one node, a tissue so ragged that the stored
     range or the correction list would dominate): the caller then takes the general quad-plan kernel."""
@@ -716,7 +725,7 @@ def lattice_plan(xy: torch.Tensor, nbr: torch.Tensor, bbox: torch.Tensor | None 
         return None
     if n_rows > max_fill * n or n_rows >= 2 ** 31 or chunks.shape[0] >= 65536:
         return None
-    ci, cj, cc, wj, ww = lattice_corrections(ix, iy, nbr, shape)
+    ci, cj, cc, wj, ww = lattice_corrections(ix, iy, nbr, shape, simple_lists)
     if ci.numel() + wj.numel() > max_corr_frac * n * k:
         return None
     f32bits = lambda t: t.to(torch.float32).view(torch.int32)

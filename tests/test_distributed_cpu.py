@@ -95,7 +95,7 @@ class _FakeDevice:
         assert np.array_equal(col_map[cols], np.arange(len(cols)))
         return X[:, cols]
 
-    def lattice_plan(self, xy, nbr, bbox=None):
+    def lattice_plan(self, xy, nbr, bbox=None, **kw):
         return None
 
     def to_host(self, t):
