@@ -150,7 +150,6 @@ def svg_stage(X, spatial, min_spots: float, neighbors: int, geary: bool, already
     # matrix run on a side stream; the side stream waits for everything enqueued so far, not for the upload enqueued next.
     main = torch.cuda.current_stream() if torch.cuda.is_available() else None
     side = _side_stream()
-    dense_buf = None
     # core.py:61-62  coordinates (x, -y): uploaded BEFORE the counts, otherwise this small copy queues behind the
     # multi-GB transfer on the copy engine and the side-stream work below cannot start until the upload has finished
     # (the sign flip of y happens on the device: the host makes no copy of the coordinates)
