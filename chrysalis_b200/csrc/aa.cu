@@ -310,8 +310,8 @@ __device__ __forceinline__ void stage_wait() {
 // stream whatever its passive set P is: the least-squares problem on P is solved as the FULL NA x NA system
 //     G'_ij = G_ij  (i, j in P),   delta_ij otherwise;      rhs'_i = c_i (i in P), 0 otherwise
 // (NA = n_archetypes padded to a multiple of 4, padding rows are never passive), with a compile-time unrolled
-// Cholesky whose factor lives in shared memory as L[entry][thread] (conflict-free), the row being eliminated in
-// registers.  One loop iteration = one solve, then either "accept + KKT test + add the arg-max archetype" or
+// Cholesky: up to 12 archetypes the matrix and its factor stay in registers, 13 - 16 keep the factor in shared memory as
+// L[entry][thread] (conflict-free) with the row being eliminated in registers.  One loop iteration = one solve, then either "accept + KKT test + add the arg-max archetype" or
 // "step back to the feasible region + drop" (Lawson-Hanson, same tolerances as nnls_normal); lanes that have
 // converged idle.  A warm start (previous coefficients) usually needs 1-3 solves.  The minimiser is unique, so
 // this and nnls_normal agree to rounding.
@@ -362,8 +362,9 @@ struct AlphaFixed {
     }
 
     // solve on the passive set `P` (bit mask); returns s (0 outside P); indices whose pivot collapses are dropped from P.
-    // Right-looking Cholesky with the (masked) matrix in registers: column j is scaled, written to shared memory once
-    // (the back substitution reads it) and subtracted from the trailing entries; the forward substitution is fused.
+    // Right-looking Cholesky with the (masked) matrix in registers: column j is scaled IN PLACE (the factor replaces the matrix
+    // entry by entry; the back substitution reads it from the same registers - no shared-memory round trip) and subtracted from
+    // the trailing entries; the forward substitution is fused.
     // Every entry sees the subtractions in the order k = 0, 1, ... of the inner-product form.
     static __device__ __forceinline__ void solve(const double* __restrict__ G, unsigned& P, const double (&c)[NA], double* __restrict__ Lt,
                                                  double (&s)[NA]) {
@@ -388,26 +389,25 @@ struct AlphaFixed {
             if (!ok) P &= ~(1u << j);
             v = ok ? v : 1.0;
             const double dj = rsqrt(v);
-            Lt[(j * (j + 1) / 2 + j) * kThreads] = dj;                  // the diagonal slot keeps 1 / L_jj
+            A[j * (j + 1) / 2 + j] = dj;                                // the diagonal slot keeps 1 / L_jj
             y[j] = ok ? y[j] * dj : 0.0;
-            double col[NA];
 #pragma unroll
             for (int i = j + 1; i < NA; ++i) {
-                col[i] = ok ? A[i * (i + 1) / 2 + j] * dj : 0.0;
-                Lt[(i * (i + 1) / 2 + j) * kThreads] = col[i];
-                y[i] -= col[i] * y[j];
+                const double c = ok ? A[i * (i + 1) / 2 + j] * dj : 0.0;
+                A[i * (i + 1) / 2 + j] = c;                             // the factor replaces the matrix entry by entry (registers)
+                y[i] -= c * y[j];
             }
 #pragma unroll
             for (int i = j + 1; i < NA; ++i)
 #pragma unroll
-                for (int k = j + 1; k <= i; ++k) A[i * (i + 1) / 2 + k] -= col[i] * col[k];
+                for (int k = j + 1; k <= i; ++k) A[i * (i + 1) / 2 + k] -= A[i * (i + 1) / 2 + j] * A[k * (k + 1) / 2 + j];
         }
 #pragma unroll
         for (int i = NA - 1; i >= 0; --i) {
             double v = y[i];
 #pragma unroll
-            for (int k = i + 1; k < NA; ++k) v -= Lt[(k * (k + 1) / 2 + i) * kThreads] * s[k];
-            s[i] = v * Lt[(i * (i + 1) / 2 + i) * kThreads];
+            for (int k = i + 1; k < NA; ++k) v -= A[k * (k + 1) / 2 + i] * s[k];
+            s[i] = v * A[i * (i + 1) / 2 + i];
         }
     }
 };
@@ -616,7 +616,7 @@ static size_t aa_alpha_fixed_region_doubles(int NA, int na, int d) {
     const int W = na + d, Wp4 = (W + 3) & ~3, S = Wp4 + 2, nstrip = Wp4 >> 2;
     int nE = 0;
     for (int ab = 0; ab < NA / 4; ++ab) nE += nstrip - ab;
-    const size_t tri = (size_t)NA * (NA + 1) / 2 * 128;                            // Cholesky factors
+    const size_t tri = NA > 12 ? (size_t)NA * (NA + 1) / 2 * 128 : 0;              // Cholesky factors (NA <= 12 keeps them in registers)
     const size_t xs = (size_t)128 * (d | 1);                                       // staged rows
     const size_t b = (size_t)128 * S + (size_t)4 * nE * 16;                        // [alphas | X] rows + the warps' partial blocks
     size_t r = tri > xs ? tri : xs;
