@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r7"
 txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "chrysalis_b200", "libchrysalis_b200.so")], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
-want = {"moran_lattice_kernel (TMA producer, default)": "moran_lattice_kernelILb1ELi2EE", "moran_lattice_kernel (CSR-fed)": "moran_lattice_kernelILb1ELi1EE", "moran_lattice_perm_kernel": "moran_lattice_perm_kernel",
-        "gram_tcgen05_kernel": "gram_tcgen05_kernel", "moran_tile_kernel (GEARY=0,SHIFT=1,MAPPED=0)": "moran_tile_kernelILb0ELb1ELb0E"}
+want = {"moran_lattice_kernel (TMA producer, default)": "moran_lattice_kernelILb1ELi2EE", "moran_lattice_kernel (CSR-fed)": "moran_lattice_kernelILb1ELi1EE", "moran_lattice_perm_kernel (bulk-copy producer, default)": "moran_lattice_perm_kernelILb1EE",
+        "gram_tcgen05_super_kernel (default)": "gram_tcgen05_super_kernel", "gram_tcgen05_kernel (variant 2)": "gram_tcgen05_kernelE", "moran_tile_kernel (GEARY=0,SHIFT=1,MAPPED=0)": "moran_tile_kernelILb0ELb1ELb0E"}
 pat = re.compile(r"/\*[0-9a-f]{4}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)")
 out = ["SASS excerpts of the hot kernels in chrysalis_b200/libchrysalis_b200.so (cuobjdump -sass, sm_100a; mnemonic histograms + the lines that",
        "show the async-copy / tensor / packed-fp32 paths).  Regenerate with scripts/sass_excerpt.py after a build.", ""]
