@@ -215,3 +215,41 @@ def test_gene_sharded_detect_svgs_world2(tmp_path):
     _run("_check_sharded_svgs", tmp_path)
     a, b = (np.load(os.path.join(tmp_path, f"I_rank{r}.npy")) for r in range(2))
     assert np.array_equal(a, b, equal_nan=True)                     # every rank holds the same full result
+
+
+def _check_gene_shard_names(rank, size, out_dir):
+    """A gene-sharded AnnData per rank (.uns['chr_gene_shard']): unique names take the hash exchange and the array path, a
+    name that occurs on both ranks falls back to the names and to the reference's pandas statements."""
+    from conftest import golden_csr
+    import chrysalis_b200 as ch
+    from chrysalis_b200 import core
+    from chrysalis_b200 import distributed as dd
+    z = np.load(os.path.join(GOLDEN, "svg_hex_k6.npz"), allow_pickle=False)
+    core.dv = _FakeDevice()
+    X = golden_csr(z)
+    g = X.shape[1]
+    lo, hi = dd.shard_range(g, rank, size)
+    for case in ("unique", "duplicated"):
+        names = [f"g{j}" for j in range(g)]
+        if case == "duplicated":
+            names[g - 1] = names[0]                                   # the same name on the first and on the last rank
+        ad = ch.AnnDataLite(X[:, lo:hi].tocsr(), obsm={"spatial": z["xy"]}, var_names=names[lo:hi], uns={"chr_gene_shard": True})
+        ch.detect_svgs(ad, neighbors=int(z["k"]), top_svg=int(z["top_svg"]), min_morans=float(z["min_morans"]))
+        np.save(os.path.join(out_dir, f"{case}_I_rank{rank}.npy"), ad.var["Moran's I"].to_numpy())
+        np.save(os.path.join(out_dir, f"{case}_sv_rank{rank}.npy"), ad.var["spatially_variable"].to_numpy())
+
+
+def test_gene_sharded_anndata_names_world2(tmp_path):
+    _run("_check_gene_shard_names", tmp_path)
+    z = np.load(os.path.join(GOLDEN, "svg_hex_k6.npz"), allow_pickle=False)
+    m = z["gene_mask"]
+    I = np.concatenate([np.load(os.path.join(tmp_path, f"unique_I_rank{r}.npy")) for r in range(2)])
+    sv = np.concatenate([np.load(os.path.join(tmp_path, f"unique_sv_rank{r}.npy")) for r in range(2)])
+    assert np.array_equal(np.isnan(I), ~m) and np.allclose(I[m], z["morans"][m], rtol=1e-5, atol=2e-7)
+    assert np.array_equal(sv, z["spatially_variable"])
+    # duplicated name: the statistics are the same; the fields follow the reference's index alignment (var_names_make_unique
+    # renames the second occurrence, so the row labelled with the duplicate name reads the first occurrence's value)
+    Id = np.concatenate([np.load(os.path.join(tmp_path, f"duplicated_I_rank{r}.npy")) for r in range(2)])
+    same = np.ones(len(I), dtype=bool)
+    same[[0, len(I) - 1]] = False
+    assert np.allclose(Id[same], I[same], rtol=1e-12, atol=0, equal_nan=True)
