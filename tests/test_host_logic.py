@@ -254,3 +254,40 @@ def test_compact_csr_round_trip_and_limits():
 def torch_dtype(name):
     import torch
     return getattr(torch, name)
+
+
+def test_lattice_layout_band_tables_against_brute_force():
+    """device.lattice_layout: per band the first / last occupied column, rows and row numbering - against a numpy loop; an empty
+    band in the middle, a short last band, and two spots on one node (no layout)."""
+    import torch
+    from chrysalis_b200 import device as dv
+
+    rng = np.random.default_rng(4)
+    W, H = 83, 3 * dv.LATTICE_BAND_ROWS + 17
+    keep = rng.random((H, W)) < 0.55
+    keep[dv.LATTICE_BAND_ROWS:2 * dv.LATTICE_BAND_ROWS] = False                    # band 1 is empty
+    keep[:, :5] &= rng.random((H, 5)) < 0.1
+    keep[0, 0] = keep[H - 1, W - 1] = True                                          # the grid spans (W, H)
+    iy, ix = np.nonzero(keep)
+    order = rng.permutation(len(ix))
+    ix, iy = ix[order], iy[order]
+    row_of_spot, n_rows, bands, chunks, shape = dv.lattice_layout(torch.from_numpy(ix), torch.from_numpy(iy))
+    assert shape == (W, H)
+    bands = bands.numpy()
+    exp_rows, row0 = np.empty(len(ix), dtype=np.int64), 0
+    for b in range(len(bands)):
+        inb = iy // dv.LATTICE_BAND_ROWS == b
+        bh = min(dv.LATTICE_BAND_ROWS, H - b * dv.LATTICE_BAND_ROWS)
+        if not inb.any():
+            assert tuple(bands[b]) == (row0, 0, 0, bh)
+            continue
+        x0, x1 = ix[inb].min(), ix[inb].max()
+        assert tuple(bands[b]) == (row0, x0, x1 - x0 + 1, bh)
+        exp_rows[inb] = row0 + (ix[inb] - x0) * bh + (iy[inb] - b * dv.LATTICE_BAND_ROWS)
+        row0 += (x1 - x0 + 1) * bh
+    assert n_rows == row0 and np.array_equal(row_of_spot.numpy(), exp_rows)
+    ch = chunks.numpy()
+    assert all(ch[ch[:, 0] == b, 2].sum() == bands[b, 2] for b in range(len(bands))) and (ch[:, 2] <= dv.LATTICE_CHUNK_COLS).all()
+    # two spots on one node
+    out = dv.lattice_layout(torch.from_numpy(np.append(ix, ix[0])), torch.from_numpy(np.append(iy, iy[0])))
+    assert out[0] is None
